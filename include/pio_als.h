@@ -1,0 +1,182 @@
+/*
+ * pio_als.h -- C ABI of the B200-native ALS hot path for PredictionIO engine templates.
+ *
+ * This is the drop-in boundary: exactly what a JNI shim in a `native-als` Scala module
+ * binds in place of the Spark-MLlib calls the templates make today (INTEGRATION.md shows
+ * the binding).  Plain C: opaque handle, plain pointers and sizes, int status returns
+ * (0 = OK, <0 = error; text via pio_als_last_error).  The caller owns every host buffer;
+ * the library owns all device memory behind the handle.  One handle = one training job /
+ * one trained model; a handle is not thread-safe for mutation, but pio_als_recommend /
+ * pio_als_similar on a trained handle serialise internally and may be called from
+ * several threads (the reference calls predict from concurrent HTTP threads,
+ * core/src/main/scala/org/apache/predictionio/workflow/CreateServer.scala:508-510).
+ *
+ * There is NO CPU fallback: every entry point that computes fails with
+ * PIO_ALS_ERR_CUDA when no sm_100 device / CUDA runtime is usable.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   pio_als_create + pio_als_set_ratings_coo + pio_als_run + pio_als_get_factors  (or the
+ *   one-shot pio_als_train) replace
+ *     new ALS().setRank(..)...run(mllibRatings)
+ *       examples/scala-parallel-recommendation/blacklist-items/src/main/scala/ALSAlgorithm.scala:76-86
+ *     ALS.train(ratings, rank, iterations, lambda, -1, seed)
+ *       examples/scala-parallel-ecommercerecommendation/train-with-rate-event/src/main/scala/ECommAlgorithm.scala:116-122
+ *     ALS.trainImplicit(ratings, rank, iterations, lambda, -1, 1.0, seed)
+ *       examples/scala-parallel-similarproduct/multi-events-multi-algos/src/main/scala/ALSAlgorithm.scala:121-128
+ *   pio_als_recommend replaces recommendProductsWithFilter / recommend
+ *       examples/scala-parallel-recommendation/blacklist-items/src/main/scala/ALSModel.scala:44-60
+ *     and the cartesian batchPredict
+ *       examples/scala-parallel-recommendation/blacklist-items/src/main/scala/ALSAlgorithm.scala:117-158
+ *   pio_als_similar replaces the cosine scan + getTopN
+ *       examples/scala-parallel-similarproduct/multi-events-multi-algos/src/main/scala/ALSAlgorithm.scala:138-234
+ *   pio_als_save / pio_als_load replace ALSModel.save / ALSModel.apply
+ *       examples/scala-parallel-recommendation/blacklist-items/src/main/scala/ALSModel.scala:63-100
+ *   pio_nb_train / pio_nb_predict replace NaiveBayes.train / model.predict
+ *       examples/scala-parallel-classification/add-algorithm/src/main/scala/NaiveBayesAlgorithm.scala:41-57
+ */
+#ifndef PIO_ALS_H_
+#define PIO_ALS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PIO_API __attribute__((visibility("default")))
+#else
+#define PIO_API
+#endif
+
+#define PIO_ALS_ABI_VERSION 1
+
+/* status codes */
+#define PIO_ALS_OK 0
+#define PIO_ALS_ERR_ARG (-1)      /* bad argument (the templates' require(...) failures) */
+#define PIO_ALS_ERR_CUDA (-2)     /* CUDA runtime / no usable device */
+#define PIO_ALS_ERR_STATE (-3)    /* call order (e.g. run before set_ratings) */
+#define PIO_ALS_ERR_NUMERIC (-4)  /* a normal equation was not positive definite (MLlib: dppsv info != 0) */
+#define PIO_ALS_ERR_IO (-5)
+#define PIO_ALS_ERR_COMM (-6)     /* NCCL */
+
+/* how repeated (user,item) pairs are treated by pio_als_set_ratings_coo */
+#define PIO_ALS_DEDUP_NONE 0      /* recommendation template: every event is its own rating (ALSAlgorithm.scala:62-65) */
+#define PIO_ALS_DEDUP_SUM 1       /* similarproduct: reduceByKey(_ + _) (multi-events ALSAlgorithm.scala:106) */
+#define PIO_ALS_DEDUP_KEEP_LAST 2 /* ecommerce: latest timestamp wins (ECommAlgorithm.scala:189-197) */
+
+#define PIO_ALS_INIT_CALLER 0     /* pio_als_set_init supplies initial factors */
+#define PIO_ALS_INIT_HASH 1       /* unit-norm Gaussian rows from the counter hash (synth.py synth_init_factors) */
+
+typedef struct pio_als_handle pio_als_handle;
+
+typedef struct pio_als_config {
+  int32_t abi_version;    /* PIO_ALS_ABI_VERSION */
+  int32_t rank;           /* ALSAlgorithmParams.rank, 1..128 */
+  int32_t implicit_prefs; /* setImplicitPrefs */
+  int32_t n_users;        /* size of userStringIntMap */
+  int32_t n_items;        /* size of itemStringIntMap */
+  int32_t device;         /* CUDA device ordinal for this process */
+  int32_t world_size;     /* number of cooperating processes (1 GPU each); 1 = single GPU */
+  int32_t world_rank;
+  int32_t init_mode;      /* PIO_ALS_INIT_* */
+  int32_t reserved0;
+  double lambda;          /* setLambda */
+  double alpha;           /* setAlpha (implicit only) */
+  int64_t seed;           /* setSeed; used by PIO_ALS_INIT_HASH */
+  uint8_t nccl_id[128];   /* world_size > 1: the same ncclUniqueId on every rank (pio_als_nccl_unique_id on rank 0) */
+} pio_als_config;
+
+typedef struct pio_als_stats {
+  int64_t nnz;              /* ratings after dedup (global) */
+  int64_t kernel_launches;  /* kernels of this library launched on behalf of this handle */
+  int64_t solve_launches;   /* of which half-step solve kernels */
+  double last_run_ms;       /* device time of the last pio_als_run (CUDA events) */
+  double last_solve_ms;     /* device time inside solve kernels during the last pio_als_run */
+  double last_gram_ms;      /* ... inside YtY kernels */
+  double last_comm_ms;      /* ... inside all-gathers */
+  double last_ingest_ms;    /* device time of the last set_ratings (H2D + CSR build) */
+  int32_t n_users_active;   /* users owning a factor */
+  int32_t n_items_active;
+  int32_t sm_count;
+  int32_t reserved;
+} pio_als_stats;
+
+PIO_API int pio_als_abi_version(void);
+/* number of visible sm_100 devices, or PIO_ALS_ERR_CUDA */
+PIO_API int pio_als_device_count(void);
+PIO_API int pio_als_nccl_unique_id(uint8_t out_id[128]);
+
+PIO_API int pio_als_create(const pio_als_config* cfg, pio_als_handle** out);
+PIO_API void pio_als_destroy(pio_als_handle* h);
+/* h may be NULL: returns the last error of a failed pio_als_create / pio_als_load on this thread */
+PIO_API const char* pio_als_last_error(const pio_als_handle* h);
+
+/* Ratings as COO triplets in HOST memory (indices from BiMap.stringInt, data/.../storage/BiMap.scala:116-128).
+ * ts (int64, nullable) is only read for PIO_ALS_DEDUP_KEEP_LAST (NULL = input order is time order).
+ * world_size > 1: every rank passes the same full COO; each keeps the rows it owns. nnz == 0 is
+ * PIO_ALS_ERR_ARG (the templates' require(!ratings.isEmpty)). */
+PIO_API int pio_als_set_ratings_coo(pio_als_handle* h, const int32_t* user, const int32_t* item,
+                                    const float* rating, int64_t nnz, int dedup_mode,
+                                    const int64_t* ts);
+/* Same, the three arrays already resident in device memory of cfg.device. */
+PIO_API int pio_als_set_ratings_coo_device(pio_als_handle* h, const int32_t* d_user,
+                                           const int32_t* d_item, const float* d_rating,
+                                           int64_t nnz, int dedup_mode, const int64_t* d_ts);
+/* Initial factors, HOST, row-major n_users x rank / n_items x rank (item_factors may be NULL:
+ * MLlib overwrites item factors in the first half-step). Rows that own no rating are zeroed. */
+PIO_API int pio_als_set_init(pio_als_handle* h, const float* user_factors, const float* item_factors);
+/* n_iters ALS iterations: each = item half-step (from user factors) then user half-step. May be
+ * called repeatedly. */
+PIO_API int pio_als_run(pio_als_handle* h, int n_iters);
+/* Factors back to HOST. user_has/item_has (nullable): 1 if the row owns a factor (occurs in the
+ * ratings), else 0 and the row is all zeros (MLlib emits no factor for it). */
+PIO_API int pio_als_get_factors(pio_als_handle* h, float* user_out, float* item_out,
+                                uint8_t* user_has, uint8_t* item_has);
+/* One-shot: create-less convenience used by the JNI shim for ALS.train / ALS.trainImplicit:
+ * set_ratings + (init) + run(iters) + get_factors on an existing handle. */
+PIO_API int pio_als_train(pio_als_handle* h, const int32_t* user, const int32_t* item,
+                          const float* rating, int64_t nnz, int dedup_mode, const int64_t* ts,
+                          const float* user_init, const float* item_init, int n_iters,
+                          float* user_out, float* item_out, uint8_t* user_has, uint8_t* item_has);
+
+/* Top-k scoring on a trained (or loaded) handle; HOST buffers.
+ * recommend: for each users[q]: score_i = <x_u, y_i> over items that own a factor and have
+ *   item_mask[i] == 0 (nullable = no filter); out_items/out_scores are n x topk, best first,
+ *   padded with -1 / 0; out_count[q] (nullable) = number of valid entries (0 for an unknown user).
+ *   Ties: smaller item index first. */
+PIO_API int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk,
+                              const uint8_t* item_mask, int32_t* out_items, float* out_scores,
+                              int32_t* out_count);
+/* similar: score_i = sum_q cosine(y_q, y_i) over query items that own a factor; candidates are
+ *   items owning a factor, not in the query, item_mask[i]==0, score > 0. */
+PIO_API int pio_als_similar(pio_als_handle* h, const int32_t* query_items, int nq, int topk,
+                            const uint8_t* item_mask, int32_t* out_items, float* out_scores,
+                            int32_t* out_count);
+
+/* Model persistence (one little-endian file: header, has flags, fp32 factors). */
+PIO_API int pio_als_save(pio_als_handle* h, const char* path);
+PIO_API int pio_als_load(const char* path, int device, pio_als_handle** out);
+
+PIO_API int pio_als_get_stats(const pio_als_handle* h, pio_als_stats* out);
+
+/* Device pointers to the library-owned rating generator output, for benchmarks that must start
+ * with inputs resident in HBM: fills d_user/d_item/d_rating (device, nnz each) with the
+ * synthetic events of SURVEY 8(d) (bit-identical to synth.py). */
+PIO_API int pio_als_synth_ratings_device(int device, int32_t n_users, int32_t n_items, int64_t nnz,
+                                         int64_t seed, int implicit, int64_t start,
+                                         int32_t* d_user, int32_t* d_item, float* d_rating);
+
+/* MLlib multinomial NaiveBayes (classification template). HOST buffers.
+ * label: class index 0..n_class-1; x: n x n_feat, non-negative. pi: n_class, theta: n_class x n_feat
+ * (fp64 log-probabilities, as MLlib's NaiveBayesModel.pi/theta). */
+PIO_API int pio_nb_train(int device, const int32_t* label, const float* x, int64_t n, int n_feat,
+                         int n_class, double lambda, double* pi, double* theta);
+PIO_API int pio_nb_predict(int device, const float* x, int64_t n, int n_feat, int n_class,
+                           const double* pi, const double* theta, int32_t* out_label);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIO_ALS_H_ */

@@ -1,0 +1,618 @@
+// als_kernels.cuh -- the ALS half-iteration on sm_100a.
+//
+// Replaces MLlib's `computeFactors` (called through als.run at
+// examples/scala-parallel-recommendation/blacklist-items/src/main/scala/ALSAlgorithm.scala:86):
+// for every destination row j with rated set Omega_j
+//     explicit:  A = sum y y^T + lambda n I,                 b = sum r y
+//     implicit:  A = YtY + sum c1 y y^T + lambda n+ I,       b = sum_{r>0} (1+c1) y,  c1 = alpha |r|
+// solve A x = b by Cholesky, store x (fp32).
+//
+// Design (one kernel does gather -> Gramian -> Cholesky -> factor row, nothing round-trips HBM):
+//  * rows are processed in degree-descending order (the ingest renumbers rows that way), so the
+//    NG rows of one CTA batch have near-equal length;
+//  * the upper triangle of the KPxKP Gramian is tiled in TBxTB register blocks, one block per
+//    thread, G = NB(NB+1)/2 threads ("group") per row; a CTA runs NG groups = NG rows at once
+//    (LIGHT) or NG slices of one very long row (HEAVY, reduced through shared memory);
+//  * gathered source rows are staged by cp.async (16 B per thread) into a 3-deep shared-memory
+//    ring; a short in-place pass scales them by sqrt(c1) (implicit) and accumulates b;
+//  * each warp then factorises one row's matrix with the rows held in registers
+//    (lane l owns rows l and N-1-l), pivots broadcast by shuffle, columns through shared memory;
+//    forward substitution is fused into the factorisation, back substitution reads L from smem.
+// FP32 throughout the Gramian (the FMA pipe is the binding roofline at rank >= 32);
+// YtY is accumulated in fp64 by gram_partial_kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pio {
+
+struct SolveParams {
+  const long long* ptr;  // local CSR row pointers, offsets into idx/val
+  const int* idx;        // internal ids of source rows
+  const float* val;      // ratings
+  const float* src;      // source factor matrix, row stride KP (zero padded)
+  float* dst;            // destination factor matrix (full replica), row stride KP
+  const float* yty;      // KP x KP (implicit only)
+  const float* nreg;     // per local row: n of the ridge term lambda * n
+  int* fail;             // incremented once per row whose matrix was not positive definite
+  float lambda;
+  float alpha;
+  int k;                 // true rank (<= KP)
+  int row_begin;         // local rows [row_begin, row_end) are covered by this launch
+  int row_end;
+  int dst_row_offset;    // internal id of local row 0
+};
+
+template <int KP_, int TB_, int NG_, int CH_>
+struct SolveCfg {
+  static constexpr int KP = KP_, TB = TB_, NB = KP_ / TB_, G = NB * (NB + 1) / 2;
+  static constexpr int NG = NG_, CH = CH_;
+  static constexpr int NT = ((NG * G + 31) / 32) * 32;
+  static constexpr int NW = NT / 32;
+  static constexpr int ROWS = NG * CH;          // gathered rows per stage
+  static constexpr int F4ROW = KP / 4;
+  static constexpr int STAGE = ROWS * KP;       // floats
+  static constexpr int STAGE_F4 = ROWS * F4ROW;
+  static constexpr int NF = (STAGE_F4 + NT - 1) / NT;
+  static constexpr int NSTAGE = 3;
+  static constexpr int BLK = TB * TB + 8;       // padded block stride inside a slot (floats)
+  static constexpr int SLOT = G * BLK;
+  static constexpr bool WARP_CHOL = KP <= 64;
+  static constexpr int LM = WARP_CHOL ? 0 : KP * (KP + 1);  // cooperative Cholesky scratch
+
+  __host__ __device__ static constexpr int region0(bool heavy) {
+    return heavy ? (NSTAGE + 1) * STAGE + NG * SLOT
+                 : ((NSTAGE + 1) * STAGE > NG * SLOT ? (NSTAGE + 1) * STAGE : NG * SLOT);
+  }
+  __host__ __device__ static constexpr size_t smem_bytes(bool heavy) {
+    return sizeof(float) * (size_t)(region0(heavy) + NG * KP + NW * 2 * KP + NW * KP +
+                                    NSTAGE * ROWS + LM) +
+           sizeof(long long) * 2 * NG + sizeof(int) * NG + 16;
+  }
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// position (in float4 units) of original float4 column-group cg inside a staged row.
+// TB == 8: the two halves of every 8-wide block are split so that the NB first halves are
+// contiguous (bank-conflict-free LDS.128 for lanes that differ in the block index).
+template <int TB, int NB>
+__device__ __forceinline__ int f4slot(int cg) {
+  if (TB == 8) return (cg & 1) * NB + (cg >> 1);
+  return cg;
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp Cholesky + solve for N <= 64 (N = KP). Matrix comes from `slot` (upper-triangular TBxTB
+// blocks, block (bi,bj) at ((bi*NB - bi*(bi-1)/2) + bj - bi) * BLK, element [a][b] at a*TB+b).
+// ------------------------------------------------------------------------------------------
+template <int N, int TB, int BLK, bool IMPLICIT>
+__device__ __forceinline__ void chol_solve_warp(float* slot, const float* bvec, const float* yty,
+                                                float ridge, int k, float* colbuf, float* dinv,
+                                                float* dst_row, int* fail) {
+  constexpr int H = N / 2;
+  constexpr int NB = N / TB;
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < H;
+  const int l = act ? lane : 0;
+  const int rA = l, rB = N - 1 - l;
+  float ra[H], rb[N];
+  {
+    const int ibA = rA / TB, bA = rA % TB, ibB = rB / TB, bB = rB % TB;
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int cb = c / TB, a = c % TB;
+      const int base = (cb * NB - cb * (cb - 1) / 2 - cb) * BLK + a * TB;
+      if (c < H) {
+        float v = 0.f;
+        if (c <= rA) {
+          v = slot[base + ibA * BLK + bA];
+          if (IMPLICIT) v += yty[rA * N + c];
+          if (c == rA) v += ridge + (rA >= k ? 1.f : 0.f);
+        }
+        ra[c] = v;
+      }
+      float v = 0.f;
+      if (c <= rB) {
+        v = slot[base + ibB * BLK + bB];
+        if (IMPLICIT) v += yty[rB * N + c];
+        if (c == rB) v += ridge + (rB >= k ? 1.f : 0.f);
+      }
+      rb[c] = v;
+    }
+  }
+  float bAv = bvec[rA], bBv = bvec[rB];
+  float yA = 0.f, yB = 0.f;
+  bool bad = false;
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    float* cb_ = colbuf + (j & 1) * N;
+    const float d = (j < H) ? __shfl_sync(0xffffffffu, ra[j < H ? j : 0], j < H ? j : 0)
+                            : __shfl_sync(0xffffffffu, rb[j], N - 1 - j);
+    const float bj = (j < H) ? __shfl_sync(0xffffffffu, bAv, j < H ? j : 0)
+                             : __shfl_sync(0xffffffffu, bBv, N - 1 - j);
+    float dd = d;
+    if (!(dd > 0.f)) { bad = true; dd = 1.f; }
+    float inv = rsqrtf(dd);
+    inv = inv * (1.5f - 0.5f * dd * inv * inv);
+    const float yj = bj * inv;
+    float la = 0.f;
+    if (j < H) {
+      la = ra[j < H ? j : 0] * inv;
+      ra[j < H ? j : 0] = la;
+    }
+    const float lb = rb[j] * inv;
+    rb[j] = lb;
+    if (act) {
+      if (j < H) cb_[rA] = la;
+      cb_[rB] = lb;
+    }
+    if (lane == 0) dinv[j] = inv;
+    if (j < H && rA == j) yA = yj;
+    if (rB == j) yB = yj;
+    bAv -= la * yj;
+    bBv -= lb * yj;
+    __syncwarp();
+#pragma unroll
+    for (int c = j + 1; c < N; ++c) {
+      const float x = cb_[c];
+      rb[c] -= lb * x;
+      if (c < H) ra[c < H ? c : 0] -= la * x;
+    }
+  }
+  // L rows -> shared (packed lower, row i at i(i+1)/2), reusing the slot
+  __syncwarp();
+  if (act) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      if (c < H && c <= rA) slot[rA * (rA + 1) / 2 + c] = ra[c < H ? c : 0];
+      if (c <= rB) slot[rB * (rB + 1) / 2 + c] = rb[c];
+    }
+  }
+  __syncwarp();
+  float xA = 0.f, xB = 0.f;
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    const float yi = (i < H) ? __shfl_sync(0xffffffffu, yA, i < H ? i : 0)
+                             : __shfl_sync(0xffffffffu, yB, N - 1 - i);
+    const float xi = yi * dinv[i];
+    if (rA == i) xA = xi;
+    if (rB == i) xB = xi;
+    const float* Li = slot + i * (i + 1) / 2;
+    if (act) {
+      if (rA < i) yA -= Li[rA] * xi;
+      if (rB < i) yB -= Li[rB] * xi;
+    }
+  }
+  if (act) {
+    dst_row[rA] = xA;
+    dst_row[rB] = xB;
+  }
+  if (bad && lane == 0) atomicAdd(fail, 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// Cooperative Cholesky + solve for N > 64 (rank 65..128): whole CTA, matrix unpacked to smem.
+// Parity path for the rank-128 configuration; not yet tuned.
+// ------------------------------------------------------------------------------------------
+template <int N, int TB, int BLK, bool IMPLICIT, int NT>
+__device__ void chol_solve_cta(const float* slot, const float* bvec, const float* yty, float ridge,
+                               int k, float* Lm /* N x (N+1) */, float* dst_row, int* fail) {
+  constexpr int NB = N / TB;
+  constexpr int LD = N + 1;
+  const int tid = threadIdx.x;
+  __shared__ float s_inv;
+  __shared__ int s_bad;
+  if (tid == 0) s_bad = 0;
+  for (int o = tid; o < N * N; o += NT) {
+    const int i = o / N, c = o % N;
+    if (c <= i) {
+      const int cb = c / TB, a = c % TB, ib = i / TB, b = i % TB;
+      float v = slot[(cb * NB - cb * (cb - 1) / 2 + ib - cb) * BLK + a * TB + b];
+      if (IMPLICIT) v += yty[i * N + c];
+      if (c == i) v += ridge + (i >= k ? 1.f : 0.f);
+      Lm[i * LD + c] = v;
+    }
+  }
+  float* y = Lm + N;  // column N of every row is free: y[i] at Lm[i*LD + N]
+  for (int i = tid; i < N; i += NT) Lm[i * LD + N] = bvec[i];
+  __syncthreads();
+  for (int j = 0; j < N; ++j) {
+    if (tid == 0) {
+      float d = Lm[j * LD + j];
+      if (!(d > 0.f)) { s_bad = 1; d = 1.f; }
+      float inv = rsqrtf(d);
+      inv = inv * (1.5f - 0.5f * d * inv * inv);
+      s_inv = inv;
+      Lm[j * LD + j] = d * inv;
+    }
+    __syncthreads();
+    const float inv = s_inv;
+    for (int i = j + 1 + tid; i < N; i += NT) Lm[i * LD + j] *= inv;
+    __syncthreads();
+    const int m = N - 1 - j;
+    for (int o = tid; o < m * m; o += NT) {
+      const int i = j + 1 + o / m, c = j + 1 + o % m;
+      if (c <= i) Lm[i * LD + c] -= Lm[i * LD + j] * Lm[c * LD + j];
+    }
+    __syncthreads();
+  }
+  (void)y;
+  if (tid < 32) {  // triangular solves by one warp (lanes stride the rows)
+    const int lane = tid;
+    for (int j = 0; j < N; ++j) {  // forward
+      float yj = 0.f;
+      if (lane == 0) {
+        yj = Lm[j * LD + N] / Lm[j * LD + j];
+        Lm[j * LD + N] = yj;
+      }
+      yj = __shfl_sync(0xffffffffu, yj, 0);
+      for (int i = j + 1 + lane; i < N; i += 32) Lm[i * LD + N] -= Lm[i * LD + j] * yj;
+      __syncwarp();
+    }
+    for (int i = N - 1; i >= 0; --i) {  // backward
+      float xi = 0.f;
+      if (lane == 0) {
+        xi = Lm[i * LD + N] / Lm[i * LD + i];
+        Lm[i * LD + N] = xi;
+      }
+      xi = __shfl_sync(0xffffffffu, xi, 0);
+      for (int j = lane; j < i; j += 32) Lm[j * LD + N] -= Lm[i * LD + j] * xi;
+      __syncwarp();
+    }
+    for (int i = lane; i < N; i += 32) dst_row[i] = Lm[i * LD + N];
+    if (lane == 0 && s_bad) atomicAdd(fail, 1);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// The half-step kernel.
+// ------------------------------------------------------------------------------------------
+template <class Cfg, bool IMPLICIT, bool HEAVY>
+__global__ void __launch_bounds__(Cfg::NT, (HEAVY || !Cfg::WARP_CHOL) ? 1 : 2)
+als_solve_kernel(const SolveParams p) {
+  constexpr int KP = Cfg::KP, TB = Cfg::TB, NB = Cfg::NB, G = Cfg::G, NG = Cfg::NG, CH = Cfg::CH;
+  constexpr int NT = Cfg::NT, NW = Cfg::NW, ROWS = Cfg::ROWS, F4ROW = Cfg::F4ROW;
+  constexpr int STAGE = Cfg::STAGE, STAGE_F4 = Cfg::STAGE_F4, NF = Cfg::NF, NSTAGE = Cfg::NSTAGE;
+  constexpr int BLK = Cfg::BLK, SLOT = Cfg::SLOT;
+  constexpr int FLUSH = 64;  // HEAVY: chunks between register->smem flushes (two-level summation)
+
+  extern __shared__ __align__(16) float smem[];
+  float* stage = smem;
+  float* bpart = stage + NSTAGE * STAGE;
+  float* slots = HEAVY ? bpart + STAGE : smem;
+  float* bvec = smem + Cfg::region0(HEAVY);
+  float* colbuf = bvec + NG * KP;
+  float* dinvb = colbuf + NW * 2 * KP;
+  float* mval = dinvb + NW * KP;
+  float* lm = mval + NSTAGE * ROWS;
+  long long* segb = reinterpret_cast<long long*>(
+      (reinterpret_cast<uintptr_t>(lm + Cfg::LM) + 15) & ~uintptr_t(15));
+  long long* sege = segb + NG;
+  int* srow = reinterpret_cast<int*>(sege + NG);
+
+  const int tid = threadIdx.x;
+  const int g = tid / G;                 // group of this thread (>= NG: staging helper only)
+  const int bid = tid - g * G;           // block id inside the triangle
+  const bool worker = g < NG;
+  int bi = 0, bj = 0;
+  {
+    int t = bid;
+    while (t >= NB - bi) { t -= NB - bi; ++bi; }
+    bj = bi + t;
+  }
+
+  if (tid < NG) {
+    if (!HEAVY) {
+      const int r = p.row_begin + blockIdx.x * NG + tid;
+      if (r < p.row_end) {
+        segb[tid] = p.ptr[r];
+        sege[tid] = p.ptr[r + 1];
+        srow[tid] = r;
+      } else {
+        segb[tid] = 0;
+        sege[tid] = 0;
+        srow[tid] = -1;
+      }
+    } else {
+      const int r = p.row_begin + blockIdx.x;
+      const long long b = p.ptr[r], e = p.ptr[r + 1];
+      const long long d = e - b;
+      long long L = (d + NG - 1) / NG;
+      L = (L + CH - 1) / CH * CH;
+      long long sb = b + (long long)tid * L;
+      if (sb > e) sb = e;
+      long long se = sb + L;
+      if (se > e) se = e;
+      segb[tid] = sb;
+      sege[tid] = se;
+      srow[tid] = r;
+    }
+  }
+  // zero the b partials (and the slots when they do not alias the ring)
+  for (int o = tid; o < STAGE; o += NT) bpart[o] = 0.f;
+  if (HEAVY)
+    for (int o = tid; o < NG * SLOT; o += NT) slots[o] = 0.f;
+  __syncthreads();
+
+  long long maxlen = 0;
+#pragma unroll 1
+  for (int q = 0; q < NG; ++q) {
+    const long long len = sege[q] - segb[q];
+    maxlen = len > maxlen ? len : maxlen;
+  }
+  const int nchunks = (int)((maxlen + CH - 1) / CH);
+  const long long mylen = worker ? sege[g] - segb[g] : 0;
+
+  // ---- staging helpers -----------------------------------------------------------------
+  int nidx[NF];
+  float nval[NF];
+  auto prefetch_meta = [&](int c) {
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+      const int f = tid + j * NT;
+      nidx[j] = -1;
+      nval[j] = 0.f;
+      if (f < STAGE_F4 && c < nchunks) {
+        const int q = f / F4ROW;
+        const int gg = q / CH, i = q % CH;
+        const long long e = segb[gg] + (long long)c * CH + i;
+        if (e < sege[gg]) {
+          nidx[j] = __ldg(p.idx + e);
+          nval[j] = __ldg(p.val + e);
+        }
+      }
+    }
+  };
+  auto issue = [&](int c) {  // uses nidx/nval prefetched for chunk c
+    float* sbuf = stage + (c % NSTAGE) * STAGE;
+    float* mv = mval + (c % NSTAGE) * ROWS;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+      const int f = tid + j * NT;
+      if (f < STAGE_F4 && c < nchunks) {
+        const int q = f / F4ROW, cg = f % F4ROW;
+        float4* d4 = reinterpret_cast<float4*>(sbuf) + q * F4ROW + f4slot<TB, NB>(cg);
+        if (nidx[j] >= 0) {
+          cp_async16(d4, p.src + (size_t)nidx[j] * KP + cg * 4);
+        } else {
+          *d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (cg == 0) mv[q] = nval[j];
+      }
+    }
+    cp_async_commit();
+  };
+
+  float acc[TB][TB];
+#pragma unroll
+  for (int a = 0; a < TB; ++a)
+#pragma unroll
+    for (int b = 0; b < TB; ++b) acc[a][b] = 0.f;
+
+  float* myslot = slots + (worker ? g : 0) * SLOT + bid * BLK;
+
+  prefetch_meta(0);
+  issue(0);
+  prefetch_meta(1);
+  issue(1);
+  prefetch_meta(2);
+
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<1>();
+    __syncthreads();
+    issue(c + 2);
+    prefetch_meta(c + 3);
+    float* sbuf = stage + (c % NSTAGE) * STAGE;
+    const float* mv = mval + (c % NSTAGE) * ROWS;
+    // b accumulation (+ sqrt(c1) scaling in place for implicit feedback)
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+      const int f = tid + j * NT;
+      if (f < STAGE_F4) {
+        const int q = f / F4ROW, cg = f % F4ROW;
+        const int o4 = q * F4ROW + f4slot<TB, NB>(cg);
+        const float r = mv[q];
+        float4 y = reinterpret_cast<float4*>(sbuf)[o4];
+        float wb, sc;
+        if (IMPLICIT) {
+          const float c1 = p.alpha * fabsf(r);
+          wb = r > 0.f ? 1.f + c1 : 0.f;
+          sc = sqrtf(c1);
+        } else {
+          wb = r;
+          sc = 1.f;
+        }
+        float4 bp = reinterpret_cast<float4*>(bpart)[o4];
+        bp.x = fmaf(wb, y.x, bp.x);
+        bp.y = fmaf(wb, y.y, bp.y);
+        bp.z = fmaf(wb, y.z, bp.z);
+        bp.w = fmaf(wb, y.w, bp.w);
+        reinterpret_cast<float4*>(bpart)[o4] = bp;
+        if (IMPLICIT) {
+          y.x *= sc; y.y *= sc; y.z *= sc; y.w *= sc;
+          reinterpret_cast<float4*>(sbuf)[o4] = y;
+        }
+      }
+    }
+    if (IMPLICIT) __syncthreads();
+    if (worker) {
+      long long rem = mylen - (long long)c * CH;
+      const int cnt = rem <= 0 ? 0 : (rem < CH ? (int)rem : CH);
+      const float4* rowp = reinterpret_cast<const float4*>(sbuf + (g * CH) * KP);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        if (i < cnt) {
+          const float4* rp = rowp + i * F4ROW;
+          float P[TB], Q[TB];
+          if (TB == 8) {
+            const float4 p0 = rp[bi], p1 = rp[NB + bi], q0 = rp[bj], q1 = rp[NB + bj];
+            P[0] = p0.x; P[1] = p0.y; P[2] = p0.z; P[3] = p0.w;
+            P[4 % TB] = p1.x; P[5 % TB] = p1.y; P[6 % TB] = p1.z; P[7 % TB] = p1.w;
+            Q[0] = q0.x; Q[1] = q0.y; Q[2] = q0.z; Q[3] = q0.w;
+            Q[4 % TB] = q1.x; Q[5 % TB] = q1.y; Q[6 % TB] = q1.z; Q[7 % TB] = q1.w;
+          } else {
+            const float4 p0 = rp[bi], q0 = rp[bj];
+            P[0] = p0.x; P[1] = p0.y; P[2] = p0.z; P[3] = p0.w;
+            Q[0] = q0.x; Q[1] = q0.y; Q[2] = q0.z; Q[3] = q0.w;
+          }
+#pragma unroll
+          for (int a = 0; a < TB; ++a)
+#pragma unroll
+            for (int b = 0; b < TB; ++b) acc[a][b] = fmaf(P[a], Q[b], acc[a][b]);
+        }
+      }
+      if (HEAVY && ((c + 1) % FLUSH == 0)) {
+#pragma unroll
+        for (int a = 0; a < TB; ++a)
+#pragma unroll
+          for (int b = 0; b < TB; ++b) {
+            myslot[a * TB + b] += acc[a][b];
+            acc[a][b] = 0.f;
+          }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- b: fixed-order reduction of the per-staged-row partials ----------------------------
+  if (!HEAVY) {
+    for (int o = tid; o < NG * KP; o += NT) {
+      const int gg = o / KP, col = o % KP;
+      const int pos = f4slot<TB, NB>(col >> 2) * 4 + (col & 3);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) s += bpart[(gg * CH + i) * KP + pos];
+      bvec[o] = s;
+    }
+  } else {
+    for (int col = tid; col < KP; col += NT) {
+      const int pos = f4slot<TB, NB>(col >> 2) * 4 + (col & 3);
+      float s = 0.f;
+      for (int q = 0; q < ROWS; ++q) s += bpart[q * KP + pos];
+      bvec[col] = s;
+    }
+  }
+  __syncthreads();  // ring + bpart are dead from here on (LIGHT: slots alias them)
+  if (worker) {
+#pragma unroll
+    for (int a = 0; a < TB; ++a)
+#pragma unroll
+      for (int b = 0; b < TB; ++b) {
+        if (HEAVY) myslot[a * TB + b] += acc[a][b];
+        else myslot[a * TB + b] = acc[a][b];
+      }
+  }
+  __syncthreads();
+  if (HEAVY) {
+    for (int o = tid; o < SLOT; o += NT) {
+      float s = slots[o];
+#pragma unroll 1
+      for (int q = 1; q < NG; ++q) s += slots[q * SLOT + o];
+      slots[o] = s;
+    }
+    __syncthreads();
+  }
+
+  // ---- Cholesky + triangular solves ---------------------------------------------------------
+  constexpr int NMAT = HEAVY ? 1 : NG;
+  if (Cfg::WARP_CHOL) {
+    const int w = tid >> 5;
+    for (int m = w; m < NMAT; m += NW) {
+      const int r = srow[m];
+      if (r < 0) continue;
+      if (p.ptr[r + 1] == p.ptr[r]) continue;  // no ratings: MLlib emits no factor
+      const float ridge = p.lambda * p.nreg[r];
+      chol_solve_warp<Cfg::WARP_CHOL ? KP : 16, TB, BLK, IMPLICIT>(
+          slots + m * SLOT, bvec + m * KP, p.yty, ridge, p.k, colbuf + w * 2 * KP, dinvb + w * KP,
+          p.dst + (size_t)(p.dst_row_offset + r) * KP, p.fail);
+    }
+  } else {
+    for (int m = 0; m < NMAT; ++m) {
+      const int r = srow[m];
+      if (r < 0) continue;
+      if (p.ptr[r + 1] == p.ptr[r]) continue;
+      const float ridge = p.lambda * p.nreg[r];
+      chol_solve_cta<KP, TB, BLK, IMPLICIT, NT>(slots + m * SLOT, bvec + m * KP, p.yty, ridge, p.k,
+                                                 lm, p.dst + (size_t)(p.dst_row_offset + r) * KP,
+                                                 p.fail);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// YtY (implicit feedback): fp64 accumulation of X^T X over all rows of a zero-padded factor
+// matrix; per-CTA partials reduced in fixed order (deterministic).
+// ------------------------------------------------------------------------------------------
+constexpr int GRAM_THREADS = 256;
+constexpr int GRAM_ROWS = 32;
+
+template <int KP>
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_partial_kernel(const float* __restrict__ X, int n_rows, double* __restrict__ partial) {
+  constexpr int TM = KP / 16;
+  __shared__ __align__(16) float tile[GRAM_ROWS * KP];
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  double acc[TM][TM];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TM; ++j) acc[i][j] = 0.0;
+  const int per = (n_rows + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per;
+  const int r1 = min(n_rows, r0 + per);
+  for (int base = r0; base < r1; base += GRAM_ROWS) {
+    const int nr = min(GRAM_ROWS, r1 - base);
+    for (int o = tid; o < GRAM_ROWS * KP / 4; o += GRAM_THREADS) {
+      const int rr = o / (KP / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rr < nr) v = reinterpret_cast<const float4*>(X + (size_t)(base + rr) * KP)[o % (KP / 4)];
+      reinterpret_cast<float4*>(tile)[o] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = 0; rr < GRAM_ROWS; ++rr) {
+      double a[TM], b[TM];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        a[i] = (double)tile[rr * KP + ty * TM + i];
+        b[i] = (double)tile[rr * KP + tx * TM + i];
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TM; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  double* out = partial + (size_t)blockIdx.x * KP * KP;
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TM; ++j) out[(ty * TM + i) * KP + tx * TM + j] = acc[i][j];
+}
+
+__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nparts, int n,
+                                   float* __restrict__ out) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  double s = 0.0;
+  for (int q = 0; q < nparts; ++q) s += partial[(size_t)q * n + o];
+  out[o] = (float)s;
+}
+
+}  // namespace pio

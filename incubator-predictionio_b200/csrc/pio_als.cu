@@ -1,0 +1,1289 @@
+// pio_als.cu -- C-ABI implementation (see include/pio_als.h for the reference interfaces each
+// entry point replaces).  Host orchestration only; all arithmetic is in the CUDA kernels of
+// als_kernels.cuh / sort_scan.cuh / topk.cuh.  No CPU fallback: without a usable sm_100 device
+// every computing entry point returns PIO_ALS_ERR_CUDA.
+#include "../../include/pio_als.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "als_kernels.cuh"
+#include "sort_scan.cuh"
+#include "topk.cuh"
+
+namespace pio {
+
+constexpr int HEAVY_T = 4096;  // rows with more ratings than this are solved one per CTA (split mode)
+
+static thread_local std::string g_create_error;
+
+static int ceil_log2(uint64_t n) {
+  int b = 0;
+  while (b < 63 && (1ull << b) < n) ++b;
+  return b < 1 ? 1 : b;
+}
+static int pad_rank(int k) { return k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : 128; }
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library has no link-time NCCL dependency and shares whichever libnccl
+// the host process already loaded (torch's bundled one under torchrun, the system one under a JVM).
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return;
+    api.lib = lib;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(lib, "ncclCommInitRank");
+    api.AllGather = (decltype(api.AllGather))dlsym(lib, "ncclAllGather");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(lib, "ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(lib, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy;
+  });
+  return api;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small kernels of the ingest / model plumbing
+// ---------------------------------------------------------------------------------------------
+__global__ void validate_coo_kernel(const int* u, const int* i, long long n, int nu, int ni, int* bad) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n && (u[e] < 0 || u[e] >= nu || i[e] < 0 || i[e] >= ni)) atomicAdd(bad, 1);
+}
+__global__ void make_keys_ext_kernel(const int* u, const int* i, long long n, int bits_i, uint64_t* keys,
+                                     uint32_t* pay) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) {
+    keys[e] = ((uint64_t)(uint32_t)u[e] << bits_i) | (uint64_t)(uint32_t)i[e];
+    pay[e] = (uint32_t)e;
+  }
+}
+__global__ void head_flags_kernel(const uint64_t* keys, long long n, uint32_t* flag) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) flag[e] = (e == 0 || keys[e] != keys[e - 1]) ? 1u : 0u;
+}
+// one thread per run head: fold the run in event order (sum) or pick the latest event (keep-last)
+__global__ void dedup_compact_kernel(const uint64_t* keys, const uint32_t* pay, const uint32_t* pos,
+                                     long long n, int bits_i, const float* rating, const long long* ts,
+                                     int mode, int* ou, int* oi, float* orr) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const uint64_t key = keys[e];
+  if (e > 0 && keys[e - 1] == key) return;
+  float acc;
+  if (mode == PIO_ALS_DEDUP_SUM) {
+    acc = 0.f;
+    for (long long t = e; t < n && keys[t] == key; ++t) acc += rating[pay[t]];
+  } else {
+    long long best_t = ts ? ts[pay[e]] : 0;
+    uint32_t best_p = pay[e];
+    for (long long t = e + 1; t < n && keys[t] == key; ++t) {
+      const uint32_t pp = pay[t];
+      const long long tt = ts ? ts[pp] : 0;
+      if (tt >= best_t) { best_t = tt; best_p = pp; }  // payload order == event order (stable sort)
+    }
+    acc = rating[best_p];
+  }
+  const uint32_t o = pos[e];
+  ou[o] = (int)(key >> bits_i);
+  oi[o] = (int)(key & ((1ull << bits_i) - 1ull));
+  orr[o] = acc;
+}
+__global__ void degree_kernel(const int* u, const int* i, const float* r, long long n, uint32_t* du,
+                              uint32_t* di, uint32_t* pu, uint32_t* pi) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  atomicAdd(&du[u[e]], 1u);
+  atomicAdd(&di[i[e]], 1u);
+  if (r[e] > 0.f) {
+    atomicAdd(&pu[u[e]], 1u);
+    atomicAdd(&pi[i[e]], 1u);
+  }
+}
+__global__ void degree_keys_kernel(const uint32_t* deg, int n, uint64_t* keys, uint32_t* pay) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) {
+    keys[r] = (uint64_t)(0xFFFFFFFFu - deg[r]);
+    pay[r] = (uint32_t)r;
+  }
+}
+// sorted position p -> internal id: rows are dealt to ranks in snake order so every rank gets
+// the same number of rows and a near-equal share of the ratings; a rank's rows stay
+// degree-descending.
+__global__ void assign_internal_kernel(const uint32_t* order, int n, int W, int R, int* perm, int* inv) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int row = (int)order[p];
+  const int blk = p / W, pos = p % W;
+  const int rk = (blk & 1) ? (W - 1 - pos) : pos;
+  const int internal = rk * R + blk;
+  perm[row] = internal;
+  inv[internal] = row;
+}
+__global__ void fill_int_kernel(int* a, long long n, int v) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) a[e] = v;
+}
+__global__ void make_keys_int_kernel(const int* rowext, const int* colext, long long n, const int* perm_row,
+                                     const int* perm_col, int bits_col, uint64_t* keys, uint32_t* pay) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) {
+    keys[e] = ((uint64_t)(uint32_t)perm_row[rowext[e]] << bits_col) | (uint64_t)(uint32_t)perm_col[colext[e]];
+    pay[e] = (uint32_t)e;
+  }
+}
+__global__ void build_ptr_kernel(const uint64_t* keys, long long n, int bits_col, int n_rows, long long* ptr) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int r = (int)(keys[e] >> bits_col);
+  const int rp = e == 0 ? -1 : (int)(keys[e - 1] >> bits_col);
+  for (int rr = rp + 1; rr <= r; ++rr) ptr[rr] = e;
+  if (e == n - 1)
+    for (int rr = r + 1; rr <= n_rows; ++rr) ptr[rr] = n;
+}
+__global__ void extract_csr_kernel(const uint64_t* keys, const uint32_t* pay, const float* rating, long long b,
+                                   long long cnt, int bits_col, int* idx, float* val) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt) return;
+  idx[t] = (int)(keys[b + t] & ((1ull << bits_col) - 1ull));
+  val[t] = rating[pay[b + t]];
+}
+__global__ void local_rows_kernel(const long long* ptr_full, int row0, int R, long long base, const int* inv,
+                                  const uint32_t* deg, const uint32_t* npos, int implicit, long long* ptr,
+                                  float* nreg, int* counts /* [0]=active [1]=heavy */, int heavy_t) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > R) return;
+  ptr[r] = ptr_full[row0 + r] - base;
+  if (r == R) return;
+  const int ext = inv[row0 + r];
+  float nr = 0.f;
+  if (ext >= 0) {
+    const uint32_t d = deg[ext];
+    nr = implicit ? (float)npos[ext] : (float)d;
+    if (d > 0) atomicAdd(&counts[0], 1);
+    if (d > (uint32_t)heavy_t) atomicAdd(&counts[1], 1);
+  }
+  nreg[r] = nr;
+}
+__global__ void scatter_init_kernel(const float* ext_f, int n, int k, int kp, const int* perm, const uint32_t* deg,
+                                    float* F) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (long long)n * kp) return;
+  const int r = (int)(o / kp), c = (int)(o % kp);
+  float v = 0.f;
+  if (c < k && deg[r] > 0) v = ext_f[(size_t)r * k + c];
+  F[(size_t)perm[r] * kp + c] = v;
+}
+__device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  uint64_t z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// unit-norm Gaussian rows from the counter hash (mirrors synth.py synth_init_factors)
+__global__ void hash_init_kernel(int n, int k, int kp, uint64_t seed, int side, const int* perm,
+                                 const uint32_t* deg, float* F) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float* row = F + (size_t)perm[r] * kp;
+  if (deg[r] == 0) {
+    for (int c = 0; c < kp; ++c) row[c] = 0.f;
+    return;
+  }
+  const uint64_t s = seed ^ 0xA5A5A5A55A5A5A5Aull;
+  double nrm = 0.0;
+  for (int c = 0; c < k; ++c) {
+    const uint64_t ctr = ((uint64_t)r * (uint64_t)k + (uint64_t)c) * 2ull + ((uint64_t)side << 62);
+    const uint64_t h1 = splitmix64_dev(s ^ ctr), h2 = splitmix64_dev(s ^ (ctr + 1ull));
+    const double u1 = ((double)(h1 >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+    const double u2 = (double)(h2 >> 11) * (1.0 / 9007199254740992.0);
+    const float g = (float)(sqrt(-2.0 * log(u1)) * cos(2.0 * 3.14159265358979323846 * u2));
+    row[c] = g;
+    nrm += (double)g * (double)g;
+  }
+  float nf = (float)sqrt(nrm);
+  if (nf == 0.f) nf = 1.f;
+  for (int c = 0; c < k; ++c) row[c] = row[c] / nf;
+  for (int c = k; c < kp; ++c) row[c] = 0.f;
+}
+__global__ void gather_factors_kernel(const float* F, int n, int k, int kp, const int* perm, float* out) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (long long)n * k) return;
+  const int r = (int)(o / k), c = (int)(o % k);
+  out[o] = F[(size_t)perm[r] * kp + c];
+}
+__global__ void has_kernel(const uint32_t* deg, int n, uint8_t* has) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) has[r] = deg[r] > 0 ? 1 : 0;
+}
+// internal row -> external id if the row owns a factor, else -1 (candidate table for top-k)
+__global__ void cand_ext_kernel(const int* inv, const uint32_t* deg, int n_internal, int* out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_internal) return;
+  const int ext = inv[r];
+  out[r] = (ext >= 0 && deg[ext] > 0) ? ext : -1;
+}
+__global__ void gather_rows_kernel(const float* F, int kp, const int* rows_ext, int n, const int* perm,
+                                   const uint32_t* deg, int n_ext, float* out, uint8_t* valid) {
+  const int q = blockIdx.x;
+  const int r = rows_ext[q];
+  const bool ok = r >= 0 && r < n_ext && deg[r] > 0;
+  for (int c = threadIdx.x; c < kp; c += blockDim.x) out[(size_t)q * kp + c] = ok ? F[(size_t)perm[r] * kp + c] : 0.f;
+  if (threadIdx.x == 0 && valid) valid[q] = ok ? 1 : 0;
+  (void)n;
+}
+__global__ void synth_kernel(int nu, int ni, long long n, uint64_t seed, int implicit, long long start, int* u,
+                             int* it, float* r) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const uint64_t base = (uint64_t)(start + e) * 4ull;
+  const uint64_t h1 = splitmix64_dev(seed ^ (base + 1ull));
+  const uint64_t h2 = splitmix64_dev(seed ^ (base + 2ull));
+  const uint64_t h3 = splitmix64_dev(seed ^ (base + 3ull));
+  u[e] = (int)(h1 % (uint64_t)nu);
+  const double uu = (double)(h2 >> 11) * (1.0 / 9007199254740992.0);
+  long long item = (long long)floor(__dmul_rn(__dmul_rn((double)ni, uu), uu));
+  if (item > ni - 1) item = ni - 1;
+  it[e] = (int)item;
+  if (implicit) {
+    int tz = h3 == 0 ? 64 : __ffsll((long long)h3) - 1;
+    if (tz > 9) tz = 9;
+    r[e] = (float)(1 + tz);
+  } else {
+    r[e] = (float)(1 + (int)(h3 % 5ull));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct Side {
+  int n = 0;           // external rows
+  int R = 0;           // rows owned per rank
+  int n_internal = 0;  // world * R
+  int bits = 1;        // bits of an internal id
+  int* perm = nullptr;       // [n]
+  int* inv = nullptr;        // [n_internal]
+  uint32_t* deg = nullptr;   // [n]
+  uint32_t* npos = nullptr;  // [n]
+  long long* ptr = nullptr;  // [R+1]
+  int* idx = nullptr;
+  float* val = nullptr;
+  long long nnz_local = 0;
+  float* nreg = nullptr;     // [R]
+  float* F = nullptr;        // [n_internal][KP]
+  int* cand_ext = nullptr;   // [n_internal]
+  int n_active = 0, n_heavy = 0;
+};
+
+enum EvKind { EV_SOLVE = 0, EV_GRAM = 1, EV_COMM = 2 };
+struct EvPair {
+  cudaEvent_t a, b;
+  int kind;
+};
+
+}  // namespace pio
+
+using namespace pio;
+
+struct pio_als_handle {
+  pio_als_config cfg;
+  int KP = 0;
+  cudaStream_t stream = nullptr;
+  Side U, I;
+  float* yty = nullptr;
+  double* gram_partial = nullptr;
+  int gram_blocks = 0;
+  int* d_fail = nullptr;
+  int* d_counts = nullptr;
+  bool have_ratings = false, have_init = false, trained = false;
+  ncclComm_t comm = nullptr;
+  std::string err;
+  pio_als_stats st{};
+  std::vector<EvPair> ev_pool;
+  size_t ev_used = 0;
+  std::mutex mu;
+  int sm_count = 0;
+};
+
+namespace pio {
+
+static int fail(pio_als_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+#define CK(h, call)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(h, PIO_ALS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                           \
+  } while (0)
+#define LAUNCHED(h) (++(h)->st.kernel_launches)
+
+static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+template <class T>
+static cudaError_t dalloc(pio_als_handle* h, T** p, size_t n) {
+  return cudaMallocAsync((void**)p, (n ? n : 1) * sizeof(T), h->stream);
+}
+template <class T>
+static void dfree(pio_als_handle* h, T*& p) {
+  if (p) cudaFreeAsync((void*)p, h->stream);
+  p = nullptr;
+}
+
+static void free_side(pio_als_handle* h, Side& s, bool keep_factors) {
+  dfree(h, s.perm); dfree(h, s.inv); dfree(h, s.deg); dfree(h, s.npos); dfree(h, s.ptr);
+  dfree(h, s.idx); dfree(h, s.val); dfree(h, s.nreg); dfree(h, s.cand_ext);
+  if (!keep_factors) dfree(h, s.F);
+}
+
+static EvPair& next_ev(pio_als_handle* h, int kind) {
+  if (h->ev_used == h->ev_pool.size()) {
+    EvPair p;
+    cudaEventCreate(&p.a);
+    cudaEventCreate(&p.b);
+    p.kind = kind;
+    h->ev_pool.push_back(p);
+  }
+  EvPair& p = h->ev_pool[h->ev_used++];
+  p.kind = kind;
+  return p;
+}
+
+// ---- ingest ---------------------------------------------------------------------------------
+static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* rowext, const int* colext,
+                      const float* rating, long long nnz, uint64_t* ka, uint32_t* va, uint64_t* kb, uint32_t* vb) {
+  cudaStream_t st = h->stream;
+  const int W = h->cfg.world_size, rk = h->cfg.world_rank;
+  make_keys_int_kernel<<<nblk(nnz, 256), 256, 0, st>>>(rowext, colext, nnz, row.perm, col.perm, col.bits, ka, va);
+  LAUNCHED(h);
+  bool in_b = false;
+  CK(h, radix_sort_pairs(ka, va, kb, vb, (size_t)nnz, row.bits + col.bits, st, &in_b, &h->st.kernel_launches));
+  const uint64_t* ks = in_b ? kb : ka;
+  const uint32_t* vs = in_b ? vb : va;
+  long long* ptr_full = nullptr;
+  CK(h, dalloc(h, &ptr_full, (size_t)row.n_internal + 1));
+  build_ptr_kernel<<<nblk(nnz, 256), 256, 0, st>>>(ks, nnz, col.bits, row.n_internal, ptr_full);
+  LAUNCHED(h);
+  long long be[2];
+  CK(h, cudaMemcpyAsync(&be[0], ptr_full + (size_t)rk * row.R, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaMemcpyAsync(&be[1], ptr_full + (size_t)(rk + 1) * row.R, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  row.nnz_local = be[1] - be[0];
+  if (row.nnz_local >= (1ll << 31))
+    return fail(h, PIO_ALS_ERR_ARG, "more than 2^31-1 ratings on one GPU (%lld); use more GPUs", row.nnz_local);
+  CK(h, dalloc(h, &row.idx, (size_t)row.nnz_local));
+  CK(h, dalloc(h, &row.val, (size_t)row.nnz_local));
+  CK(h, dalloc(h, &row.ptr, (size_t)row.R + 1));
+  CK(h, dalloc(h, &row.nreg, (size_t)row.R));
+  if (row.nnz_local > 0) {
+    extract_csr_kernel<<<nblk(row.nnz_local, 256), 256, 0, st>>>(ks, vs, rating, be[0], row.nnz_local, col.bits,
+                                                                 row.idx, row.val);
+    LAUNCHED(h);
+  }
+  CK(h, cudaMemsetAsync(h->d_counts, 0, 2 * sizeof(int), st));
+  local_rows_kernel<<<nblk(row.R + 1, 256), 256, 0, st>>>(ptr_full, rk * row.R, row.R, be[0], row.inv, row.deg,
+                                                           row.npos, h->cfg.implicit_prefs, row.ptr, row.nreg,
+                                                           h->d_counts, HEAVY_T);
+  LAUNCHED(h);
+  int counts[2];
+  CK(h, cudaMemcpyAsync(counts, h->d_counts, sizeof counts, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  row.n_active = counts[0];
+  row.n_heavy = counts[1];
+  dfree(h, ptr_full);
+  (void)W;
+  return PIO_ALS_OK;
+}
+
+static int rank_rows(pio_als_handle* h, Side& s, uint64_t* ka, uint32_t* va, uint64_t* kb, uint32_t* vb) {
+  cudaStream_t st = h->stream;
+  degree_keys_kernel<<<nblk(s.n, 256), 256, 0, st>>>(s.deg, s.n, ka, va);
+  LAUNCHED(h);
+  bool in_b = false;
+  CK(h, radix_sort_pairs(ka, va, kb, vb, (size_t)s.n, 32, st, &in_b, &h->st.kernel_launches));
+  fill_int_kernel<<<nblk(s.n_internal, 256), 256, 0, st>>>(s.inv, s.n_internal, -1);
+  LAUNCHED(h);
+  assign_internal_kernel<<<nblk(s.n, 256), 256, 0, st>>>(in_b ? vb : va, s.n, h->cfg.world_size, s.R, s.perm, s.inv);
+  LAUNCHED(h);
+  return PIO_ALS_OK;
+}
+
+static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item, const float* d_rating,
+                         long long nnz, int dedup, const long long* d_ts) {
+  cudaStream_t st = h->stream;
+  if (nnz <= 0)
+    return fail(h, PIO_ALS_ERR_ARG, "ratings cannot be empty (the templates require(!ratings.take(1).isEmpty))");
+  if (nnz >= (1ll << 32)) return fail(h, PIO_ALS_ERR_ARG, "nnz must be < 2^32 per call");
+  if (dedup < 0 || dedup > 2) return fail(h, PIO_ALS_ERR_ARG, "bad dedup_mode %d", dedup);
+  free_side(h, h->U, true);
+  free_side(h, h->I, true);
+  h->have_ratings = false;
+  const int W = h->cfg.world_size;
+  Side& U = h->U;
+  Side& I = h->I;
+  U.n = h->cfg.n_users;
+  I.n = h->cfg.n_items;
+  U.R = (U.n + W - 1) / W;
+  I.R = (I.n + W - 1) / W;
+  U.n_internal = U.R * W;
+  I.n_internal = I.R * W;
+  U.bits = ceil_log2((uint64_t)U.n_internal);
+  I.bits = ceil_log2((uint64_t)I.n_internal);
+
+  CK(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
+  validate_coo_kernel<<<nblk(nnz, 256), 256, 0, st>>>(d_user, d_item, nnz, U.n, I.n, h->d_fail);
+  LAUNCHED(h);
+  int bad = 0;
+  CK(h, cudaMemcpyAsync(&bad, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  if (bad) return fail(h, PIO_ALS_ERR_ARG, "%d ratings have a user/item index out of range", bad);
+
+  const size_t nmax = (size_t)(nnz > U.n ? nnz : U.n) > (size_t)I.n ? (size_t)(nnz > U.n ? nnz : U.n) : (size_t)I.n;
+  uint64_t *ka = nullptr, *kb = nullptr;
+  uint32_t *va = nullptr, *vb = nullptr;
+  CK(h, dalloc(h, &ka, nmax));
+  CK(h, dalloc(h, &kb, nmax));
+  CK(h, dalloc(h, &va, nmax));
+  CK(h, dalloc(h, &vb, nmax));
+
+  // 1. optional dedup of repeated (user,item) pairs
+  const int* cu = d_user;
+  const int* ci = d_item;
+  const float* cr = d_rating;
+  int *du_ = nullptr, *di_ = nullptr;
+  float* dr_ = nullptr;
+  long long n2 = nnz;
+  if (dedup != PIO_ALS_DEDUP_NONE) {
+    const int bu = ceil_log2((uint64_t)U.n), bi = ceil_log2((uint64_t)I.n);
+    make_keys_ext_kernel<<<nblk(nnz, 256), 256, 0, st>>>(d_user, d_item, nnz, bi, ka, va);
+    LAUNCHED(h);
+    bool in_b = false;
+    CK(h, radix_sort_pairs(ka, va, kb, vb, (size_t)nnz, bu + bi, st, &in_b, &h->st.kernel_launches));
+    const uint64_t* ks = in_b ? kb : ka;
+    const uint32_t* vs = in_b ? vb : va;
+    uint32_t* flag = nullptr;
+    CK(h, dalloc(h, &flag, (size_t)nnz));
+    head_flags_kernel<<<nblk(nnz, 256), 256, 0, st>>>(ks, nnz, flag);
+    LAUNCHED(h);
+    uint32_t last_flag = 0, last_pos = 0;
+    CK(h, cudaMemcpyAsync(&last_flag, flag + nnz - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(h, scan_exclusive_u32(flag, flag, (size_t)nnz, st, &h->st.kernel_launches));
+    CK(h, cudaMemcpyAsync(&last_pos, flag + nnz - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    n2 = (long long)last_pos + last_flag;
+    CK(h, dalloc(h, &du_, (size_t)n2));
+    CK(h, dalloc(h, &di_, (size_t)n2));
+    CK(h, dalloc(h, &dr_, (size_t)n2));
+    dedup_compact_kernel<<<nblk(nnz, 256), 256, 0, st>>>(ks, vs, flag, nnz, bi, d_rating, d_ts, dedup, du_, di_, dr_);
+    LAUNCHED(h);
+    dfree(h, flag);
+    cu = du_;
+    ci = di_;
+    cr = dr_;
+  }
+  h->st.nnz = n2;
+
+  // 2. degrees, positive-rating counts
+  for (Side* s : {&U, &I}) {
+    CK(h, dalloc(h, &s->deg, (size_t)s->n));
+    CK(h, dalloc(h, &s->npos, (size_t)s->n));
+    CK(h, dalloc(h, &s->perm, (size_t)s->n));
+    CK(h, dalloc(h, &s->inv, (size_t)s->n_internal));
+    CK(h, cudaMemsetAsync(s->deg, 0, sizeof(uint32_t) * s->n, st));
+    CK(h, cudaMemsetAsync(s->npos, 0, sizeof(uint32_t) * s->n, st));
+  }
+  degree_kernel<<<nblk(n2, 256), 256, 0, st>>>(cu, ci, cr, n2, U.deg, I.deg, U.npos, I.npos);
+  LAUNCHED(h);
+
+  // 3. renumber rows: degree-descending, dealt to ranks
+  int rc = rank_rows(h, U, ka, va, kb, vb);
+  if (rc) return rc;
+  rc = rank_rows(h, I, ka, va, kb, vb);
+  if (rc) return rc;
+
+  // 4. the two CSR orientations in internal numbering (only this rank's rows are kept)
+  rc = build_side(h, U, I, cu, ci, cr, n2, ka, va, kb, vb);
+  if (rc) return rc;
+  rc = build_side(h, I, U, ci, cu, cr, n2, ka, va, kb, vb);
+  if (rc) return rc;
+
+  // 5. factor matrices (zero: rows without ratings must stay zero) and candidate tables
+  for (Side* s : {&U, &I}) {
+    if (!s->F) {
+      CK(h, dalloc(h, &s->F, (size_t)s->n_internal * h->KP));
+      h->have_init = false;
+    }
+    CK(h, dalloc(h, &s->cand_ext, (size_t)s->n_internal));
+    cand_ext_kernel<<<nblk(s->n_internal, 256), 256, 0, st>>>(s->inv, s->deg, s->n_internal, s->cand_ext);
+    LAUNCHED(h);
+  }
+  h->have_init = false;
+  dfree(h, du_); dfree(h, di_); dfree(h, dr_);
+  dfree(h, ka); dfree(h, kb); dfree(h, va); dfree(h, vb);
+  CK(h, cudaStreamSynchronize(st));
+  int au[2] = {U.n_active, I.n_active};
+  h->st.n_users_active = au[0];
+  h->st.n_items_active = au[1];
+  if (W > 1) {
+    // n_active per rank is local; report global actives via degrees instead (cheap host-side sum avoided):
+    h->st.n_users_active = -1;
+    h->st.n_items_active = -1;
+  }
+  h->have_ratings = true;
+  h->trained = false;
+  return PIO_ALS_OK;
+}
+
+static int init_hash(pio_als_handle* h) {
+  cudaStream_t st = h->stream;
+  CK(h, cudaMemsetAsync(h->U.F, 0, sizeof(float) * (size_t)h->U.n_internal * h->KP, st));
+  CK(h, cudaMemsetAsync(h->I.F, 0, sizeof(float) * (size_t)h->I.n_internal * h->KP, st));
+  hash_init_kernel<<<nblk(h->U.n, 128), 128, 0, st>>>(h->U.n, h->cfg.rank, h->KP, (uint64_t)h->cfg.seed, 0, h->U.perm,
+                                                      h->U.deg, h->U.F);
+  LAUNCHED(h);
+  hash_init_kernel<<<nblk(h->I.n, 128), 128, 0, st>>>(h->I.n, h->cfg.rank, h->KP, (uint64_t)h->cfg.seed, 1, h->I.perm,
+                                                      h->I.deg, h->I.F);
+  LAUNCHED(h);
+  h->have_init = true;
+  return PIO_ALS_OK;
+}
+
+// ---- solve dispatch ---------------------------------------------------------------------------
+template <class Cfg, bool IMPLICIT, bool HEAVY>
+static cudaError_t launch_solve_one(pio_als_handle* h, const SolveParams& p, int grid) {
+  static bool attr_set[64] = {};
+  int dev = h->cfg.device;
+  auto kern = als_solve_kernel<Cfg, IMPLICIT, HEAVY>;
+  const size_t smem = Cfg::smem_bytes(HEAVY);
+  if (dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  kern<<<grid, Cfg::NT, smem, h->stream>>>(p);
+  LAUNCHED(h);
+  ++h->st.solve_launches;
+  return cudaGetLastError();
+}
+
+template <class Cfg>
+static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& src) {
+  SolveParams p;
+  p.ptr = dst.ptr;
+  p.idx = dst.idx;
+  p.val = dst.val;
+  p.src = src.F;
+  p.dst = dst.F;
+  p.yty = h->yty;
+  p.nreg = dst.nreg;
+  p.fail = h->d_fail;
+  p.lambda = (float)h->cfg.lambda;
+  p.alpha = (float)h->cfg.alpha;
+  p.k = h->cfg.rank;
+  p.dst_row_offset = h->cfg.world_rank * dst.R;
+  const bool imp = h->cfg.implicit_prefs != 0;
+  cudaError_t e = cudaSuccess;
+  if (dst.n_heavy > 0) {
+    p.row_begin = 0;
+    p.row_end = dst.n_heavy;
+    e = imp ? launch_solve_one<Cfg, true, true>(h, p, dst.n_heavy) : launch_solve_one<Cfg, false, true>(h, p, dst.n_heavy);
+    if (e != cudaSuccess) return e;
+  }
+  const int nlight = dst.n_active - dst.n_heavy;
+  if (nlight > 0) {
+    p.row_begin = dst.n_heavy;
+    p.row_end = dst.n_active;
+    const int grid = (nlight + Cfg::NG - 1) / Cfg::NG;
+    e = imp ? launch_solve_one<Cfg, true, false>(h, p, grid) : launch_solve_one<Cfg, false, false>(h, p, grid);
+  }
+  return e;
+}
+
+using Cfg16 = SolveCfg<16, 4, 25, 8>;
+using Cfg32 = SolveCfg<32, 8, 25, 4>;
+using Cfg64 = SolveCfg<64, 8, 7, 8>;
+using Cfg128 = SolveCfg<128, 8, 2, 9>;
+
+static cudaError_t launch_solve(pio_als_handle* h, Side& dst, const Side& src) {
+  switch (h->KP) {
+    case 16: return launch_solve_cfg<Cfg16>(h, dst, src);
+    case 32: return launch_solve_cfg<Cfg32>(h, dst, src);
+    case 64: return launch_solve_cfg<Cfg64>(h, dst, src);
+    default: return launch_solve_cfg<Cfg128>(h, dst, src);
+  }
+}
+
+static cudaError_t launch_gram(pio_als_handle* h, const Side& src) {
+  const int nb = h->gram_blocks;
+  switch (h->KP) {
+    case 16: gram_partial_kernel<16><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.n_internal, h->gram_partial); break;
+    case 32: gram_partial_kernel<32><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.n_internal, h->gram_partial); break;
+    case 64: gram_partial_kernel<64><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.n_internal, h->gram_partial); break;
+    default: gram_partial_kernel<128><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.n_internal, h->gram_partial); break;
+  }
+  LAUNCHED(h);
+  const int n = h->KP * h->KP;
+  gram_reduce_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(h->gram_partial, nb, n, h->yty);
+  LAUNCHED(h);
+  return cudaGetLastError();
+}
+
+static int half_step(pio_als_handle* h, Side& dst, const Side& src) {
+  cudaStream_t st = h->stream;
+  if (h->cfg.implicit_prefs) {
+    EvPair& e = next_ev(h, EV_GRAM);
+    cudaEventRecord(e.a, st);
+    CK(h, launch_gram(h, src));
+    cudaEventRecord(e.b, st);
+  }
+  {
+    EvPair& e = next_ev(h, EV_SOLVE);
+    cudaEventRecord(e.a, st);
+    CK(h, launch_solve(h, dst, src));
+    cudaEventRecord(e.b, st);
+  }
+  if (h->cfg.world_size > 1) {
+    EvPair& e = next_ev(h, EV_COMM);
+    cudaEventRecord(e.a, st);
+    const size_t cnt = (size_t)dst.R * h->KP;
+    ncclResult_t r = nccl_api().AllGather(dst.F + (size_t)h->cfg.world_rank * cnt, dst.F, cnt, ncclFloat, h->comm, st);
+    if (r != ncclSuccess)
+      return fail(h, PIO_ALS_ERR_COMM, "ncclAllGather failed: %s",
+                  nccl_api().GetErrorString ? nccl_api().GetErrorString(r) : "?");
+    cudaEventRecord(e.b, st);
+  }
+  return PIO_ALS_OK;
+}
+
+}  // namespace pio
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int pio_als_abi_version(void) { return PIO_ALS_ABI_VERSION; }
+
+int pio_als_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return PIO_ALS_ERR_CUDA;
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, d) == cudaSuccess && pr.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int pio_als_nccl_unique_id(uint8_t out_id[128]) {
+  NcclApi& a = nccl_api();
+  if (!a.ok) return fail(nullptr, PIO_ALS_ERR_COMM, "libnccl.so.2 not loadable");
+  ncclUniqueId id;
+  if (a.GetUniqueId(&id) != ncclSuccess) return fail(nullptr, PIO_ALS_ERR_COMM, "ncclGetUniqueId failed");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out_id, &id, 128);
+  return PIO_ALS_OK;
+}
+
+const char* pio_als_last_error(const pio_als_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static int create_common(pio_als_handle* h) {
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, PIO_ALS_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                cudaGetErrorString(ce));
+  if (h->cfg.device < 0 || h->cfg.device >= ndev) return fail(nullptr, PIO_ALS_ERR_ARG, "bad device %d", h->cfg.device);
+  cudaDeviceProp pr;
+  if (cudaGetDeviceProperties(&pr, h->cfg.device) != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaGetDeviceProperties");
+  if (pr.major != 10)
+    return fail(nullptr, PIO_ALS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                h->cfg.device, pr.major, pr.minor);
+  h->sm_count = pr.multiProcessorCount;
+  h->st.sm_count = pr.multiProcessorCount;
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaSetDevice");
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaStreamCreate");
+  // keep freed blocks in the pool (ingest allocates and frees multi-GB scratch repeatedly)
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, h->cfg.device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  h->KP = pad_rank(h->cfg.rank);
+  h->gram_blocks = 2 * h->sm_count;
+  if (cudaMallocAsync((void**)&h->yty, sizeof(float) * h->KP * h->KP, h->stream) != cudaSuccess ||
+      cudaMallocAsync((void**)&h->gram_partial, sizeof(double) * (size_t)h->gram_blocks * h->KP * h->KP, h->stream) != cudaSuccess ||
+      cudaMallocAsync((void**)&h->d_fail, sizeof(int), h->stream) != cudaSuccess ||
+      cudaMallocAsync((void**)&h->d_counts, 4 * sizeof(int), h->stream) != cudaSuccess)
+    return fail(nullptr, PIO_ALS_ERR_CUDA, "device allocation failed");
+  cudaMemsetAsync(h->yty, 0, sizeof(float) * h->KP * h->KP, h->stream);
+  cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream);
+  return PIO_ALS_OK;
+}
+
+int pio_als_create(const pio_als_config* cfg, pio_als_handle** out) {
+  if (!cfg || !out) return fail(nullptr, PIO_ALS_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != PIO_ALS_ABI_VERSION) return fail(nullptr, PIO_ALS_ERR_ARG, "abi_version mismatch");
+  if (cfg->rank < 1 || cfg->rank > 128) return fail(nullptr, PIO_ALS_ERR_ARG, "rank must be in 1..128 (got %d)", cfg->rank);
+  if (cfg->n_users < 1 || cfg->n_items < 1) return fail(nullptr, PIO_ALS_ERR_ARG, "n_users and n_items must be >= 1");
+  if (cfg->world_size < 1 || cfg->world_rank < 0 || cfg->world_rank >= cfg->world_size)
+    return fail(nullptr, PIO_ALS_ERR_ARG, "bad world_size/world_rank");
+  if (!(cfg->lambda >= 0.0)) return fail(nullptr, PIO_ALS_ERR_ARG, "lambda must be >= 0");
+  pio_als_handle* h = new pio_als_handle();
+  h->cfg = *cfg;
+  int rc = create_common(h);
+  if (rc == PIO_ALS_OK && cfg->world_size > 1) {
+    NcclApi& a = nccl_api();
+    if (!a.ok) rc = fail(nullptr, PIO_ALS_ERR_COMM, "libnccl.so.2 not loadable");
+    else {
+      ncclUniqueId id;
+      memcpy(&id, cfg->nccl_id, 128);
+      ncclResult_t r = a.CommInitRank(&h->comm, cfg->world_size, id, cfg->world_rank);
+      if (r != ncclSuccess) rc = fail(nullptr, PIO_ALS_ERR_COMM, "ncclCommInitRank failed: %s", a.GetErrorString ? a.GetErrorString(r) : "?");
+    }
+  }
+  if (rc != PIO_ALS_OK) {
+    pio_als_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return PIO_ALS_OK;
+}
+
+void pio_als_destroy(pio_als_handle* h) {
+  if (!h) return;
+  if (h->stream) {
+    cudaSetDevice(h->cfg.device);
+    free_side(h, h->U, false);
+    free_side(h, h->I, false);
+    dfree(h, h->yty);
+    dfree(h, h->gram_partial);
+    dfree(h, h->d_fail);
+    dfree(h, h->d_counts);
+    cudaStreamSynchronize(h->stream);
+    for (auto& e : h->ev_pool) {
+      cudaEventDestroy(e.a);
+      cudaEventDestroy(e.b);
+    }
+    if (h->comm) nccl_api().CommDestroy(h->comm);
+    cudaStreamDestroy(h->stream);
+  }
+  delete h;
+}
+
+int pio_als_set_ratings_coo_device(pio_als_handle* h, const int32_t* d_user, const int32_t* d_item,
+                                   const float* d_rating, int64_t nnz, int dedup_mode, const int64_t* d_ts) {
+  if (!h) return PIO_ALS_ERR_ARG;
+  if (!d_user || !d_item || !d_rating) return fail(h, PIO_ALS_ERR_ARG, "null rating arrays");
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, h->stream);
+  int rc = ingest_device(h, d_user, d_item, d_rating, nnz, dedup_mode, (const long long*)d_ts);
+  cudaEventRecord(b, h->stream);
+  cudaEventSynchronize(b);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a, b);
+  h->st.last_ingest_ms = ms;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return rc;
+}
+
+int pio_als_set_ratings_coo(pio_als_handle* h, const int32_t* user, const int32_t* item, const float* rating,
+                            int64_t nnz, int dedup_mode, const int64_t* ts) {
+  if (!h) return PIO_ALS_ERR_ARG;
+  if (nnz <= 0) return fail(h, PIO_ALS_ERR_ARG, "ratings cannot be empty (the templates require(!ratings.take(1).isEmpty))");
+  if (!user || !item || !rating) return fail(h, PIO_ALS_ERR_ARG, "null rating arrays");
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, st);
+  int *du = nullptr, *di = nullptr;
+  float* dr = nullptr;
+  long long* dts = nullptr;
+  CK(h, dalloc(h, &du, (size_t)nnz));
+  CK(h, dalloc(h, &di, (size_t)nnz));
+  CK(h, dalloc(h, &dr, (size_t)nnz));
+  CK(h, cudaMemcpyAsync(du, user, sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
+  CK(h, cudaMemcpyAsync(di, item, sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
+  CK(h, cudaMemcpyAsync(dr, rating, sizeof(float) * nnz, cudaMemcpyHostToDevice, st));
+  if (ts && dedup_mode == PIO_ALS_DEDUP_KEEP_LAST) {
+    CK(h, dalloc(h, &dts, (size_t)nnz));
+    CK(h, cudaMemcpyAsync(dts, ts, sizeof(long long) * nnz, cudaMemcpyHostToDevice, st));
+  }
+  int rc = ingest_device(h, du, di, dr, nnz, dedup_mode, dts);
+  dfree(h, du); dfree(h, di); dfree(h, dr); dfree(h, dts);
+  cudaEventRecord(b, st);
+  cudaEventSynchronize(b);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a, b);
+  h->st.last_ingest_ms = ms;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return rc;
+}
+
+int pio_als_set_init(pio_als_handle* h, const float* user_factors, const float* item_factors) {
+  if (!h) return PIO_ALS_ERR_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->have_ratings) return fail(h, PIO_ALS_ERR_STATE, "set_init before set_ratings");
+  if (!user_factors) return fail(h, PIO_ALS_ERR_ARG, "user_factors is null");
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  const int k = h->cfg.rank;
+  struct { Side* s; const float* f; } jobs[2] = {{&h->U, user_factors}, {&h->I, item_factors}};
+  for (auto& j : jobs) {
+    CK(h, cudaMemsetAsync(j.s->F, 0, sizeof(float) * (size_t)j.s->n_internal * h->KP, st));
+    if (!j.f) continue;
+    float* tmp = nullptr;
+    CK(h, dalloc(h, &tmp, (size_t)j.s->n * k));
+    CK(h, cudaMemcpyAsync(tmp, j.f, sizeof(float) * (size_t)j.s->n * k, cudaMemcpyHostToDevice, st));
+    scatter_init_kernel<<<nblk((long long)j.s->n * h->KP, 256), 256, 0, st>>>(tmp, j.s->n, k, h->KP, j.s->perm, j.s->deg, j.s->F);
+    LAUNCHED(h);
+    dfree(h, tmp);
+  }
+  CK(h, cudaStreamSynchronize(st));
+  h->have_init = true;
+  return PIO_ALS_OK;
+}
+
+int pio_als_run(pio_als_handle* h, int n_iters) {
+  if (!h) return PIO_ALS_ERR_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->have_ratings) return fail(h, PIO_ALS_ERR_STATE, "run before set_ratings");
+  if (n_iters < 0) return fail(h, PIO_ALS_ERR_ARG, "n_iters < 0");
+  CK(h, cudaSetDevice(h->cfg.device));
+  if (!h->have_init) {
+    if (h->cfg.init_mode == PIO_ALS_INIT_HASH) {
+      int rc = init_hash(h);
+      if (rc) return rc;
+    } else {
+      return fail(h, PIO_ALS_ERR_STATE, "no initial factors: call pio_als_set_init or use PIO_ALS_INIT_HASH");
+    }
+  }
+  cudaStream_t st = h->stream;
+  h->ev_used = 0;
+  CK(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
+  EvPair& tot = next_ev(h, -1);
+  cudaEventRecord(tot.a, st);
+  for (int it = 0; it < n_iters; ++it) {
+    int rc = half_step(h, h->I, h->U);  // item factors from user factors
+    if (rc) return rc;
+    rc = half_step(h, h->U, h->I);      // user factors from item factors
+    if (rc) return rc;
+  }
+  cudaEventRecord(tot.b, st);
+  int nfail = 0;
+  CK(h, cudaMemcpyAsync(&nfail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  double ms[3] = {0, 0, 0};
+  float t = 0;
+  for (size_t i = 0; i < h->ev_used; ++i) {
+    EvPair& e = h->ev_pool[i];
+    cudaEventElapsedTime(&t, e.a, e.b);
+    if (e.kind >= 0) ms[e.kind] += t;
+    else h->st.last_run_ms = t;
+  }
+  h->st.last_solve_ms = ms[EV_SOLVE];
+  h->st.last_gram_ms = ms[EV_GRAM];
+  h->st.last_comm_ms = ms[EV_COMM];
+  h->trained = true;
+  if (nfail)
+    return fail(h, PIO_ALS_ERR_NUMERIC, "%d normal equations were not positive definite (MLlib: dppsv info != 0)", nfail);
+  return PIO_ALS_OK;
+}
+
+int pio_als_get_factors(pio_als_handle* h, float* user_out, float* item_out, uint8_t* user_has, uint8_t* item_has) {
+  if (!h) return PIO_ALS_ERR_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->have_ratings && !h->trained) return fail(h, PIO_ALS_ERR_STATE, "no model");
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  const int k = h->cfg.rank;
+  struct { Side* s; float* f; uint8_t* has; } jobs[2] = {{&h->U, user_out, user_has}, {&h->I, item_out, item_has}};
+  for (auto& j : jobs) {
+    if (j.f) {
+      float* tmp = nullptr;
+      CK(h, dalloc(h, &tmp, (size_t)j.s->n * k));
+      gather_factors_kernel<<<nblk((long long)j.s->n * k, 256), 256, 0, st>>>(j.s->F, j.s->n, k, h->KP, j.s->perm, tmp);
+      LAUNCHED(h);
+      CK(h, cudaMemcpyAsync(j.f, tmp, sizeof(float) * (size_t)j.s->n * k, cudaMemcpyDeviceToHost, st));
+      dfree(h, tmp);
+    }
+    if (j.has) {
+      uint8_t* tmp = nullptr;
+      CK(h, dalloc(h, &tmp, (size_t)j.s->n));
+      has_kernel<<<nblk(j.s->n, 256), 256, 0, st>>>(j.s->deg, j.s->n, tmp);
+      LAUNCHED(h);
+      CK(h, cudaMemcpyAsync(j.has, tmp, (size_t)j.s->n, cudaMemcpyDeviceToHost, st));
+      dfree(h, tmp);
+    }
+  }
+  CK(h, cudaStreamSynchronize(st));
+  return PIO_ALS_OK;
+}
+
+int pio_als_train(pio_als_handle* h, const int32_t* user, const int32_t* item, const float* rating, int64_t nnz,
+                  int dedup_mode, const int64_t* ts, const float* user_init, const float* item_init, int n_iters,
+                  float* user_out, float* item_out, uint8_t* user_has, uint8_t* item_has) {
+  int rc = pio_als_set_ratings_coo(h, user, item, rating, nnz, dedup_mode, ts);
+  if (rc) return rc;
+  if (user_init) {
+    rc = pio_als_set_init(h, user_init, item_init);
+    if (rc) return rc;
+  }
+  rc = pio_als_run(h, n_iters);
+  if (rc) return rc;
+  return pio_als_get_factors(h, user_out, item_out, user_has, item_has);
+}
+
+int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, const uint8_t* item_mask,
+                      int32_t* out_items, float* out_scores, int32_t* out_count) {
+  if (!h) return PIO_ALS_ERR_ARG;
+  if (n < 0 || topk < 1 || topk > TK_MAXK) return fail(h, PIO_ALS_ERR_ARG, "topk must be in 1..%d", TK_MAXK);
+  if (n == 0) return PIO_ALS_OK;
+  if (!users || !out_items || !out_scores) return fail(h, PIO_ALS_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->U.F || !h->I.F || !h->I.cand_ext) return fail(h, PIO_ALS_ERR_STATE, "no model");
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  const int KP = h->KP, k = h->cfg.rank;
+  int* d_users = nullptr;
+  float* d_xq = nullptr;
+  uint8_t *d_valid = nullptr, *d_mask = nullptr;
+  ScoreIdx* d_cand = nullptr;
+  int *d_oi = nullptr, *d_oc = nullptr;
+  float* d_os = nullptr;
+  const int ntiles = (h->I.n_internal + TK_TILE - 1) / TK_TILE;
+  CK(h, dalloc(h, &d_users, (size_t)n));
+  CK(h, dalloc(h, &d_xq, (size_t)n * KP));
+  CK(h, dalloc(h, &d_valid, (size_t)n));
+  CK(h, dalloc(h, &d_cand, (size_t)n * ntiles * topk));
+  CK(h, dalloc(h, &d_oi, (size_t)n * topk));
+  CK(h, dalloc(h, &d_os, (size_t)n * topk));
+  CK(h, dalloc(h, &d_oc, (size_t)n));
+  CK(h, cudaMemcpyAsync(d_users, users, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  if (item_mask) {
+    CK(h, dalloc(h, &d_mask, (size_t)h->I.n));
+    CK(h, cudaMemcpyAsync(d_mask, item_mask, (size_t)h->I.n, cudaMemcpyHostToDevice, st));
+  }
+  gather_rows_kernel<<<n, 64, 0, st>>>(h->U.F, KP, d_users, n, h->U.perm, h->U.deg, h->U.n, d_xq, d_valid);
+  LAUNCHED(h);
+  // grid.y is limited to 65535 queries per launch
+  for (int q0 = 0; q0 < n; q0 += 32768) {
+    const int nq = n - q0 < 32768 ? n - q0 : 32768;
+    score_dot_topk_kernel<<<dim3(ntiles, nq), TK_THREADS, sizeof(float) * k, st>>>(
+        h->I.F, h->I.n_internal, KP, k, d_xq + (size_t)q0 * KP, d_valid + q0, h->I.cand_ext, d_mask, topk,
+        d_cand + (size_t)q0 * ntiles * topk);
+    LAUNCHED(h);
+  }
+  topk_merge_kernel<<<n, TK_THREADS, 0, st>>>(d_cand, ntiles * topk, topk, d_oi, d_os, d_oc);
+  LAUNCHED(h);
+  CK(h, cudaMemcpyAsync(out_items, d_oi, sizeof(int) * (size_t)n * topk, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaMemcpyAsync(out_scores, d_os, sizeof(float) * (size_t)n * topk, cudaMemcpyDeviceToHost, st));
+  if (out_count) CK(h, cudaMemcpyAsync(out_count, d_oc, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  dfree(h, d_users); dfree(h, d_xq); dfree(h, d_valid); dfree(h, d_mask); dfree(h, d_cand);
+  dfree(h, d_oi); dfree(h, d_os); dfree(h, d_oc);
+  CK(h, cudaStreamSynchronize(st));
+  return PIO_ALS_OK;
+}
+
+int pio_als_similar(pio_als_handle* h, const int32_t* query_items, int nq, int topk, const uint8_t* item_mask,
+                    int32_t* out_items, float* out_scores, int32_t* out_count) {
+  if (!h) return PIO_ALS_ERR_ARG;
+  if (nq < 0 || topk < 1 || topk > TK_MAXK) return fail(h, PIO_ALS_ERR_ARG, "topk must be in 1..%d", TK_MAXK);
+  if (!out_items || !out_scores || (nq > 0 && !query_items)) return fail(h, PIO_ALS_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->I.F || !h->I.cand_ext) return fail(h, PIO_ALS_ERR_STATE, "no model");
+  for (int t = 0; t < topk; ++t) { out_items[t] = -1; out_scores[t] = 0.f; }
+  if (out_count) *out_count = 0;
+  if (nq == 0) return PIO_ALS_OK;
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  const int KP = h->KP, k = h->cfg.rank;
+  int* d_q = nullptr;
+  float* d_qf = nullptr;
+  uint8_t *d_valid = nullptr, *d_mask = nullptr;
+  CK(h, dalloc(h, &d_q, (size_t)nq));
+  CK(h, dalloc(h, &d_qf, (size_t)nq * KP));
+  CK(h, dalloc(h, &d_valid, (size_t)nq));
+  CK(h, cudaMemcpyAsync(d_q, query_items, sizeof(int) * nq, cudaMemcpyHostToDevice, st));
+  gather_rows_kernel<<<nq, 64, 0, st>>>(h->I.F, KP, d_q, nq, h->I.perm, h->I.deg, h->I.n, d_qf, d_valid);
+  LAUNCHED(h);
+  std::vector<uint8_t> valid(nq);
+  CK(h, cudaMemcpyAsync(valid.data(), d_valid, (size_t)nq, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  // compact the query vectors that own a factor (order preserved); all query ids stay excluded
+  std::vector<int> keep;
+  for (int q = 0; q < nq; ++q)
+    if (valid[q]) keep.push_back(q);
+  int rc = PIO_ALS_OK;
+  if (!keep.empty()) {
+    float* d_qc = nullptr;
+    CK(h, dalloc(h, &d_qc, keep.size() * (size_t)KP));
+    for (size_t j = 0; j < keep.size(); ++j)
+      CK(h, cudaMemcpyAsync(d_qc + j * KP, d_qf + (size_t)keep[j] * KP, sizeof(float) * KP, cudaMemcpyDeviceToDevice, st));
+    if (item_mask) {
+      CK(h, dalloc(h, &d_mask, (size_t)h->I.n));
+      CK(h, cudaMemcpyAsync(d_mask, item_mask, (size_t)h->I.n, cudaMemcpyHostToDevice, st));
+    }
+    const int ntiles = (h->I.n_internal + TK_TILE - 1) / TK_TILE;
+    ScoreIdx* d_cand = nullptr;
+    int *d_oi = nullptr, *d_oc = nullptr;
+    float* d_os = nullptr;
+    CK(h, dalloc(h, &d_cand, (size_t)ntiles * topk));
+    CK(h, dalloc(h, &d_oi, (size_t)topk));
+    CK(h, dalloc(h, &d_os, (size_t)topk));
+    CK(h, dalloc(h, &d_oc, 1));
+    score_cos_topk_kernel<<<ntiles, TK_THREADS, 0, st>>>(h->I.F, h->I.n_internal, KP, k, d_qc, d_q, nq, (int)keep.size(),
+                                                         h->I.cand_ext, d_mask, topk, d_cand);
+    LAUNCHED(h);
+    topk_merge_kernel<<<1, TK_THREADS, 0, st>>>(d_cand, ntiles * topk, topk, d_oi, d_os, d_oc);
+    LAUNCHED(h);
+    CK(h, cudaMemcpyAsync(out_items, d_oi, sizeof(int) * topk, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(out_scores, d_os, sizeof(float) * topk, cudaMemcpyDeviceToHost, st));
+    int cnt = 0;
+    CK(h, cudaMemcpyAsync(&cnt, d_oc, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    if (out_count) *out_count = cnt;
+    dfree(h, d_qc); dfree(h, d_cand); dfree(h, d_oi); dfree(h, d_os); dfree(h, d_oc); dfree(h, d_mask);
+  }
+  dfree(h, d_q); dfree(h, d_qf); dfree(h, d_valid);
+  CK(h, cudaStreamSynchronize(st));
+  return rc;
+}
+
+// ---- persistence ------------------------------------------------------------------------------
+struct ModelHeader {
+  char magic[8];
+  int32_t version, rank, implicit_prefs, n_users, n_items, reserved;
+  double lambda, alpha;
+};
+
+int pio_als_save(pio_als_handle* h, const char* path) {
+  if (!h || !path) return PIO_ALS_ERR_ARG;
+  const size_t nu = h->cfg.n_users, ni = h->cfg.n_items, k = h->cfg.rank;
+  std::vector<float> uf(nu * k), itf(ni * k);
+  std::vector<uint8_t> uh(nu), ih(ni);
+  int rc = pio_als_get_factors(h, uf.data(), itf.data(), uh.data(), ih.data());
+  if (rc) return rc;
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(h, PIO_ALS_ERR_IO, "cannot open %s for writing", path);
+  ModelHeader hd{};
+  memcpy(hd.magic, "PIOALS01", 8);
+  hd.version = 1;
+  hd.rank = h->cfg.rank;
+  hd.implicit_prefs = h->cfg.implicit_prefs;
+  hd.n_users = h->cfg.n_users;
+  hd.n_items = h->cfg.n_items;
+  hd.lambda = h->cfg.lambda;
+  hd.alpha = h->cfg.alpha;
+  bool ok = fwrite(&hd, sizeof hd, 1, f) == 1 && fwrite(uh.data(), 1, nu, f) == nu && fwrite(ih.data(), 1, ni, f) == ni &&
+            fwrite(uf.data(), sizeof(float), nu * k, f) == nu * k && fwrite(itf.data(), sizeof(float), ni * k, f) == ni * k;
+  ok = (fclose(f) == 0) && ok;
+  return ok ? PIO_ALS_OK : fail(h, PIO_ALS_ERR_IO, "short write to %s", path);
+}
+
+__global__ void load_side_kernel(const uint8_t* has, int n, int* perm, int* inv, uint32_t* deg, uint32_t* npos) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  perm[r] = r;
+  inv[r] = r;
+  deg[r] = has[r] ? 1u : 0u;
+  npos[r] = deg[r];
+}
+
+int pio_als_load(const char* path, int device, pio_als_handle** out) {
+  if (!path || !out) return fail(nullptr, PIO_ALS_ERR_ARG, "null argument");
+  *out = nullptr;
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(nullptr, PIO_ALS_ERR_IO, "cannot open %s", path);
+  ModelHeader hd;
+  if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "PIOALS01", 8) != 0 || hd.version != 1) {
+    fclose(f);
+    return fail(nullptr, PIO_ALS_ERR_IO, "%s is not a PIOALS01 model file", path);
+  }
+  const size_t nu = hd.n_users, ni = hd.n_items, k = hd.rank;
+  std::vector<float> uf(nu * k), itf(ni * k);
+  std::vector<uint8_t> uh(nu), ih(ni);
+  bool ok = fread(uh.data(), 1, nu, f) == nu && fread(ih.data(), 1, ni, f) == ni &&
+            fread(uf.data(), sizeof(float), nu * k, f) == nu * k && fread(itf.data(), sizeof(float), ni * k, f) == ni * k;
+  fclose(f);
+  if (!ok) return fail(nullptr, PIO_ALS_ERR_IO, "%s is truncated", path);
+  pio_als_config cfg{};
+  cfg.abi_version = PIO_ALS_ABI_VERSION;
+  cfg.rank = hd.rank;
+  cfg.implicit_prefs = hd.implicit_prefs;
+  cfg.n_users = hd.n_users;
+  cfg.n_items = hd.n_items;
+  cfg.device = device;
+  cfg.world_size = 1;
+  cfg.lambda = hd.lambda;
+  cfg.alpha = hd.alpha;
+  pio_als_handle* h = nullptr;
+  int rc = pio_als_create(&cfg, &h);
+  if (rc) return rc;
+  cudaStream_t st = h->stream;
+  struct { Side* s; size_t n; const uint8_t* has; const float* fac; } jobs[2] = {{&h->U, nu, uh.data(), uf.data()},
+                                                                                {&h->I, ni, ih.data(), itf.data()}};
+  auto body = [&]() -> int {
+    for (auto& j : jobs) {
+      Side& s = *j.s;
+      s.n = (int)j.n;
+      s.R = s.n;
+      s.n_internal = s.n;
+      s.bits = ceil_log2((uint64_t)s.n);
+      CK(h, dalloc(h, &s.perm, j.n)); CK(h, dalloc(h, &s.inv, j.n)); CK(h, dalloc(h, &s.deg, j.n));
+      CK(h, dalloc(h, &s.npos, j.n)); CK(h, dalloc(h, &s.cand_ext, j.n));
+      CK(h, dalloc(h, &s.F, j.n * (size_t)h->KP));
+      uint8_t* dh = nullptr;
+      float* tmp = nullptr;
+      CK(h, dalloc(h, &dh, j.n));
+      CK(h, dalloc(h, &tmp, j.n * k));
+      CK(h, cudaMemcpyAsync(dh, j.has, j.n, cudaMemcpyHostToDevice, st));
+      CK(h, cudaMemcpyAsync(tmp, j.fac, sizeof(float) * j.n * k, cudaMemcpyHostToDevice, st));
+      load_side_kernel<<<nblk(s.n, 256), 256, 0, st>>>(dh, s.n, s.perm, s.inv, s.deg, s.npos);
+      LAUNCHED(h);
+      scatter_init_kernel<<<nblk((long long)s.n * h->KP, 256), 256, 0, st>>>(tmp, s.n, (int)k, h->KP, s.perm, s.deg, s.F);
+      LAUNCHED(h);
+      cand_ext_kernel<<<nblk(s.n, 256), 256, 0, st>>>(s.inv, s.deg, s.n, s.cand_ext);
+      LAUNCHED(h);
+      dfree(h, dh);
+      dfree(h, tmp);
+    }
+    CK(h, cudaStreamSynchronize(st));
+    return PIO_ALS_OK;
+  };
+  rc = body();
+  if (rc) {
+    g_create_error = h->err;
+    pio_als_destroy(h);
+    return rc;
+  }
+  h->trained = true;
+  *out = h;
+  return PIO_ALS_OK;
+}
+
+int pio_als_get_stats(const pio_als_handle* h, pio_als_stats* out) {
+  if (!h || !out) return PIO_ALS_ERR_ARG;
+  *out = h->st;
+  return PIO_ALS_OK;
+}
+
+int pio_als_synth_ratings_device(int device, int32_t n_users, int32_t n_items, int64_t nnz, int64_t seed, int implicit,
+                                 int64_t start, int32_t* d_user, int32_t* d_item, float* d_rating) {
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  if (nnz <= 0) return PIO_ALS_OK;
+  synth_kernel<<<nblk(nnz, 256), 256>>>(n_users, n_items, nnz, (uint64_t)seed, implicit, start, d_user, d_item, d_rating);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "synth kernel: %s", cudaGetErrorString(e));
+  return PIO_ALS_OK;
+}
+
+// ---- NaiveBayes ---------------------------------------------------------------------------------
+#define CK0(call)                                                                                         \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+int pio_nb_train(int device, const int32_t* label, const float* x, int64_t n, int n_feat, int n_class, double lambda,
+                 double* pi, double* theta) {
+  if (!label || !x || !pi || !theta || n <= 0 || n_feat < 1 || n_class < 1)
+    return fail(nullptr, PIO_ALS_ERR_ARG, "bad NaiveBayes arguments");
+  const int width = n_class * (n_feat + 1);
+  if ((size_t)width * 8 * sizeof(double) > 200 * 1024) return fail(nullptr, PIO_ALS_ERR_ARG, "n_class*(n_feat+1) too large");
+  CK0(cudaSetDevice(device));
+  for (int64_t r = 0; r < n; ++r)
+    if (label[r] < 0 || label[r] >= n_class) return fail(nullptr, PIO_ALS_ERR_ARG, "label out of range at row %lld", (long long)r);
+  int* dl = nullptr;
+  float* dx = nullptr;
+  double *dp = nullptr, *dout = nullptr;
+  const int nb = 296;
+  CK0(cudaMalloc((void**)&dl, sizeof(int) * n));
+  CK0(cudaMalloc((void**)&dx, sizeof(float) * n * n_feat));
+  CK0(cudaMalloc((void**)&dp, sizeof(double) * (size_t)nb * width));
+  CK0(cudaMalloc((void**)&dout, sizeof(double) * width));
+  CK0(cudaMemcpy(dl, label, sizeof(int) * n, cudaMemcpyHostToDevice));
+  CK0(cudaMemcpy(dx, x, sizeof(float) * n * n_feat, cudaMemcpyHostToDevice));
+  const size_t smem = sizeof(double) * 8 * width;
+  CK0(cudaFuncSetAttribute(nb_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nb_partial_kernel<<<nb, 256, smem>>>(dl, dx, n, n_feat, n_class, dp);
+  nb_reduce_kernel<<<nblk(width, 128), 128>>>(dp, nb, width, dout);
+  std::vector<double> acc(width);
+  CK0(cudaMemcpy(acc.data(), dout, sizeof(double) * width, cudaMemcpyDeviceToHost));
+  cudaFree(dl); cudaFree(dx); cudaFree(dp); cudaFree(dout);
+  // MLlib multinomial: pi_c = log(n_c + l) - log(N + C l); theta_cj = log(s_cj + l) - log(sum_j s_cj + F l)
+  const double logden = log((double)n + n_class * lambda);
+  for (int c = 0; c < n_class; ++c) {
+    pi[c] = log(acc[c * (n_feat + 1) + n_feat] + lambda) - logden;
+    double tot = 0;
+    for (int j = 0; j < n_feat; ++j) tot += acc[c * (n_feat + 1) + j];
+    const double lt = log(tot + n_feat * lambda);
+    for (int j = 0; j < n_feat; ++j) theta[c * n_feat + j] = log(acc[c * (n_feat + 1) + j] + lambda) - lt;
+  }
+  return PIO_ALS_OK;
+}
+
+int pio_nb_predict(int device, const float* x, int64_t n, int n_feat, int n_class, const double* pi, const double* theta,
+                   int32_t* out_label) {
+  if (!x || !pi || !theta || !out_label || n <= 0) return fail(nullptr, PIO_ALS_ERR_ARG, "bad NaiveBayes arguments");
+  CK0(cudaSetDevice(device));
+  float* dx = nullptr;
+  double *dpi = nullptr, *dth = nullptr;
+  int* dout = nullptr;
+  CK0(cudaMalloc((void**)&dx, sizeof(float) * n * n_feat));
+  CK0(cudaMalloc((void**)&dpi, sizeof(double) * n_class));
+  CK0(cudaMalloc((void**)&dth, sizeof(double) * n_class * n_feat));
+  CK0(cudaMalloc((void**)&dout, sizeof(int) * n));
+  CK0(cudaMemcpy(dx, x, sizeof(float) * n * n_feat, cudaMemcpyHostToDevice));
+  CK0(cudaMemcpy(dpi, pi, sizeof(double) * n_class, cudaMemcpyHostToDevice));
+  CK0(cudaMemcpy(dth, theta, sizeof(double) * n_class * n_feat, cudaMemcpyHostToDevice));
+  nb_predict_kernel<<<nblk(n, 256), 256>>>(dx, n, n_feat, n_class, dpi, dth, dout);
+  CK0(cudaMemcpy(out_label, dout, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dpi); cudaFree(dth); cudaFree(dout);
+  return PIO_ALS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs.  Tolerance (north_star): trained factors within 1e-4 relative of the
+fp64-accumulating reference algorithm; integer/index outputs and fp64-accumulated scores bit-exact.
+"""
+import numpy as np
+import pytest
+
+from pio_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # relative (Frobenius) error of the factor matrices vs the oracle
+
+
+def frob_rel(a, b):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def max_row_rel(a, b):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    nb = np.linalg.norm(b, axis=1)
+    d = np.linalg.norm(a - b, axis=1)
+    return float((d / np.maximum(nb, 1e-3 * nb.max() + 1e-30)).max())
+
+
+def run_both(native, oracle, nu, ni, u, i, r, rank, iters, lam, implicit, alpha, seed=5, dedup=0):
+    u0 = synth.synth_init_factors(nu, rank, seed, 0)
+    i0 = synth.synth_init_factors(ni, rank, seed, 1)
+    m = native.NativeALS(rank, nu, ni, lam=lam, implicit=implicit, alpha=alpha)
+    m.set_ratings(u, i, r, dedup=dedup)
+    m.set_init(u0, i0)
+    m.run(iters)
+    g = m.get_factors()
+    if dedup:
+        uu, ii, rr = oracle.dedup_coo(u, i, r, {1: "sum", 2: "keep_last"}[dedup])
+    else:
+        uu, ii, rr = u, i, r
+    o = oracle.als_train(nu, ni, uu, ii, rr, rank, iters, lam, implicit, alpha, u0, i0)
+    return m, g, o
+
+
+@pytest.mark.parametrize("rank,implicit", [(10, False), (10, True), (64, False), (64, True), (32, True), (20, False),
+                                           (128, True), (100, False), (1, False), (7, True)])
+def test_one_iteration_parity(native, oracle, rank, implicit):
+    nu, ni, nnz = 3000, 400, 60000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=3, implicit=implicit)
+    _, g, o = run_both(native, oracle, nu, ni, u, i, r, rank, 1, 0.01, implicit, 1.0)
+    assert (g[2] == o[2]).all() and (g[3] == o[3]).all()
+    assert frob_rel(g[0], o[0]) <= 2e-5 and frob_rel(g[1], o[1]) <= 2e-5, (frob_rel(g[0], o[0]), frob_rel(g[1], o[1]))
+
+
+@pytest.mark.parametrize("rank,implicit,iters", [(10, False, 20), (64, True, 10), (64, False, 10), (32, True, 10),
+                                                 (128, True, 5)])
+def test_trained_factors_within_tolerance(native, oracle, rank, implicit, iters):
+    nu, ni, nnz = 4000, 600, 120000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=3, implicit=implicit)
+    dedup = 1 if implicit else 2
+    _, g, o = run_both(native, oracle, nu, ni, u, i, r, rank, iters, 0.01, implicit, 1.0, dedup=dedup)
+    eu, ei = frob_rel(g[0], o[0]), frob_rel(g[1], o[1])
+    assert eu <= TOL and ei <= TOL, (eu, ei, max_row_rel(g[0], o[0]), max_row_rel(g[1], o[1]))
+
+
+def test_config_c1_recommendation_template(native, oracle):
+    """BASELINE.json configs[0]: rank 10, 10k x 1k, 100k ratings, explicit, lambda 0.01, 20 iterations, seed 3."""
+    nu, ni, nnz = 10000, 1000, 100000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=3, implicit=False)
+    m, g, o = run_both(native, oracle, nu, ni, u, i, r, 10, 20, 0.01, False, 1.0, seed=3)
+    eu, ei = frob_rel(g[0], o[0]), frob_rel(g[1], o[1])
+    assert eu <= TOL and ei <= TOL, (eu, ei)
+    # predicted scores agree as well
+    pg = np.einsum("ij,ij->i", g[0][u].astype(np.float64), g[1][i].astype(np.float64))
+    po = np.einsum("ij,ij->i", o[0][u].astype(np.float64), o[1][i].astype(np.float64))
+    assert np.abs(pg - po).max() <= 1e-3 * max(1.0, np.abs(po).max())
+
+
+def test_heavy_rows_split_mode(native, oracle):
+    """Items with far more than 4096 ratings take the one-row-per-CTA split path."""
+    nu, ni, nnz = 20000, 40, 400000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=9, implicit=True)
+    _, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 3, 0.05, True, 1.0)
+    assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
+    _, g, o = run_both(native, oracle, nu, ni, u, i, r, 10, 3, 0.05, False, 1.0)
+    assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
+
+
+def test_ragged_and_empty_rows(native, oracle):
+    """Users/items that never occur own no factor (has=0, zero row); duplicates count separately."""
+    nu, ni = 50, 30
+    rng = np.random.default_rng(1)
+    u = rng.integers(0, 25, 400).astype(np.int32) * 2          # odd users never occur
+    i = rng.integers(0, 10, 400).astype(np.int32) * 3          # only every third item occurs
+    r = rng.integers(1, 6, 400).astype(np.float32)
+    u[:20] = u[0]
+    i[:20] = i[0]                                             # 20 duplicates of one pair
+    _, g, o = run_both(native, oracle, nu, ni, u, i, r, 8, 4, 0.1, False, 1.0)
+    assert (g[2] == o[2]).all() and (g[3] == o[3]).all()
+    assert (g[0][g[2] == 0] == 0).all() and (g[1][g[3] == 0] == 0).all()
+    assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
+
+
+def test_single_rating(native, oracle):
+    u = np.array([2], np.int32)
+    i = np.array([1], np.int32)
+    r = np.array([3.0], np.float32)
+    _, g, o = run_both(native, oracle, 4, 3, u, i, r, 5, 2, 0.1, False, 1.0)
+    assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_dedup_modes_match_host_preparation(native, oracle, mode):
+    nu, ni, nnz = 300, 40, 6000   # many repeated pairs
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=21, implicit=(mode == 1))
+    u0 = synth.synth_init_factors(nu, 6, 1, 0)
+    i0 = synth.synth_init_factors(ni, 6, 1, 1)
+    ts = None
+    if mode == 2:
+        ts = np.random.default_rng(3).integers(0, 50, nnz).astype(np.int64)
+    m = native.NativeALS(6, nu, ni, lam=0.05, implicit=(mode == 1), alpha=2.0)
+    m.set_ratings(u, i, r, dedup=mode, ts=ts)
+    m.set_init(u0, i0)
+    m.run(3)
+    g = m.get_factors()
+    uu, ii, rr = oracle.dedup_coo(u, i, r, {1: "sum", 2: "keep_last"}[mode], ts)
+    assert m.stats()["nnz"] == uu.shape[0]
+    o = oracle.als_train(nu, ni, uu, ii, rr, 6, 3, 0.05, mode == 1, 2.0, u0, i0)
+    assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
+
+
+def test_implicit_negative_and_zero_preferences(native, oracle):
+    nu, ni, nnz = 500, 80, 8000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=4, implicit=True)
+    r = r.copy()
+    r[::5] = -r[::5]
+    r[::7] = 0.0
+    _, g, o = run_both(native, oracle, nu, ni, u, i, r, 12, 4, 0.02, True, 0.7)
+    assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
+
+
+def test_run_is_deterministic_and_resumable(native, oracle):
+    nu, ni, nnz = 2000, 300, 40000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=3, implicit=True)
+    u0 = synth.synth_init_factors(nu, 64, 5, 0)
+    outs = []
+    for split in ((4,), (1, 3)):
+        m = native.NativeALS(64, nu, ni, lam=0.01, implicit=True)
+        m.set_ratings(u, i, r)
+        m.set_init(u0)
+        for n in split:
+            m.run(n)
+        outs.append(m.get_factors())
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_recommend_and_similar_are_bit_exact(native, oracle):
+    nu, ni, nnz = 3000, 5000, 50000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=8, implicit=True)
+    m = native.NativeALS(16, nu, ni, lam=0.01, implicit=True)
+    m.set_ratings(u, i, r, dedup=1)
+    m.set_init(synth.synth_init_factors(nu, 16, 2, 0))
+    m.run(3)
+    uf, itf, uh, ih = m.get_factors()
+    users = np.array([0, 1, 17, 2999, int(np.flatnonzero(uh == 0)[0]) if (uh == 0).any() else 5, -1], np.int32)
+    mask = (np.arange(ni) % 13 == 0).astype(np.uint8)
+    for mk in (None, mask):
+        gi, gs, gc = m.recommend(users, 10, mk)
+        oi, os_, oc = oracle.recommend(uf, uh, itf, ih, users, 10, mk)
+        assert np.array_equal(gi, oi) and np.array_equal(gs, os_) and np.array_equal(gc, oc)
+    have = np.flatnonzero(ih)
+    miss = np.flatnonzero(ih == 0)
+    for q in ([int(have[0])], [int(have[3]), int(have[10]), int(have[50])],
+              [int(have[1]), int(miss[0])] if miss.size else [int(have[1])], [int(miss[0])] if miss.size else []):
+        q = np.array(q, np.int32)
+        for mk in (None, mask):
+            gi, gs, gc = m.similar(q, 20, mk)
+            oi, os_, oc = oracle.similar(itf, ih, q, 20, mk)
+            assert np.array_equal(gi, oi) and np.array_equal(gs, os_) and gc == oc
+
+
+def test_save_load_round_trip(native, oracle, tmp_path):
+    nu, ni, nnz = 800, 200, 9000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=8, implicit=False)
+    m = native.NativeALS(10, nu, ni, lam=0.01)
+    m.set_ratings(u, i, r)
+    m.set_init(synth.synth_init_factors(nu, 10, 2, 0))
+    m.run(2)
+    p = tmp_path / "model.pioals"
+    m.save(p)
+    m2 = native.NativeALS.load(p)
+    a, b = m.get_factors(), m2.get_factors()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    users = np.arange(20, dtype=np.int32)
+    ra, rb = m.recommend(users, 5), m2.recommend(users, 5)
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x, y)
+
+
+def test_error_behaviour(native):
+    m = native.NativeALS(8, 10, 10)
+    with pytest.raises(native.NativeError) as ei:
+        m.run(1)
+    assert ei.value.code == native.ERR_STATE
+    with pytest.raises(native.NativeError) as ei:
+        m.set_ratings(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32))
+    assert ei.value.code == native.ERR_ARG          # the templates' require(!ratings.isEmpty)
+    with pytest.raises(native.NativeError) as ei:
+        m.set_ratings(np.array([10], np.int32), np.array([0], np.int32), np.array([1], np.float32))
+    assert ei.value.code == native.ERR_ARG
+    m.set_ratings(np.array([1], np.int32), np.array([0], np.int32), np.array([1], np.float32))
+    with pytest.raises(native.NativeError) as ei:
+        m.run(1)                                     # no initial factors supplied
+    assert ei.value.code == native.ERR_STATE
+
+
+def test_device_generator_matches_host(native):
+    import torch
+    nu, ni, nnz = 100000, 7000, 300000
+    for implicit in (False, True):
+        du = torch.empty(nnz, dtype=torch.int32, device="cuda")
+        di = torch.empty(nnz, dtype=torch.int32, device="cuda")
+        dr = torch.empty(nnz, dtype=torch.float32, device="cuda")
+        native.synth_ratings_device(0, nu, ni, nnz, 3, implicit, 12345, du.data_ptr(), di.data_ptr(), dr.data_ptr())
+        hu, hi, hr = synth.synth_ratings(nu, ni, nnz, seed=3, implicit=implicit, start=12345)
+        assert np.array_equal(du.cpu().numpy(), hu) and np.array_equal(di.cpu().numpy(), hi)
+        assert np.array_equal(dr.cpu().numpy(), hr)
+
+
+def test_device_resident_ratings_equal_host_ratings(native):
+    import torch
+    nu, ni, nnz = 5000, 700, 80000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=3, implicit=True)
+    u0 = synth.synth_init_factors(nu, 64, 5, 0)
+    a = native.NativeALS(64, nu, ni, implicit=True)
+    a.set_ratings(u, i, r, dedup=1)
+    a.set_init(u0)
+    a.run(2)
+    b = native.NativeALS(64, nu, ni, implicit=True)
+    tu, ti, tr = (torch.from_numpy(x).cuda() for x in (u, i, r))
+    b.set_ratings_device(tu.data_ptr(), ti.data_ptr(), tr.data_ptr(), nnz, dedup=1)
+    b.set_init(u0)
+    b.run(2)
+    for x, y in zip(a.get_factors(), b.get_factors()):
+        assert np.array_equal(x, y)
+
+
+def test_naive_bayes_parity(native, oracle):
+    rng = np.random.default_rng(0)
+    n = 200000
+    y = rng.integers(0, 4, n).astype(np.int32)
+    x = rng.integers(0, 10, (n, 3)).astype(np.float32)
+    pi, theta = native.nb_train(y, x, 4, 1.0)
+    opi, otheta = oracle.nb_train(y, x, 4, 1.0)
+    assert np.array_equal(pi, opi) and np.array_equal(theta, otheta)
+    assert np.array_equal(native.nb_predict(x, pi, theta), oracle.nb_predict(x, opi, otheta))
