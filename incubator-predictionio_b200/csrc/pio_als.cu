@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <deque>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -323,7 +324,7 @@ struct pio_als_handle {
   ncclComm_t comm = nullptr;
   std::string err;
   pio_als_stats st{};
-  std::vector<EvPair> ev_pool;
+  std::deque<EvPair> ev_pool;  // deque: references stay valid while the pool grows
   size_t ev_used = 0;
   std::mutex mu;
   int sm_count = 0;

@@ -49,7 +49,11 @@ def test_one_iteration_parity(native, oracle, rank, implicit):
     u, i, r = synth.synth_ratings(nu, ni, nnz, seed=3, implicit=implicit)
     _, g, o = run_both(native, oracle, nu, ni, u, i, r, rank, 1, 0.01, implicit, 1.0)
     assert (g[2] == o[2]).all() and (g[3] == o[3]).all()
-    assert frob_rel(g[0], o[0]) <= 2e-5 and frob_rel(g[1], o[1]) <= 2e-5, (frob_rel(g[0], o[0]), frob_rel(g[1], o[1]))
+    # implicit systems carry YtY and are well conditioned: one half-step agrees to ~1e-6.  Explicit,
+    # lambda=0.01 with fewer ratings than the rank is ill conditioned (cond ~ 1e3..1e4): fp32 normal
+    # equations then sit within, not far below, the stated 1e-4 tolerance.
+    tol = 2e-5 if (implicit or rank <= 20) else TOL
+    assert frob_rel(g[0], o[0]) <= tol and frob_rel(g[1], o[1]) <= tol, (frob_rel(g[0], o[0]), frob_rel(g[1], o[1]))
 
 
 @pytest.mark.parametrize("rank,implicit,iters", [(10, False, 20), (64, True, 10), (64, False, 10), (32, True, 10),
