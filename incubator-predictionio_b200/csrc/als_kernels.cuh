@@ -90,9 +90,27 @@ __device__ __forceinline__ int f4slot(int cg) {
   return cg;
 }
 
+// inverse of f4slot: which source column group lands in staged slot sl
+template <int TB, int NB>
+__device__ __forceinline__ int f4cg(int sl) {
+  if (TB == 8) return ((sl % NB) << 1) | (sl / NB);
+  return sl;
+}
+
 // ------------------------------------------------------------------------------------------
 // Warp Cholesky + solve for N <= 64 (N = KP). Matrix comes from `slot` (upper-triangular TBxTB
 // blocks, block (bi,bj) at ((bi*NB - bi*(bi-1)/2) + bj - bi) * BLK, element [a][b] at a*TB+b).
+//
+// 2x2 blocked, H = N/2, lane l < H owns row l (top) and row H+l (bottom):
+//   A: right-looking Cholesky of [A11; A21] (rows in registers, pivots by shuffle, the scaled
+//      column through a double-buffered shared line), forward substitution of b fused in;
+//   B: A22 -= L21 L21^T as H dot products per lane (own L21 row in registers, the other rows
+//      broadcast from shared memory);
+//   C: Cholesky of A22 as in A;
+//   then back substitution reading L (packed) from shared memory.
+// Deferring the A22 update keeps at most 2*H row registers live (no local-memory spills).
+// L is written over the slot: L11 packed at 0, L21 dense (row stride H+4) after it, L22 packed
+// behind; the layout never overwrites a block that is still to be read (static_asserts below).
 // ------------------------------------------------------------------------------------------
 template <int N, int TB, int BLK, bool IMPLICIT>
 __device__ __forceinline__ void chol_solve_warp(float* slot, const float* bvec, const float* yty,
@@ -100,100 +118,148 @@ __device__ __forceinline__ void chol_solve_warp(float* slot, const float* bvec, 
                                                 float* dst_row, int* fail) {
   constexpr int H = N / 2;
   constexpr int NB = N / TB;
+  constexpr int L21S = H + 4;
+  constexpr int OFF21 = H * (H + 1) / 2;
+  constexpr int OFF22 = OFF21 + H * L21S;
+  constexpr int A22_FIRST = ((NB / 2) * NB - (NB / 2) * (NB / 2 - 1) / 2) * BLK;
+  static_assert(OFF22 <= A22_FIRST, "L11/L21 would overwrite unread A22 blocks");
+  static_assert(OFF22 + H * (H + 1) / 2 <= (NB * (NB + 1) / 2) * BLK, "L does not fit in the slot");
+  static_assert(H % 4 == 0, "H must be a multiple of 4");
   const int lane = threadIdx.x & 31;
   const bool act = lane < H;
   const int l = act ? lane : 0;
-  const int rA = l, rB = N - 1 - l;
-  float ra[H], rb[N];
-  {
-    const int ibA = rA / TB, bA = rA % TB, ibB = rB / TB, bB = rB % TB;
+  const int rA = l, rB = H + l;
+  const int ibA = rA / TB, bA_ = rA % TB, ibB = rB / TB, bB_ = rB % TB;
+  auto cbase = [](int c) { return ((c / TB) * NB - (c / TB) * ((c / TB) - 1) / 2 - (c / TB)) * BLK + (c % TB) * TB; };
+
+  float ra[H], rm[H];
 #pragma unroll
-    for (int c = 0; c < N; ++c) {
-      constexpr int dummy = 0;
-      (void)dummy;
-      const int cb = c / TB, a = c % TB;
-      const int base = (cb * NB - cb * (cb - 1) / 2 - cb) * BLK + a * TB;
-      if (c < H) {
-        float v = 0.f;
-        if (c <= rA) {
-          v = slot[base + ibA * BLK + bA];
-          if (IMPLICIT) v += yty[rA * N + c];
-          if (c == rA) v += ridge + (rA >= k ? 1.f : 0.f);
-        }
-        ra[c] = v;
-      }
-      float v = 0.f;
-      if (c <= rB) {
-        v = slot[base + ibB * BLK + bB];
-        if (IMPLICIT) v += yty[rB * N + c];
-        if (c == rB) v += ridge + (rB >= k ? 1.f : 0.f);
-      }
-      rb[c] = v;
+  for (int c = 0; c < H; ++c) {
+    float v = 0.f;
+    if (c <= rA) {
+      v = slot[cbase(c) + ibA * BLK + bA_];
+      if (IMPLICIT) v += yty[rA * N + c];
+      if (c == rA) v += ridge + (rA >= k ? 1.f : 0.f);
     }
+    ra[c] = v;
+    float w = slot[cbase(c) + ibB * BLK + bB_];
+    if (IMPLICIT) w += yty[rB * N + c];
+    rm[c] = w;
   }
   float bAv = bvec[rA], bBv = bvec[rB];
   float yA = 0.f, yB = 0.f;
   bool bad = false;
   __syncwarp();
+  // ---- phase A ----
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
+  for (int j = 0; j < H; ++j) {
     float* cb_ = colbuf + (j & 1) * N;
-    const float d = (j < H) ? __shfl_sync(0xffffffffu, ra[j < H ? j : 0], j < H ? j : 0)
-                            : __shfl_sync(0xffffffffu, rb[j], N - 1 - j);
-    const float bj = (j < H) ? __shfl_sync(0xffffffffu, bAv, j < H ? j : 0)
-                             : __shfl_sync(0xffffffffu, bBv, N - 1 - j);
+    const float d = __shfl_sync(0xffffffffu, ra[j], j);
+    const float bj = __shfl_sync(0xffffffffu, bAv, j);
     float dd = d;
     if (!(dd > 0.f)) { bad = true; dd = 1.f; }
     float inv = rsqrtf(dd);
     inv = inv * (1.5f - 0.5f * dd * inv * inv);
     const float yj = bj * inv;
-    float la = 0.f;
-    if (j < H) {
-      la = ra[j < H ? j : 0] * inv;
-      ra[j < H ? j : 0] = la;
-    }
-    const float lb = rb[j] * inv;
-    rb[j] = lb;
-    if (act) {
-      if (j < H) cb_[rA] = la;
-      cb_[rB] = lb;
-    }
+    const float la = ra[j] * inv;
+    const float lm = rm[j] * inv;
+    ra[j] = la;
+    rm[j] = lm;
+    if (act) cb_[rA] = la;
     if (lane == 0) dinv[j] = inv;
-    if (j < H && rA == j) yA = yj;
-    if (rB == j) yB = yj;
+    if (rA == j) yA = yj;
     bAv -= la * yj;
-    bBv -= lb * yj;
+    bBv -= lm * yj;
     __syncwarp();
 #pragma unroll
-    for (int c = j + 1; c < N; ++c) {
+    for (int c = j + 1; c < H; ++c) {
       const float x = cb_[c];
-      rb[c] -= lb * x;
-      if (c < H) ra[c < H ? c : 0] -= la * x;
+      ra[c] -= la * x;
+      rm[c] -= lm * x;
     }
   }
-  // L rows -> shared (packed lower, row i at i(i+1)/2), reusing the slot
   __syncwarp();
+  float* L21 = slot + OFF21;
   if (act) {
 #pragma unroll
-    for (int c = 0; c < N; ++c) {
-      if (c < H && c <= rA) slot[rA * (rA + 1) / 2 + c] = ra[c < H ? c : 0];
-      if (c <= rB) slot[rB * (rB + 1) / 2 + c] = rb[c];
+    for (int c = 0; c < H; ++c)
+      if (c <= rA) slot[rA * (rA + 1) / 2 + c] = ra[c];
+#pragma unroll
+    for (int c = 0; c < H; c += 4)
+      *reinterpret_cast<float4*>(L21 + l * L21S + c) = make_float4(rm[c], rm[c + 1], rm[c + 2], rm[c + 3]);
+  }
+  // ---- phase B ----
+  float r2[H];
+#pragma unroll
+  for (int c = 0; c < H; ++c) {
+    float v = 0.f;
+    if (c <= l) {
+      v = slot[cbase(H + c) + ibB * BLK + bB_];
+      if (IMPLICIT) v += yty[rB * N + H + c];
+      if (c == l) v += ridge + (rB >= k ? 1.f : 0.f);
     }
+    r2[c] = v;
   }
   __syncwarp();
+#pragma unroll
+  for (int c = 0; c < H; ++c) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const float4* row = reinterpret_cast<const float4*>(L21 + c * L21S);
+#pragma unroll
+    for (int t = 0; t < H; t += 4) {
+      const float4 x = row[t / 4];
+      s0 = fmaf(rm[t], x.x, s0);
+      s1 = fmaf(rm[t + 1], x.y, s1);
+      s2 = fmaf(rm[t + 2], x.z, s2);
+      s3 = fmaf(rm[t + 3], x.w, s3);
+    }
+    r2[c] -= (s0 + s1) + (s2 + s3);
+  }
+  // ---- phase C ----
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    float* cb_ = colbuf + (j & 1) * N;
+    const float d = __shfl_sync(0xffffffffu, r2[j], j);
+    const float bj = __shfl_sync(0xffffffffu, bBv, j);
+    float dd = d;
+    if (!(dd > 0.f)) { bad = true; dd = 1.f; }
+    float inv = rsqrtf(dd);
+    inv = inv * (1.5f - 0.5f * dd * inv * inv);
+    const float yj = bj * inv;
+    const float l2 = r2[j] * inv;
+    r2[j] = l2;
+    if (act) cb_[l] = l2;
+    if (lane == 0) dinv[H + j] = inv;
+    if (l == j) yB = yj;
+    bBv -= l2 * yj;
+    __syncwarp();
+#pragma unroll
+    for (int c = j + 1; c < H; ++c) r2[c] -= l2 * cb_[c];
+  }
+  __syncwarp();
+  float* L22 = slot + OFF22;
+  if (act) {
+#pragma unroll
+    for (int c = 0; c < H; ++c)
+      if (c <= l) L22[l * (l + 1) / 2 + c] = r2[c];
+  }
+  __syncwarp();
+  // ---- back substitution: L^T x = y ----
   float xA = 0.f, xB = 0.f;
 #pragma unroll
-  for (int i = N - 1; i >= 0; --i) {
-    const float yi = (i < H) ? __shfl_sync(0xffffffffu, yA, i < H ? i : 0)
-                             : __shfl_sync(0xffffffffu, yB, N - 1 - i);
-    const float xi = yi * dinv[i];
-    if (rA == i) xA = xi;
-    if (rB == i) xB = xi;
-    const float* Li = slot + i * (i + 1) / 2;
+  for (int i = H - 1; i >= 0; --i) {  // bottom rows H+i
+    const float xi = __shfl_sync(0xffffffffu, yB, i) * dinv[H + i];
+    if (l == i) xB = xi;
     if (act) {
-      if (rA < i) yA -= Li[rA] * xi;
-      if (rB < i) yB -= Li[rB] * xi;
+      if (l < i) yB -= L22[i * (i + 1) / 2 + l] * xi;
+      yA -= L21[i * L21S + l] * xi;
     }
+  }
+#pragma unroll
+  for (int i = H - 1; i >= 0; --i) {  // top rows i
+    const float xi = __shfl_sync(0xffffffffu, yA, i) * dinv[i];
+    if (l == i) xA = xi;
+    if (act && l < i) yA -= slot[i * (i + 1) / 2 + l] * xi;
   }
   if (act) {
     dst_row[rA] = xA;
@@ -383,14 +449,17 @@ als_solve_kernel(const SolveParams p) {
     for (int j = 0; j < NF; ++j) {
       const int f = tid + j * NT;
       if (f < STAGE_F4 && c < nchunks) {
-        const int q = f / F4ROW, cg = f % F4ROW;
-        float4* d4 = reinterpret_cast<float4*>(sbuf) + q * F4ROW + f4slot<TB, NB>(cg);
+        // consecutive threads fill consecutive 16 B slots of the staged row (conflict-free);
+        // the slot -> source column-group map is the inverse of f4slot
+        const int q = f / F4ROW, sl = f % F4ROW;
+        const int cg = f4cg<TB, NB>(sl);
+        float4* d4 = reinterpret_cast<float4*>(sbuf) + f;
         if (nidx[j] >= 0) {
           cp_async16(d4, p.src + (size_t)nidx[j] * KP + cg * 4);
         } else {
           *d4 = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (cg == 0) mv[q] = nval[j];
+        if (sl == 0) mv[q] = nval[j];
       }
     }
     cp_async_commit();
@@ -423,8 +492,8 @@ als_solve_kernel(const SolveParams p) {
     for (int j = 0; j < NF; ++j) {
       const int f = tid + j * NT;
       if (f < STAGE_F4) {
-        const int q = f / F4ROW, cg = f % F4ROW;
-        const int o4 = q * F4ROW + f4slot<TB, NB>(cg);
+        const int q = f / F4ROW;
+        const int o4 = f;
         const float r = mv[q];
         float4 y = reinterpret_cast<float4*>(sbuf)[o4];
         float wb, sc;

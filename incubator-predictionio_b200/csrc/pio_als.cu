@@ -314,6 +314,8 @@ struct pio_als_handle {
   pio_als_config cfg;
   int KP = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // heavy-row solve kernel runs here, concurrently with the light one
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   Side U, I;
   float* yty = nullptr;
   double* gram_partial = nullptr;
@@ -583,7 +585,7 @@ static int init_hash(pio_als_handle* h) {
 
 // ---- solve dispatch ---------------------------------------------------------------------------
 template <class Cfg, bool IMPLICIT, bool HEAVY>
-static cudaError_t launch_solve_one(pio_als_handle* h, const SolveParams& p, int grid) {
+static cudaError_t launch_solve_one(pio_als_handle* h, const SolveParams& p, int grid, cudaStream_t st) {
   static bool attr_set[64] = {};
   int dev = h->cfg.device;
   auto kern = als_solve_kernel<Cfg, IMPLICIT, HEAVY>;
@@ -593,7 +595,7 @@ static cudaError_t launch_solve_one(pio_als_handle* h, const SolveParams& p, int
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  kern<<<grid, Cfg::NT, smem, h->stream>>>(p);
+  kern<<<grid, Cfg::NT, smem, st>>>(p);
   LAUNCHED(h);
   ++h->st.solve_launches;
   return cudaGetLastError();
@@ -616,19 +618,30 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
   p.dst_row_offset = h->cfg.world_rank * dst.R;
   const bool imp = h->cfg.implicit_prefs != 0;
   cudaError_t e = cudaSuccess;
+  // the few very long rows go to stream2 so their long-running CTAs overlap the light batches
+  const bool fork = dst.n_heavy > 0 && dst.n_active > dst.n_heavy;
   if (dst.n_heavy > 0) {
     p.row_begin = 0;
     p.row_end = dst.n_heavy;
-    e = imp ? launch_solve_one<Cfg, true, true>(h, p, dst.n_heavy) : launch_solve_one<Cfg, false, true>(h, p, dst.n_heavy);
+    cudaStream_t hs = h->stream;
+    if (fork) {
+      if ((e = cudaEventRecord(h->ev_fork, h->stream)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(h->stream2, h->ev_fork, 0)) != cudaSuccess) return e;
+      hs = h->stream2;
+    }
+    e = imp ? launch_solve_one<Cfg, true, true>(h, p, dst.n_heavy, hs) : launch_solve_one<Cfg, false, true>(h, p, dst.n_heavy, hs);
     if (e != cudaSuccess) return e;
+    if (fork && (e = cudaEventRecord(h->ev_join, h->stream2)) != cudaSuccess) return e;
   }
   const int nlight = dst.n_active - dst.n_heavy;
   if (nlight > 0) {
     p.row_begin = dst.n_heavy;
     p.row_end = dst.n_active;
     const int grid = (nlight + Cfg::NG - 1) / Cfg::NG;
-    e = imp ? launch_solve_one<Cfg, true, false>(h, p, grid) : launch_solve_one<Cfg, false, false>(h, p, grid);
+    e = imp ? launch_solve_one<Cfg, true, false>(h, p, grid, h->stream) : launch_solve_one<Cfg, false, false>(h, p, grid, h->stream);
+    if (e != cudaSuccess) return e;
   }
+  if (fork) e = cudaStreamWaitEvent(h->stream, h->ev_join, 0);
   return e;
 }
 
@@ -735,7 +748,10 @@ static int create_common(pio_als_handle* h) {
   h->sm_count = pr.multiProcessorCount;
   h->st.sm_count = pr.multiProcessorCount;
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaSetDevice");
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
     return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaStreamCreate");
   // keep freed blocks in the pool (ingest allocates and frees multi-GB scratch repeatedly)
   cudaMemPool_t pool;
@@ -801,6 +817,9 @@ void pio_als_destroy(pio_als_handle* h) {
       cudaEventDestroy(e.b);
     }
     if (h->comm) nccl_api().CommDestroy(h->comm);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     cudaStreamDestroy(h->stream);
   }
   delete h;
