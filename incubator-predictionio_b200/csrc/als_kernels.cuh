@@ -112,7 +112,9 @@ __device__ __forceinline__ int f4cg(int sl) {
 // L is written over the slot: L11 packed at 0, L21 dense (row stride H+4) after it, L22 packed
 // behind; the layout never overwrites a block that is still to be read (static_asserts below).
 // ------------------------------------------------------------------------------------------
-template <int N, int TB, int BLK, bool IMPLICIT>
+// PACKED_IN = true: the matrix arrives already in the L layout (A11 packed lower at 0, A21 dense with
+// row stride H+4 at OFF21, A22 packed lower at OFF22) and is factorised in place (tensor-core path).
+template <int N, int TB, int BLK, bool IMPLICIT, bool PACKED_IN = false>
 __device__ __forceinline__ void chol_solve_warp(float* slot, const float* bvec, const float* yty,
                                                 float ridge, int k, float* colbuf, float* dinv,
                                                 float* dst_row, int* fail) {
@@ -122,8 +124,8 @@ __device__ __forceinline__ void chol_solve_warp(float* slot, const float* bvec, 
   constexpr int OFF21 = H * (H + 1) / 2;
   constexpr int OFF22 = OFF21 + H * L21S;
   constexpr int A22_FIRST = ((NB / 2) * NB - (NB / 2) * (NB / 2 - 1) / 2) * BLK;
-  static_assert(OFF22 <= A22_FIRST, "L11/L21 would overwrite unread A22 blocks");
-  static_assert(OFF22 + H * (H + 1) / 2 <= (NB * (NB + 1) / 2) * BLK, "L does not fit in the slot");
+  static_assert(PACKED_IN || OFF22 <= A22_FIRST, "L11/L21 would overwrite unread A22 blocks");
+  static_assert(PACKED_IN || OFF22 + H * (H + 1) / 2 <= (NB * (NB + 1) / 2) * BLK, "L does not fit in the slot");
   static_assert(H % 4 == 0, "H must be a multiple of 4");
   const int lane = threadIdx.x & 31;
   const bool act = lane < H;
@@ -137,12 +139,12 @@ __device__ __forceinline__ void chol_solve_warp(float* slot, const float* bvec, 
   for (int c = 0; c < H; ++c) {
     float v = 0.f;
     if (c <= rA) {
-      v = slot[cbase(c) + ibA * BLK + bA_];
+      v = PACKED_IN ? slot[rA * (rA + 1) / 2 + c] : slot[cbase(c) + ibA * BLK + bA_];
       if (IMPLICIT) v += yty[rA * N + c];
       if (c == rA) v += ridge + (rA >= k ? 1.f : 0.f);
     }
     ra[c] = v;
-    float w = slot[cbase(c) + ibB * BLK + bB_];
+    float w = PACKED_IN ? slot[OFF21 + l * L21S + c] : slot[cbase(c) + ibB * BLK + bB_];
     if (IMPLICIT) w += yty[rB * N + c];
     rm[c] = w;
   }
@@ -194,7 +196,7 @@ __device__ __forceinline__ void chol_solve_warp(float* slot, const float* bvec, 
   for (int c = 0; c < H; ++c) {
     float v = 0.f;
     if (c <= l) {
-      v = slot[cbase(H + c) + ibB * BLK + bB_];
+      v = PACKED_IN ? slot[OFF22 + l * (l + 1) / 2 + c] : slot[cbase(H + c) + ibB * BLK + bB_];
       if (IMPLICIT) v += yty[rB * N + H + c];
       if (c == l) v += ridge + (rB >= k ? 1.f : 0.f);
     }

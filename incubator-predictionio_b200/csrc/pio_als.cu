@@ -10,6 +10,7 @@
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <deque>
@@ -18,12 +19,14 @@
 #include <vector>
 
 #include "als_kernels.cuh"
+#include "als_tc_kernel.cuh"
 #include "sort_scan.cuh"
 #include "topk.cuh"
 
 namespace pio {
 
-constexpr int HEAVY_T = 4096;  // rows with more ratings than this are solved one per CTA (split mode)
+constexpr int HEAVY_T = 4096;     // FP32 path: rows with more ratings than this are solved one per CTA (split mode)
+constexpr int HEAVY_T_TC = 8192;  // tensor-core path (rank 33..64): longer rows stay on the FP32 split kernel
 
 static thread_local std::string g_create_error;
 
@@ -133,7 +136,8 @@ __global__ void degree_keys_kernel(const uint32_t* deg, int n, uint64_t* keys, u
 // sorted position p -> internal id: rows are dealt to ranks in snake order so every rank gets
 // the same number of rows and a near-equal share of the ratings; a rank's rows stay
 // degree-descending.
-__global__ void assign_internal_kernel(const uint32_t* order, int n, int W, int R, int* perm, int* inv) {
+__global__ void assign_internal_kernel(const uint32_t* order, int n, int W, int R, int* perm, int* inv, int* rpos,
+                                       int* p2i) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const int row = (int)order[p];
@@ -142,16 +146,22 @@ __global__ void assign_internal_kernel(const uint32_t* order, int n, int W, int 
   const int internal = rk * R + blk;
   perm[row] = internal;
   inv[internal] = row;
+  rpos[row] = p;       // degree-rank position: independent of the number of GPUs
+  p2i[p] = internal;
 }
+__global__ void set_int_kernel(int* a, int v) { *a = v; }
 __global__ void fill_int_kernel(int* a, long long n, int v) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) a[e] = v;
 }
+// key = (internal row, degree-rank position of the column): inside a row the ratings are ordered by a
+// quantity that does not depend on the sharding, so the fp32 summation order -- and hence every bit of the
+// result -- is the same on 1, 2, 4 or 8 GPUs.
 __global__ void make_keys_int_kernel(const int* rowext, const int* colext, long long n, const int* perm_row,
-                                     const int* perm_col, int bits_col, uint64_t* keys, uint32_t* pay) {
+                                     const int* rpos_col, int bits_col, uint64_t* keys, uint32_t* pay) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) {
-    keys[e] = ((uint64_t)(uint32_t)perm_row[rowext[e]] << bits_col) | (uint64_t)(uint32_t)perm_col[colext[e]];
+    keys[e] = ((uint64_t)(uint32_t)perm_row[rowext[e]] << bits_col) | (uint64_t)(uint32_t)rpos_col[colext[e]];
     pay[e] = (uint32_t)e;
   }
 }
@@ -165,10 +175,10 @@ __global__ void build_ptr_kernel(const uint64_t* keys, long long n, int bits_col
     for (int rr = r + 1; rr <= n_rows; ++rr) ptr[rr] = n;
 }
 __global__ void extract_csr_kernel(const uint64_t* keys, const uint32_t* pay, const float* rating, long long b,
-                                   long long cnt, int bits_col, int* idx, float* val) {
+                                   long long cnt, int bits_col, const int* p2i_col, int* idx, float* val) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= cnt) return;
-  idx[t] = (int)(keys[b + t] & ((1ull << bits_col) - 1ull));
+  idx[t] = p2i_col[(int)(keys[b + t] & ((1ull << bits_col) - 1ull))];
   val[t] = rating[pay[b + t]];
 }
 __global__ void local_rows_kernel(const long long* ptr_full, int row0, int R, long long base, const int* inv,
@@ -286,8 +296,10 @@ struct Side {
   int R = 0;           // rows owned per rank
   int n_internal = 0;  // world * R
   int bits = 1;        // bits of an internal id
-  int* perm = nullptr;       // [n]
+  int* perm = nullptr;       // [n] external row -> internal id
   int* inv = nullptr;        // [n_internal]
+  int* rpos = nullptr;       // [n] external row -> degree-rank position
+  int* p2i = nullptr;        // [n] degree-rank position -> internal id
   uint32_t* deg = nullptr;   // [n]
   uint32_t* npos = nullptr;  // [n]
   long long* ptr = nullptr;  // [R+1]
@@ -322,6 +334,11 @@ struct pio_als_handle {
   int gram_blocks = 0;
   int* d_fail = nullptr;
   int* d_counts = nullptr;
+  int* d_counter = nullptr;   // row-claim counter of the tensor-core solve kernel
+  float* d_dbg = nullptr;     // PIO_ALS_TC_DEBUG=1: A/b dump of the last tensor-core half-step
+  size_t dbg_rows = 0;
+  bool use_tc = false;        // rank in 33..64 and PIO_ALS_TC != 0
+  int heavy_t = 0;
   bool have_ratings = false, have_init = false, trained = false;
   ncclComm_t comm = nullptr;
   std::string err;
@@ -366,7 +383,7 @@ static void dfree(pio_als_handle* h, T*& p) {
 }
 
 static void free_side(pio_als_handle* h, Side& s, bool keep_factors) {
-  dfree(h, s.perm); dfree(h, s.inv); dfree(h, s.deg); dfree(h, s.npos); dfree(h, s.ptr);
+  dfree(h, s.perm); dfree(h, s.inv); dfree(h, s.rpos); dfree(h, s.p2i); dfree(h, s.deg); dfree(h, s.npos); dfree(h, s.ptr);
   dfree(h, s.idx); dfree(h, s.val); dfree(h, s.nreg); dfree(h, s.cand_ext);
   if (!keep_factors) dfree(h, s.F);
 }
@@ -389,7 +406,7 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
                       const float* rating, long long nnz, uint64_t* ka, uint32_t* va, uint64_t* kb, uint32_t* vb) {
   cudaStream_t st = h->stream;
   const int W = h->cfg.world_size, rk = h->cfg.world_rank;
-  make_keys_int_kernel<<<nblk(nnz, 256), 256, 0, st>>>(rowext, colext, nnz, row.perm, col.perm, col.bits, ka, va);
+  make_keys_int_kernel<<<nblk(nnz, 256), 256, 0, st>>>(rowext, colext, nnz, row.perm, col.rpos, col.bits, ka, va);
   LAUNCHED(h);
   bool in_b = false;
   CK(h, radix_sort_pairs(ka, va, kb, vb, (size_t)nnz, row.bits + col.bits, st, &in_b, &h->st.kernel_launches));
@@ -412,13 +429,13 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
   CK(h, dalloc(h, &row.nreg, (size_t)row.R));
   if (row.nnz_local > 0) {
     extract_csr_kernel<<<nblk(row.nnz_local, 256), 256, 0, st>>>(ks, vs, rating, be[0], row.nnz_local, col.bits,
-                                                                 row.idx, row.val);
+                                                                 col.p2i, row.idx, row.val);
     LAUNCHED(h);
   }
   CK(h, cudaMemsetAsync(h->d_counts, 0, 2 * sizeof(int), st));
   local_rows_kernel<<<nblk(row.R + 1, 256), 256, 0, st>>>(ptr_full, rk * row.R, row.R, be[0], row.inv, row.deg,
                                                            row.npos, h->cfg.implicit_prefs, row.ptr, row.nreg,
-                                                           h->d_counts, HEAVY_T);
+                                                           h->d_counts, h->heavy_t);
   LAUNCHED(h);
   int counts[2];
   CK(h, cudaMemcpyAsync(counts, h->d_counts, sizeof counts, cudaMemcpyDeviceToHost, st));
@@ -438,7 +455,8 @@ static int rank_rows(pio_als_handle* h, Side& s, uint64_t* ka, uint32_t* va, uin
   CK(h, radix_sort_pairs(ka, va, kb, vb, (size_t)s.n, 32, st, &in_b, &h->st.kernel_launches));
   fill_int_kernel<<<nblk(s.n_internal, 256), 256, 0, st>>>(s.inv, s.n_internal, -1);
   LAUNCHED(h);
-  assign_internal_kernel<<<nblk(s.n, 256), 256, 0, st>>>(in_b ? vb : va, s.n, h->cfg.world_size, s.R, s.perm, s.inv);
+  assign_internal_kernel<<<nblk(s.n, 256), 256, 0, st>>>(in_b ? vb : va, s.n, h->cfg.world_size, s.R, s.perm, s.inv,
+                                                         s.rpos, s.p2i);
   LAUNCHED(h);
   return PIO_ALS_OK;
 }
@@ -524,6 +542,8 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
     CK(h, dalloc(h, &s->npos, (size_t)s->n));
     CK(h, dalloc(h, &s->perm, (size_t)s->n));
     CK(h, dalloc(h, &s->inv, (size_t)s->n_internal));
+    CK(h, dalloc(h, &s->rpos, (size_t)s->n));
+    CK(h, dalloc(h, &s->p2i, (size_t)s->n));
     CK(h, cudaMemsetAsync(s->deg, 0, sizeof(uint32_t) * s->n, st));
     CK(h, cudaMemsetAsync(s->npos, 0, sizeof(uint32_t) * s->n, st));
   }
@@ -637,9 +657,43 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
   if (nlight > 0) {
     p.row_begin = dst.n_heavy;
     p.row_end = dst.n_active;
-    const int grid = (nlight + Cfg::NG - 1) / Cfg::NG;
-    e = imp ? launch_solve_one<Cfg, true, false>(h, p, grid, h->stream) : launch_solve_one<Cfg, false, false>(h, p, grid, h->stream);
-    if (e != cudaSuccess) return e;
+    if (h->use_tc && Cfg::KP == 64) {
+      // Gramian on tcgen05 (als_tc_kernel.cuh): persistent, one CTA per SM, rows claimed dynamically
+      static bool attr_set[64] = {};
+      const size_t smem = sizeof(tc::Smem) + 1024;
+      auto kern = imp ? tc::als_solve_tc_kernel<true> : tc::als_solve_tc_kernel<false>;
+      if (h->cfg.device < 64 && !attr_set[h->cfg.device]) {
+        if ((e = cudaFuncSetAttribute(tc::als_solve_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(tc::als_solve_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        attr_set[h->cfg.device] = true;
+      }
+      set_int_kernel<<<1, 1, 0, h->stream>>>(h->d_counter, p.row_begin);
+      LAUNCHED(h);
+      tc::TcParams tp;
+      tp.sp = p;
+      tp.counter = h->d_counter;
+      tp.dbg = nullptr;
+      if (getenv("PIO_ALS_TC_DEBUG")) {
+        if (h->dbg_rows < (size_t)dst.R) {
+          if (h->d_dbg) cudaFree(h->d_dbg);
+          if ((e = cudaMalloc((void**)&h->d_dbg, (size_t)dst.R * (tc::ASLOT + tc::KP) * sizeof(float))) != cudaSuccess) return e;
+          h->dbg_rows = dst.R;
+        }
+        cudaMemsetAsync(h->d_dbg, 0, (size_t)dst.R * (tc::ASLOT + tc::KP) * sizeof(float), h->stream);
+        tp.dbg = h->d_dbg;
+      }
+      const int per_cta = tc::NTEAM * tc::NSLOT;
+      int grid = (nlight + per_cta - 1) / per_cta;
+      if (grid > h->sm_count) grid = h->sm_count;
+      kern<<<grid, tc::NTHREADS, smem, h->stream>>>(tp);
+      LAUNCHED(h);
+      ++h->st.solve_launches;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    } else {
+      const int grid = (nlight + Cfg::NG - 1) / Cfg::NG;
+      e = imp ? launch_solve_one<Cfg, true, false>(h, p, grid, h->stream) : launch_solve_one<Cfg, false, false>(h, p, grid, h->stream);
+      if (e != cudaSuccess) return e;
+    }
   }
   if (fork) e = cudaStreamWaitEvent(h->stream, h->ev_join, 0);
   return e;
@@ -760,11 +814,17 @@ static int create_common(pio_als_handle* h) {
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   h->KP = pad_rank(h->cfg.rank);
+  {
+    const char* env = getenv("PIO_ALS_TC");
+    h->use_tc = h->KP == 64 && !(env && env[0] == '0');
+    h->heavy_t = h->use_tc ? HEAVY_T_TC : HEAVY_T;
+  }
   h->gram_blocks = 2 * h->sm_count;
   if (cudaMallocAsync((void**)&h->yty, sizeof(float) * h->KP * h->KP, h->stream) != cudaSuccess ||
       cudaMallocAsync((void**)&h->gram_partial, sizeof(double) * (size_t)h->gram_blocks * h->KP * h->KP, h->stream) != cudaSuccess ||
       cudaMallocAsync((void**)&h->d_fail, sizeof(int), h->stream) != cudaSuccess ||
-      cudaMallocAsync((void**)&h->d_counts, 4 * sizeof(int), h->stream) != cudaSuccess)
+      cudaMallocAsync((void**)&h->d_counts, 4 * sizeof(int), h->stream) != cudaSuccess ||
+      cudaMallocAsync((void**)&h->d_counter, sizeof(int), h->stream) != cudaSuccess)
     return fail(nullptr, PIO_ALS_ERR_CUDA, "device allocation failed");
   cudaMemsetAsync(h->yty, 0, sizeof(float) * h->KP * h->KP, h->stream);
   cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream);
@@ -811,6 +871,7 @@ void pio_als_destroy(pio_als_handle* h) {
     dfree(h, h->gram_partial);
     dfree(h, h->d_fail);
     dfree(h, h->d_counts);
+    dfree(h, h->d_counter);
     cudaStreamSynchronize(h->stream);
     for (auto& e : h->ev_pool) {
       cudaEventDestroy(e.a);
@@ -1223,6 +1284,15 @@ int pio_als_load(const char* path, int device, pio_als_handle** out) {
   h->trained = true;
   *out = h;
   return PIO_ALS_OK;
+}
+
+/* debug only (not in pio_als.h): copies the A/b dump of the last tensor-core half-step (rows in internal order) */
+__attribute__((visibility("default"))) int pio_als_debug_dump(pio_als_handle* h, float* out, long long n_floats) {
+  if (!h || !h->d_dbg) return PIO_ALS_ERR_STATE;
+  cudaStreamSynchronize(h->stream);
+  size_t n = h->dbg_rows * (tc::ASLOT + tc::KP);
+  if ((size_t)n_floats < n) n = (size_t)n_floats;
+  return cudaMemcpy(out, h->d_dbg, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? PIO_ALS_OK : PIO_ALS_ERR_CUDA;
 }
 
 int pio_als_get_stats(const pio_als_handle* h, pio_als_stats* out) {

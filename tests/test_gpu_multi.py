@@ -23,17 +23,18 @@ WORKER = textwrap.dedent("""
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
-    t = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        t = torch.tensor(list(native.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-    dist.broadcast(t, 0)
-    nid = bytes(t.cpu().tolist())
+    def fresh_id():      # one ncclUniqueId per communicator (= per handle)
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t = torch.tensor(list(native.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().tolist())
     for (rk, implicit, nu, ni, nnz) in ((64, True, 6000, 900, 150000), (10, False, 3000, 500, 40000),
                                         (64, True, 20000, 30, 300000)):
         u, i, r = synth.synth_ratings(nu, ni, nnz, seed=3, implicit=implicit)
         u0 = synth.synth_init_factors(nu, rk, 5, 0)
         m = native.NativeALS(rk, nu, ni, lam=0.01, implicit=implicit, device=rank, world_size=world, world_rank=rank,
-                             nccl_id=nid)
+                             nccl_id=fresh_id())
         m.set_ratings(u, i, r, dedup=1 if implicit else 0)
         m.set_init(u0)
         m.run(3)
@@ -67,5 +68,5 @@ def test_sharded_equals_single_gpu(native, tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-6000:]
     assert out.stdout.count("ok") == world
