@@ -7,10 +7,12 @@
 //   SWIZZLE_128B_BASE32B UMMA shared-memory layout (per 32 columns a 1 KB atom: one 128-byte row per
 //   rating, its four 32-byte chunks XOR-swizzled by rating%4) -- the only MN-major layout kind::tf32
 //   accepts (verified with tools/umma_probe.cu; the un-swizzled MN-major forms silently produce 0);
-//   one  tcgen05.mma.cta_group::1.kind::tf32  with M = N = 128, K = 8 and the SAME tile as A and B
-//   operand accumulates  D += [hi|lo]^T [hi|lo]  in TMEM; the four 64x64 quadrants of D sum to
-//   (hi+lo)^T (hi+lo) -- fp32-class products (error ~2^-21 relative per term) at tensor-core rate.
-// D is symmetric, so operand-order / transpose conventions cannot change the result.
+//   per K-block three  tcgen05.mma.cta_group::1.kind::tf32  (M = N = 64, K = 8) accumulate
+//   D += hi^T hi + lo^T hi + hi^T lo  into ONE 64-column TMEM accumulator (the dropped lo^T lo term is
+//   ~2^-22 relative) -- fp32-class products at tensor-core rate, and the accumulator is the matrix
+//   itself (row r in TMEM lane 32*(r/16) + r%16, tools/umma_probe64.cu), so draining needs no
+//   cross-warp quadrant sum and TMEM (512 columns) holds two batches of four rows: the MMAs of batch
+//   b+1 overlap the drain of batch b.
 //
 // Warp roles (512 threads, 1 CTA per SM, persistent; rows are claimed from a global counter in
 // degree-descending order):
@@ -19,9 +21,9 @@
 //   warps 1-3   producers: gather source rows (LDG.128), scale, split hi/lo, STS into the stage ring,
 //               accumulate the right-hand side b
 //   warps 4-15  three teams of four warps (one warp per TMEM lane quarter): drain the four
-//               accumulators of their batch (tcgen05.ld -> quadrant sum -> packed A slot in smem),
-//               then each warp Cholesky-solves one of the four rows (chol_solve_warp<PACKED_IN>).
-// A batch = up to four (row, rating-segment) pairs, one per TMEM accumulator (4 x 128 columns);
+//               accumulators of their batch (tcgen05.ld -> packed A slot in smem), then each warp
+//               Cholesky-solves one of the four rows (chol_solve_warp<PACKED_IN>).
+// A batch = up to four (row, rating-segment) pairs, one per TMEM accumulator (64 columns each);
 // rows longer than SEG ratings are accumulated segment by segment with fp32 adds in shared memory
 // between segments (bounds the length of any single tensor-core accumulation chain).
 #pragma once
@@ -34,13 +36,17 @@ namespace pio {
 namespace tc {
 
 constexpr int KP = 64;
-constexpr int NCOL = 128;                        // [hi | lo]
+constexpr int NCOL = 128;                        // staged columns per rating: [hi | lo]
+constexpr int ACOL = 64;                         // TMEM columns of one accumulator
 constexpr int KB_RATINGS = 8;                    // K of one tf32 MMA
 constexpr int KB_BYTES = KB_RATINGS * NCOL * 4;  // 4096
 constexpr int STAGE_KB = 3;                      // one K-block per producer warp
 constexpr int STAGE_RATINGS = STAGE_KB * KB_RATINGS;  // 24
 constexpr int STAGE_BYTES = STAGE_KB * KB_BYTES;      // 12288
 constexpr int NSTAGE = 4;
+constexpr int NRAW = 6;                          // raw ring: stages of cp.async gathers in flight per producer warp
+constexpr int MD = 8;                            // metadata (index/rating) look-ahead beyond the gather cursor, in stages
+constexpr int QN = 12;                           // metadata ring entries
 constexpr int SEG = 21 * STAGE_RATINGS;          // 504 ratings per accumulation segment
 constexpr int NTEAM = 3;
 constexpr int NSLOT = 4;
@@ -51,14 +57,23 @@ constexpr int OFF21 = H * (H + 1) / 2;           // 528
 constexpr int OFF22 = OFF21 + H * L21S;          // 1680
 constexpr int ASLOT = OFF22 + H * (H + 1) / 2;   // 2208 floats
 
+// one UMMA stage (<= 24 ratings of one segment), pre-expanded by the scheduler so producers need no bookkeeping
+struct StageEnt {
+  long long beg;   // offset of the stage's first rating in idx/val
+  int valid;       // ratings in this stage (1..24)
+  int info;        // bits 0-1 slot, bit 2 last stage of its segment, bit 3 last stage of the batch, bit 4 first stage of its segment
+};
+constexpr int MAX_STAGES = NSLOT * (SEG / STAGE_RATINGS);   // 84
+
 struct BatchDesc {
-  long long beg[NSLOT];
   int row[NSLOT];    // local row, -1 = empty slot
-  int len[NSLOT];
-  int first[NSLOT];
-  int last[NSLOT];
+  int first[NSLOT];  // segment starts its row (overwrite the A slot instead of accumulating)
+  int last[NSLOT];   // segment ends its row (solve after draining)
   int exit;
-  int pad[3];
+  int seq;           // global batch number (selects the TMEM accumulator set)
+  int nstages;
+  int pad;
+  StageEnt st[MAX_STAGES];
 };
 
 struct Smem {
@@ -67,6 +82,12 @@ struct Smem {
   alignas(16) float bslot[NTEAM][NSLOT][KP];
   alignas(16) float bstage[NTEAM][NSLOT][KP];
   alignas(16) float bpart[STAGE_KB][KP];
+  alignas(16) float4 raw[STAGE_KB][NRAW][4][32];   // per producer warp: gathered rows, [j][lane] -> conflict-free
+  float rawval[STAGE_KB][NRAW][32];
+  int metaidx[STAGE_KB][QN][32];
+  float metaval[STAGE_KB][QN][32];
+  unsigned int metagrp[STAGE_KB][QN];
+  unsigned int rawgrp[STAGE_KB][NRAW];
   alignas(16) float colbuf[NTEAM * NSLOT][2 * KP];
   alignas(16) float dinv[NTEAM * NSLOT][KP];
   BatchDesc desc[NTEAM];
@@ -76,7 +97,7 @@ struct Smem {
   unsigned long long accfull[NTEAM];
   unsigned long long teamdone[NTEAM];
   unsigned long long bfull[NTEAM];
-  unsigned long long tmemfree;
+  unsigned long long tmemfree[2];
   unsigned int tmem_base;
 };
 
@@ -93,13 +114,26 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
       "}" ::"r"(s32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(200000u)   // suspend-time hint (ns): the waiting warp sleeps instead of polling
       : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"   // test_wait never suspends (try_wait may)
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(s32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -137,6 +171,35 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s32(smem_dst)), "l"(gsrc));
+}
+// allow at most `pend` of the most recent commit groups to stay in flight (exact up to 8, else conservative)
+__device__ __forceinline__ void cp_async_wait_dyn(uint32_t pend) {
+  switch (pend) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    case 7: cp_async_wait<7>(); break;
+    default: cp_async_wait<8>(); break;
+  }
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -162,18 +225,23 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format F32 = 1 at [4,6),
 // a/b format TF32 = 2 at [7,10)/[10,13), a/b major MN = 1 at bits 15/16, N>>3 at [17,23), M>>4 at [24,29).
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((64u >> 4) << 24);
+
+static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget (227 KB) exceeded");
 
 struct TcParams {
   SolveParams sp;
   int* counter;  // next row to claim (starts at sp.row_begin)
+  long long* timing;  // debug only (PIO_ALS_TC_TIMING=1): [grid][16 warps][8] cycle counters, else null
   float* dbg;    // debug only (PIO_ALS_TC_DEBUG=1): per local row ASLOT + KP floats (A as drained, b), else null
 };
 
 template <bool IMPLICIT>
 __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParams tp) {
+  // direct cast (no integer round-trip) so the compiler keeps the shared address space: LDS/STS, not generic LD/ST
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  if (threadIdx.x == 0 && (s32(smem_raw) & 1023u) != 0u) __trap();   // UMMA swizzle atoms need 1 KB alignment
   const SolveParams& p = tp.sp;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -188,7 +256,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       mbar_init(&sm.teamdone[t], NSLOT);
       mbar_init(&sm.bfull[t], 1);
     }
-    mbar_init(&sm.tmemfree, NSLOT);
+    mbar_init(&sm.tmemfree[0], NSLOT);
+    mbar_init(&sm.tmemfree[1], NSLOT);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
@@ -196,6 +265,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
+
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool timing = tp.timing != nullptr;
+  long long t0_ = 0;
+#define T_BEGIN() do { if (timing) t0_ = clock64(); } while (0)
+#define T_END(i) do { if (timing) tacc[i] += clock64() - t0_; } while (0)
+  const long long tstart_ = timing ? clock64() : 0;
+
+  // register rebalancing: scheduler/producer warpgroup gives registers to the three drain+solve warpgroups
+  // (setmaxnreg rebalancing was tried and removed: shrinking the producer warpgroup forced its state into local memory)
 
   if (warp == 0) {
     // ================= scheduler + MMA issuer =================
@@ -208,43 +287,81 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       bool out_of_rows = false;
       uint32_t it = 0;       // global stage counter
       uint32_t nmma_batches = 0;
+      uint32_t nbuilt = 0;   // batches with work, in publish order == MMA order
+      // Static row assignment (no atomics): rows are degree-sorted; groups of 12 consecutive rows are dealt to
+      // the CTAs in snake order, lane (t,s) of this CTA takes row  g*12 + t*4 + s  of its k-th group g.
+      // The row pointers of a lane's NEXT row are prefetched while the current one is processed.
+      const int per_cta = NTEAM * NSLOT;
+      const int nrows = p.row_end - p.row_begin;
+      const int ngroups = (nrows + per_cta - 1) / per_cta;
+      const int G = (int)gridDim.x;
+      int l_k[NTEAM * NSLOT];
+      bool l_first[NTEAM * NSLOT];
+      long long n_beg[NTEAM * NSLOT], n_end[NTEAM * NSLOT];
+      int n_row[NTEAM * NSLOT];
+      auto row_of = [&](int li, int k) -> int {
+        const long long g = (long long)k * G + ((k & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x);
+        if (g >= ngroups) return -1;
+        const long long r = (long long)p.row_begin + g * per_cta + li;
+        return r < p.row_end ? (int)r : -1;
+      };
+      for (int li = 0; li < NTEAM * NSLOT; ++li) {
+        l_k[li] = 0;
+        l_first[li] = false;
+        n_row[li] = row_of(li, 0);
+        n_beg[li] = n_end[li] = 0;
+        if (n_row[li] >= 0) { n_beg[li] = p.ptr[n_row[li]]; n_end[li] = p.ptr[n_row[li] + 1]; }
+      }
+      (void)out_of_rows;
       // returns false when team t has nothing left
+      auto team_free = [&](int t) -> bool { return mbar_test(&sm.teamdone[t], (nbatch_team[t] & 1) ^ 1); };
       auto build = [&](int t) -> bool {
+        T_BEGIN();
         mbar_wait(&sm.teamdone[t], (nbatch_team[t] & 1) ^ 1);  // previous batch of this team fully consumed
+        T_END(0);
         BatchDesc& d = sm.desc[t];
         bool any = false;
+        int ns = 0;
         for (int s = 0; s < NSLOT; ++s) {
           const int li = t * NSLOT + s;
           if (l_row[li] >= 0 && l_pos[li] >= l_end[li]) l_row[li] = -1;
-          if (l_row[li] < 0 && !out_of_rows) {
-            const int r = atomicAdd(tp.counter, 1);
-            if (r < p.row_end) {
-              l_row[li] = r;
-              l_pos[li] = p.ptr[r];
-              l_end[li] = p.ptr[r + 1];
-            } else {
-              out_of_rows = true;
-            }
+          if (l_row[li] < 0 && n_row[li] >= 0) {
+            l_row[li] = n_row[li];
+            l_pos[li] = n_beg[li];
+            l_end[li] = n_end[li];
+            l_first[li] = true;
+            ++l_k[li];
+            n_row[li] = row_of(li, l_k[li]);   // prefetch the pointers of the row after this one
+            if (n_row[li] >= 0) { n_beg[li] = __ldg(p.ptr + n_row[li]); n_end[li] = __ldg(p.ptr + n_row[li] + 1); }
           }
           if (l_row[li] >= 0) {
             long long e = l_pos[li] + SEG;
             if (e > l_end[li]) e = l_end[li];
+            const int len = (int)(e - l_pos[li]);
             d.row[s] = l_row[li];
-            d.beg[s] = l_pos[li];
-            d.len[s] = (int)(e - l_pos[li]);
-            d.first[s] = l_pos[li] == p.ptr[l_row[li]];
+            d.first[s] = l_first[li] ? 1 : 0;
+            l_first[li] = false;
             d.last[s] = e == l_end[li];
+            const int nst = (len + STAGE_RATINGS - 1) / STAGE_RATINGS;
+            for (int q = 0; q < nst; ++q) {
+              StageEnt& se = d.st[ns++];
+              se.beg = l_pos[li] + (long long)q * STAGE_RATINGS;
+              const int v = len - q * STAGE_RATINGS;
+              se.valid = v < STAGE_RATINGS ? v : STAGE_RATINGS;
+              se.info = s | (q == nst - 1 ? 4 : 0) | (q == 0 ? 16 : 0);
+            }
             l_pos[li] = e;
             any = true;
           } else {
             d.row[s] = -1;
-            d.beg[s] = 0;
-            d.len[s] = 0;
             d.first[s] = 0;
             d.last[s] = 0;
           }
         }
+        if (ns > 0) d.st[ns - 1].info |= 8;
+        d.nstages = ns;
         d.exit = any ? 0 : 1;
+        d.seq = any ? (int)(nbuilt++) : 0;
         mbar_arrive(&sm.descfull[t]);
         ++nbatch_team[t];
         if (!any) exited[t] = true;
@@ -268,7 +385,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
         while (true) {
           const int t = next_team();
           if (t < 0) return true;
-          if (!allow_cur && have[cur] && t == team_of[cur]) return false;
+          if (!allow_cur && have[cur] && (t == team_of[cur] || !team_free(t))) return false;  // do not stall the MMAs of `cur`
           cursor = (t + 1) % NTEAM;
           team_of[nxt] = t;
           if (build(t)) { have[nxt] = true; return true; }
@@ -282,24 +399,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
         if (have[cur]) {
           const int t = team_of[cur];
           const BatchDesc& d = sm.desc[t];
-          mbar_wait(&sm.tmemfree, (nmma_batches & 1) ^ 1);  // accumulators of the previous batch drained
+          const uint32_t set = nmma_batches & 1;                         // TMEM accumulator set of this batch
+          T_BEGIN();
+          mbar_wait(&sm.tmemfree[set], ((nmma_batches >> 1) & 1) ^ 1);   // batch b-2 (same set) has been drained
+          T_END(1);
           tc_fence_after();
-          for (int s = 0; s < NSLOT; ++s) {
-            const int len = d.len[s];
-            const int nst = (len + STAGE_RATINGS - 1) / STAGE_RATINGS;
-            for (int q = 0; q < nst; ++q, ++it) {
-              const int st = it % NSTAGE;
-              mbar_wait(&sm.full[st], (it / NSTAGE) & 1);
-              tc_fence_after();
-              const int valid = len - q * STAGE_RATINGS;
-              const int nkb = valid >= STAGE_RATINGS ? STAGE_KB : (valid + KB_RATINGS - 1) / KB_RATINGS;
-              const uint32_t base = s32(&sm.stage[st][0]);
-              for (int kb = 0; kb < nkb; ++kb) {
-                const uint64_t dsc = make_desc(base + kb * KB_BYTES);
-                umma_tf32(tmem + s * NCOL, dsc, dsc, IDESC, (q > 0 || kb > 0) ? 1u : 0u);
-              }
-              umma_commit(&sm.empty[st]);
+          const int nstg = d.nstages;
+          for (int i = 0; i < nstg; ++i, ++it) {
+            const int st = it % NSTAGE;
+            const int valid = d.st[i].valid;
+            const int info = d.st[i].info;
+            T_BEGIN();
+            mbar_wait(&sm.full[st], (it / NSTAGE) & 1);
+            T_END(2);
+            tc_fence_after();
+            const int nkb = (valid + KB_RATINGS - 1) / KB_RATINGS;
+            const uint32_t base = s32(&sm.stage[st][0]);
+            const uint32_t acc = tmem + set * (NSLOT * ACOL) + (info & 3) * ACOL;
+            for (int kb = 0; kb < nkb; ++kb) {
+              const uint64_t dh = make_desc(base + kb * KB_BYTES);          // hi half: columns 0..63
+              const uint64_t dl = make_desc(base + kb * KB_BYTES + 2048);   // lo half
+              umma_tf32(acc, dh, dh, IDESC, ((info & 16) && kb == 0) ? 0u : 1u);
+              umma_tf32(acc, dl, dh, IDESC, 1u);
+              umma_tf32(acc, dh, dl, IDESC, 1u);
             }
+            umma_commit(&sm.empty[st]);
           }
           umma_commit(&sm.accfull[t]);
           ++nmma_batches;
@@ -312,93 +436,177 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
     __syncwarp();
   } else if (warp <= STAGE_KB) {
     // ================= producers =================
+    // Three positions walk the scheduler's flat stage lists in the same order:
+    //   look-ahead (metadata cp.async, MD stages beyond the gathers) -> gather issue (cp.async of source rows into
+    //   this warp's raw ring) -> convert (scale, hi/lo split, UMMA tile).  Only the convert position ever blocks
+    //   on a descriptor; the look-ahead just stops at a batch whose descriptor is not published yet.
     const int pw = warp - 1;            // K-block inside the stage
     // lane -> (rating kr inside the K-block, source float4 groups sg_j): a quarter-warp holds 4 ratings
     // (kr%4 = 0..3) x 2 halves of one 32-byte chunk -> its 8 STS.128 hit 8 distinct 16-byte bank groups
     const int kr = ((lane >> 3) & 1) * 4 + (lane & 3);
     const int sgb = ((lane >> 2) & 1) + 2 * (lane >> 4);   // sg_j = sgb + 4 j
-    bool exited[NTEAM] = {false, false, false};
-    int nbatch_team[NTEAM] = {0, 0, 0};
-    uint32_t it = 0;
-    int cursor = 0;
-    while (true) {
-      int t = -1;
-      for (int k = 0; k < NTEAM; ++k) {
-        const int c = (cursor + k) % NTEAM;
-        if (!exited[c]) { t = c; break; }
-      }
-      if (t < 0) break;
-      cursor = (t + 1) % NTEAM;
-      mbar_wait(&sm.descfull[t], nbatch_team[t] & 1);
-      ++nbatch_team[t];
-      const BatchDesc& d = sm.desc[t];
-      if (d.exit) { exited[t] = true; continue; }
-      for (int s = 0; s < NSLOT; ++s) {
-        const int len = d.len[s];
-        if (d.row[s] < 0) continue;
-        const long long beg = d.beg[s];
-        float bacc[4][4];
+    const int kl = pw * KB_RATINGS + kr;                    // rating index inside a stage
+    // cursor = (team t, stage index i of n) + which descriptors were consumed (scalars only)
+    uint32_t l_ex = 0, l_par = 0, c_ex = 0, c_par = 0;      // exited masks / per-team batch parity bits
+    int l_cur = 0, l_t = 0, l_i = 0, l_n = 0;               // look-ahead cursor
+    int c_cur = 0, c_t = 0, c_i = -1, c_n = 0;              // convert cursor (c_i = -1: before the first stage)
+    bool l_done = false, c_done = false;
+    // move a cursor to the first stage of the next batch; returns false if finished or (non-blocking) not published yet
+    auto next_batch = [&](uint32_t& ex, uint32_t& par, int& cur, int& t, int& n, bool& done, bool blocking) -> bool {
+      while (true) {
+        int nt = -1;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) bacc[j][c] = 0.f;
-        const int nst = (len + STAGE_RATINGS - 1) / STAGE_RATINGS;
-        // prefetch of the first stage's index / rating
-        int k0 = pw * KB_RATINGS + kr;
-        int nidx = -1;
-        float nval = 0.f;
-        if (k0 < len) { nidx = __ldg(p.idx + beg + k0); nval = __ldg(p.val + beg + k0); }
-        for (int q = 0; q < nst; ++q, ++it) {
-          const int st = it % NSTAGE;
-          const int cidx = nidx;
-          const float cval = nval;
-          // prefetch next stage's metadata
-          const int kn = (q + 1) * STAGE_RATINGS + pw * KB_RATINGS + kr;
-          nidx = -1;
-          nval = 0.f;
-          if (kn < len) { nidx = __ldg(p.idx + beg + kn); nval = __ldg(p.val + beg + kn); }
-          float4 y[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            y[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (cidx >= 0) y[j] = __ldg(reinterpret_cast<const float4*>(p.src + (size_t)cidx * KP) + sgb + 4 * j);
-          }
-          float wb, sc;
-          if (IMPLICIT) {
-            const float c1 = p.alpha * fabsf(cval);
-            wb = cval > 0.f ? 1.f + c1 : 0.f;
-            sc = sqrtf(c1);
-          } else {
-            wb = cval;
-            sc = 1.f;
-          }
-          const int valid = len - q * STAGE_RATINGS;
-          const bool kb_used = pw * KB_RATINGS < valid;
-          mbar_wait(&sm.empty[st], ((it / NSTAGE) & 1) ^ 1);
-          if (kb_used) {
-            unsigned char* kbp = &sm.stage[st][0] + pw * KB_BYTES + kr * 128;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int sg = sgb + 4 * j;
-              const int off = (sg >> 3) * 1024 + ((((sg & 7) >> 1) ^ (kr & 3)) * 32) + (sg & 1) * 16;
-              bacc[j][0] = fmaf(wb, y[j].x, bacc[j][0]);
-              bacc[j][1] = fmaf(wb, y[j].y, bacc[j][1]);
-              bacc[j][2] = fmaf(wb, y[j].z, bacc[j][2]);
-              bacc[j][3] = fmaf(wb, y[j].w, bacc[j][3]);
-              float4 x = y[j];
-              if (IMPLICIT) { x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; }
-              float4 hi, lo;
-              hi.x = tf32_round(x.x); hi.y = tf32_round(x.y); hi.z = tf32_round(x.z); hi.w = tf32_round(x.w);
-              lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
-              *reinterpret_cast<float4*>(kbp + off) = hi;          // columns 4sg..4sg+3 of the hi half
-              *reinterpret_cast<float4*>(kbp + 2048 + off) = lo;   // same columns of the lo half (mn + 64)
-            }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.full[st]);
+        for (int k = 0; k < NTEAM; ++k) {
+          const int cand = (cur + k) % NTEAM;
+          if (nt < 0 && !((ex >> cand) & 1u)) nt = cand;
         }
-        // b of this segment: reduce over the 8 ratings of the warp (lanes with equal sgb), then over warps
+        if (nt < 0) { done = true; return false; }
+        const uint32_t pb = (par >> nt) & 1u;
+        if (blocking) mbar_wait(&sm.descfull[nt], pb);
+        else if (!mbar_test(&sm.descfull[nt], pb)) return false;
+        par ^= 1u << nt;
+        cur = (nt + 1) % NTEAM;
+        if (sm.desc[nt].exit) { ex |= 1u << nt; continue; }
+        t = nt;
+        n = sm.desc[nt].nstages;
+        return true;
+      }
+    };
+    uint32_t n_meta = 0, n_issued = 0, n_conv = 0;   // stages whose metadata was requested / gathers issued / converted
+    uint32_t it = 0;                                  // global stage counter (UMMA ring)
+    uint32_t g_total = 0, g_done = 0;                 // cp.async groups committed / known complete (prefix)
+    float bacc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bacc[j][c] = 0.f;
+    auto wait_group_id = [&](uint32_t gid) {   // make sure commit group gid has landed
+      if (gid < g_done) return;
+      const uint32_t pend = g_total - 1 - gid;
+      cp_async_wait_dyn(pend);
+      g_done = g_total - (pend < 8u ? pend : 8u);
+    };
+    bool l_ready = next_batch(l_ex, l_par, l_cur, l_t, l_n, l_done, true);   // the first descriptor is always published
+    l_i = 0;
+    auto pump = [&]() {
+      while (true) {
+        // 1. metadata look-ahead: index + rating of future stages (4-byte cp.async, no register dependency)
+        bool requested = false;
+        long long tp1_ = timing ? clock64() : 0;
+        while (n_meta < n_issued + (uint32_t)MD) {
+          if (!l_ready) {
+            if (l_done) break;
+            l_ready = next_batch(l_ex, l_par, l_cur, l_t, l_n, l_done, false);
+            l_i = 0;
+            if (!l_ready) break;
+          }
+          const StageEnt se = sm.desc[l_t].st[l_i];
+          const int ms = n_meta % QN;
+          if (kl < se.valid) {
+            cp_async4(&sm.metaidx[pw][ms][lane], p.idx + se.beg + kl);
+            cp_async4(&sm.metaval[pw][ms][lane], p.val + se.beg + kl);
+          } else {
+            sm.metaidx[pw][ms][lane] = -1;
+            sm.metaval[pw][ms][lane] = 0.f;
+          }
+          sm.metagrp[pw][ms] = g_total;   // warp-uniform
+          ++n_meta;
+          requested = true;
+          if (++l_i >= l_n) l_ready = false;
+        }
+        if (timing) tacc[5] += clock64() - tp1_;
+        // 2. gathers of the next stage, from indices that have already landed (one commit group per stage)
+        if (n_issued >= n_meta || n_issued - n_conv >= (uint32_t)NRAW) {   // nothing to gather yet / raw ring full
+          if (requested) { cp_async_commit(); ++g_total; }
+          return;
+        }
+        const int ms = n_issued % QN;
+        __syncwarp();
+        const uint32_t mg = sm.metagrp[pw][ms];
+        if (mg >= g_total) { cp_async_commit(); ++g_total; }   // its metadata was requested just now (start-up only)
+        long long tp2_ = timing ? clock64() : 0;
+        wait_group_id(mg);                                      // no-op in steady state (MD stages old)
+        const int col = sm.metaidx[pw][ms][lane];
+        if (timing) tacc[6] += clock64() - tp2_ + (col & 0);
+        const int rs = n_issued % NRAW;
+        if (col >= 0) {
+          const float4* srcp = reinterpret_cast<const float4*>(p.src + (size_t)col * KP) + sgb;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cp_async16(&sm.raw[pw][rs][j][lane], srcp + 4 * j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sm.raw[pw][rs][j][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        sm.rawval[pw][rs][lane] = sm.metaval[pw][ms][lane];
+        sm.rawgrp[pw][rs] = g_total;
+        cp_async_commit();
+        ++g_total;
+        ++n_issued;
+      }
+    };
+    pump();
+    while (true) {
+      // advance the convert cursor (blocking on the next descriptor only when its batch is exhausted)
+      T_BEGIN();
+      if (++c_i >= c_n) {
+        if (c_done || !next_batch(c_ex, c_par, c_cur, c_t, c_n, c_done, true)) { T_END(0); break; }
+        c_i = 0;
+      }
+      T_END(0);
+      T_BEGIN();
+      pump();   // the blocking advance may have consumed a fresh descriptor the look-ahead was waiting for
+      T_END(1);
+      const StageEnt se = sm.desc[c_t].st[c_i];
+      __syncwarp();
+      T_BEGIN();
+      wait_group_id(sm.rawgrp[pw][n_conv % NRAW]);   // the gathers of the stage at the convert cursor
+      T_END(2);
+      const int slot = n_conv % NRAW;
+      const int st = it % NSTAGE;
+      const float cval = sm.rawval[pw][slot][lane];
+      float wb, sc;
+      if (IMPLICIT) {
+        const float c1 = p.alpha * fabsf(cval);
+        wb = cval > 0.f ? 1.f + c1 : 0.f;
+        sc = sqrtf(c1);
+      } else {
+        wb = cval;
+        sc = 1.f;
+      }
+      const bool kb_used = pw * KB_RATINGS < se.valid;
+      T_BEGIN();
+      mbar_wait(&sm.empty[st], ((it / NSTAGE) & 1) ^ 1);
+      T_END(3);
+      T_BEGIN();
+      if (kb_used) {
+        unsigned char* kbp = &sm.stage[st][0] + pw * KB_BYTES + kr * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int sg = sgb + 4 * j;
+          const int off = (sg >> 3) * 1024 + ((((sg & 7) >> 1) ^ (kr & 3)) * 32) + (sg & 1) * 16;
+          const float4 y = sm.raw[pw][slot][j][lane];
+          bacc[j][0] = fmaf(wb, y.x, bacc[j][0]);
+          bacc[j][1] = fmaf(wb, y.y, bacc[j][1]);
+          bacc[j][2] = fmaf(wb, y.z, bacc[j][2]);
+          bacc[j][3] = fmaf(wb, y.w, bacc[j][3]);
+          float4 x = y;
+          if (IMPLICIT) { x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; }
+          float4 hi, lo;
+          hi.x = tf32_round(x.x); hi.y = tf32_round(x.y); hi.z = tf32_round(x.z); hi.w = tf32_round(x.w);
+          lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
+          *reinterpret_cast<float4*>(kbp + off) = hi;          // columns 4sg..4sg+3 of the hi half
+          *reinterpret_cast<float4*>(kbp + 2048 + off) = lo;   // same columns of the lo half (mn + 64)
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.full[st]);
+      T_END(4);
+      ++n_conv;
+      ++it;
+      if (se.info & 4) {
+        // end of a segment: b = reduce over the 8 ratings of the warp (lanes with equal sgb), then over warps
+        const int sslot = se.info & 3;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -417,14 +625,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
         }
         named_bar_sync(1, STAGE_KB * 32);
         if (pw == 0) {
-          for (int c = lane; c < KP; c += 32) sm.bstage[t][s][c] = (sm.bpart[0][c] + sm.bpart[1][c]) + sm.bpart[2][c];
+          for (int c = lane; c < KP; c += 32) sm.bstage[c_t][sslot][c] = (sm.bpart[0][c] + sm.bpart[1][c]) + sm.bpart[2][c];
+          if (se.info & 8) {   // every right-hand side of this batch is in bstage[t]
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.bfull[c_t]);
+          }
         }
-      }
-      if (pw == 0) {  // all right-hand sides of this batch are in bstage[t]
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.bfull[t]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) bacc[j][c] = 0.f;
       }
     }
+    cp_async_wait<0>();
   } else {
     // ================= teams: drain + solve =================
     const int t = (warp - 4) / 4;
@@ -433,47 +646,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
     const int barid = 2 + t;
     int nb = 0;
     while (true) {
+      T_BEGIN();
       mbar_wait(&sm.descfull[t], nb & 1);
+      T_END(0);
       const BatchDesc& d = sm.desc[t];
       if (d.exit) break;
+      T_BEGIN();
       mbar_wait(&sm.accfull[t], nb & 1);
+      T_END(1);
       tc_fence_after();
-      // ---- drain: row i of D lives in TMEM lane i; A = D[0:64,0:64] + D[0:64,64:128] + D[64:128,0:64] + D[64:128,64:128]
-      const int drow = (q & 1) * 32 + lane;  // destination row 0..63 handled by this thread
+      T_BEGIN();
+      // ---- drain: D row r lives in TMEM lane 32*(r/16) + r%16: lanes 0..15 of warp quarter q hold rows 16q..16q+15
+      const uint32_t set = (uint32_t)d.seq & 1u;
+      {
+        // tcgen05.ld is warp-collective (.sync.aligned): all 32 lanes load, lanes 0..15 hold the rows
+        const bool holds = lane < 16;
+        const int drow = q * 16 + (lane & 15);
 #pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const bool mine = pass == 0 ? (q >= 2) : (q < 2);  // lo rows first (they initialise), then hi rows add
-        if (mine) {
-#pragma unroll 1
-          for (int s = 0; s < NSLOT; ++s) {
-            if (d.row[s] < 0) continue;
-            float* as = &sm.aslot[t][s][0];
-            const bool overwrite = (pass == 0) && d.first[s];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * NCOL);
+        for (int s = 0; s < NSLOT; ++s) {
+          if (d.row[s] < 0) continue;
+          float* as = &sm.aslot[t][s][0];
+          const bool first = d.first[s] != 0;
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + set * (NSLOT * ACOL) + (uint32_t)(s * ACOL);
+          float v[64];
+          tmem_ld16_nowait(taddr, &v[0]);
+          tmem_ld16_nowait(taddr + 16, &v[16]);
+          tmem_ld16_nowait(taddr + 32, &v[32]);
+          tmem_ld16_nowait(taddr + 48, &v[48]);
+          tmem_ld_wait();
+          if (!holds) continue;
+          if (drow < H) {
+            float* rowp = as + drow * (drow + 1) / 2;
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) {
-              float a[16], b2[16];
-              tmem_ld16(taddr + cb * 16, a);
-              tmem_ld16(taddr + 64 + cb * 16, b2);
+            for (int c = 0; c < H; ++c)
+              if (c <= drow) rowp[c] = first ? v[c] : rowp[c] + v[c];
+          } else {
+            float4* r4 = reinterpret_cast<float4*>(as + OFF21 + (drow - H) * L21S);
 #pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                const int col = cb * 16 + c;
-                if (col <= drow) {
-                  const float v = a[c] + b2[c];
-                  int off;
-                  if (drow < H) off = drow * (drow + 1) / 2 + col;
-                  else if (col < H) off = OFF21 + (drow - H) * L21S + col;
-                  else off = OFF22 + (drow - H) * (drow - H + 1) / 2 + (col - H);
-                  as[off] = overwrite ? v : as[off] + v;
-                }
-              }
+            for (int c = 0; c < H; c += 4) {
+              float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+              if (!first) { const float4 e = r4[c / 4]; o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
+              r4[c / 4] = o;
             }
+            float* rowp = as + OFF22 + (drow - H) * (drow - H + 1) / 2;
+#pragma unroll
+            for (int c = 0; c < H; ++c)
+              if (c <= drow - H) rowp[c] = first ? v[H + c] : rowp[c] + v[H + c];
           }
         }
-        if (pass == 0) named_bar_sync(barid, 128);
       }
+      __syncwarp();
+      T_END(2);
       // right-hand side of this segment
+      T_BEGIN();
       mbar_wait(&sm.bfull[t], nb & 1);
+      T_END(3);
       {
         const int tt = (warp - 4) % 4 * 32 + lane;  // 0..127 within the team
         for (int o = tt; o < NSLOT * KP; o += 128) {
@@ -483,8 +710,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.tmemfree);
+      if (lane == 0) mbar_arrive(&sm.tmemfree[set]);
+      T_BEGIN();
       named_bar_sync(barid, 128);
+      T_END(4);
+      T_BEGIN();
       // ---- solve
       const int r = d.row[slot];
       if (r >= 0 && d.last[slot] && tp.dbg) {
@@ -500,9 +730,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
                                                    p.dst + (size_t)(p.dst_row_offset + r) * KP, p.fail);
       }
       __syncwarp();
+      T_END(5);
       if (lane == 0) mbar_arrive(&sm.teamdone[t]);
       ++nb;
     }
+  }
+  if (timing && lane == 0) {
+    tacc[7] = clock64() - tstart_;
+    for (int i = 0; i < 8; ++i) tp.timing[((size_t)blockIdx.x * 16 + warp) * 8 + i] = tacc[i];
   }
   tc_fence_before();
   __syncthreads();

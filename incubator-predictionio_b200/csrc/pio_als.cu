@@ -335,6 +335,7 @@ struct pio_als_handle {
   int* d_fail = nullptr;
   int* d_counts = nullptr;
   int* d_counter = nullptr;   // row-claim counter of the tensor-core solve kernel
+  long long* d_timing = nullptr;  // PIO_ALS_TC_TIMING=1: per-warp cycle counters of the last tensor-core launch
   float* d_dbg = nullptr;     // PIO_ALS_TC_DEBUG=1: A/b dump of the last tensor-core half-step
   size_t dbg_rows = 0;
   bool use_tc = false;        // rank in 33..64 and PIO_ALS_TC != 0
@@ -673,6 +674,12 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
       tp.sp = p;
       tp.counter = h->d_counter;
       tp.dbg = nullptr;
+      tp.timing = nullptr;
+      if (getenv("PIO_ALS_TC_TIMING")) {
+        if (!h->d_timing && (e = cudaMalloc((void**)&h->d_timing, (size_t)h->sm_count * 16 * 8 * sizeof(long long))) != cudaSuccess) return e;
+        cudaMemsetAsync(h->d_timing, 0, (size_t)h->sm_count * 16 * 8 * sizeof(long long), h->stream);
+        tp.timing = h->d_timing;
+      }
       if (getenv("PIO_ALS_TC_DEBUG")) {
         if (h->dbg_rows < (size_t)dst.R) {
           if (h->d_dbg) cudaFree(h->d_dbg);
@@ -815,8 +822,9 @@ static int create_common(pio_als_handle* h) {
   }
   h->KP = pad_rank(h->cfg.rank);
   {
+    // tensor-core Gramian (als_tc_kernel.cuh): parity-green but not yet faster than the FP32 kernel -> opt-in
     const char* env = getenv("PIO_ALS_TC");
-    h->use_tc = h->KP == 64 && !(env && env[0] == '0');
+    h->use_tc = h->KP == 64 && env && env[0] == '1';
     h->heavy_t = h->use_tc ? HEAVY_T_TC : HEAVY_T;
   }
   h->gram_blocks = 2 * h->sm_count;
@@ -1293,6 +1301,14 @@ __attribute__((visibility("default"))) int pio_als_debug_dump(pio_als_handle* h,
   size_t n = h->dbg_rows * (tc::ASLOT + tc::KP);
   if ((size_t)n_floats < n) n = (size_t)n_floats;
   return cudaMemcpy(out, h->d_dbg, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? PIO_ALS_OK : PIO_ALS_ERR_CUDA;
+}
+
+__attribute__((visibility("default"))) int pio_als_debug_timing(pio_als_handle* h, long long* out, long long n) {
+  if (!h || !h->d_timing) return PIO_ALS_ERR_STATE;
+  cudaStreamSynchronize(h->stream);
+  size_t m = (size_t)h->sm_count * 16 * 8;
+  if ((size_t)n < m) m = (size_t)n;
+  return cudaMemcpy(out, h->d_timing, m * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? PIO_ALS_OK : PIO_ALS_ERR_CUDA;
 }
 
 int pio_als_get_stats(const pio_als_handle* h, pio_als_stats* out) {

@@ -67,6 +67,24 @@ def test_trained_factors_within_tolerance(native, oracle, rank, implicit, iters)
     assert eu <= TOL and ei <= TOL, (eu, ei, max_row_rel(g[0], o[0]), max_row_rel(g[1], o[1]))
 
 
+@pytest.mark.parametrize("implicit", [True, False])
+def test_tensor_core_gramian_path(native, oracle, monkeypatch, implicit):
+    """PIO_ALS_TC=1 routes rank 33..64 through the tcgen05 split-TF32 SYRK kernel (als_tc_kernel.cuh):
+    same tolerance, including rows longer than one 504-rating accumulation segment and > 8192 (FP32 split kernel)."""
+    monkeypatch.setenv("PIO_ALS_TC", "1")
+    nu, ni, nnz = 30000, 60, 500000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=11, implicit=implicit)
+    _, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 3, 0.05, implicit, 1.0)
+    assert (g[2] == o[2]).all() and (g[3] == o[3]).all()
+    eu, ei = frob_rel(g[0], o[0]), frob_rel(g[1], o[1])
+    assert eu <= TOL and ei <= TOL, (eu, ei)
+    nu, ni, nnz = 4000, 600, 120000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=3, implicit=implicit)
+    _, g, o = run_both(native, oracle, nu, ni, u, i, r, 48, 8, 0.01, implicit, 1.0, dedup=1 if implicit else 2)
+    eu, ei = frob_rel(g[0], o[0]), frob_rel(g[1], o[1])
+    assert eu <= TOL and ei <= TOL, (eu, ei)
+
+
 def test_config_c1_recommendation_template(native, oracle):
     """BASELINE.json configs[0]: rank 10, 10k x 1k, 100k ratings, explicit, lambda 0.01, 20 iterations, seed 3."""
     nu, ni, nnz = 10000, 1000, 100000
