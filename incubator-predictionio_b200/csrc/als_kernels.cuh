@@ -41,6 +41,12 @@ struct SolveParams {
   int row_begin;         // local rows [row_begin, row_end) are covered by this launch
   int row_end;
   int dst_row_offset;    // internal id of local row 0
+  // optional work list (parts of very long rows): item i covers ratings [wl_beg[i], wl_end[i]); its Gramian
+  // blocks and right-hand side go to partial[i * (SLOT + KP)] instead of being solved in this kernel
+  const long long* wl_beg;
+  const long long* wl_end;
+  float* partial;
+  int n_items;
 };
 
 template <int KP_, int TB_, int NG_, int CH_>
@@ -88,6 +94,14 @@ template <int TB, int NB>
 __device__ __forceinline__ int f4slot(int cg) {
   if (TB == 8) return (cg & 1) * NB + (cg >> 1);
   return cg;
+}
+
+// pivots of a positive definite fp32 matrix are far from the denormal range: the flush-to-zero approximation plus one
+// Newton step (in the callers) gives 1/sqrt to ~1 ulp without rsqrtf()'s denormal fix-up code
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 // inverse of f4slot: which source column group lands in staged slot sl
@@ -160,7 +174,7 @@ __device__ __forceinline__ void chol_solve_warp(float* slot, const float* bvec, 
     const float bj = __shfl_sync(0xffffffffu, bAv, j);
     float dd = d;
     if (!(dd > 0.f)) { bad = true; dd = 1.f; }
-    float inv = rsqrtf(dd);
+    float inv = rsqrt_fast(dd);
     inv = inv * (1.5f - 0.5f * dd * inv * inv);
     const float yj = bj * inv;
     const float la = ra[j] * inv;
@@ -225,7 +239,7 @@ __device__ __forceinline__ void chol_solve_warp(float* slot, const float* bvec, 
     const float bj = __shfl_sync(0xffffffffu, bBv, j);
     float dd = d;
     if (!(dd > 0.f)) { bad = true; dd = 1.f; }
-    float inv = rsqrtf(dd);
+    float inv = rsqrt_fast(dd);
     inv = inv * (1.5f - 0.5f * dd * inv * inv);
     const float yj = bj * inv;
     const float l2 = r2[j] * inv;
@@ -300,7 +314,7 @@ __device__ void chol_solve_cta(const float* slot, const float* bvec, const float
     if (tid == 0) {
       float d = Lm[j * LD + j];
       if (!(d > 0.f)) { s_bad = 1; d = 1.f; }
-      float inv = rsqrtf(d);
+      float inv = rsqrt_fast(d);
       inv = inv * (1.5f - 0.5f * d * inv * inv);
       s_inv = inv;
       Lm[j * LD + j] = d * inv;
@@ -383,7 +397,18 @@ als_solve_kernel(const SolveParams p) {
   }
 
   if (tid < NG) {
-    if (!HEAVY) {
+    if (!HEAVY && p.partial) {
+      const int item = blockIdx.x * NG + tid;
+      if (item < p.n_items) {
+        segb[tid] = p.wl_beg[item];
+        sege[tid] = p.wl_end[item];
+        srow[tid] = item;
+      } else {
+        segb[tid] = 0;
+        sege[tid] = 0;
+        srow[tid] = -1;
+      }
+    } else if (!HEAVY) {
       const int r = p.row_begin + blockIdx.x * NG + tid;
       if (r < p.row_end) {
         segb[tid] = p.ptr[r];
@@ -579,6 +604,22 @@ als_solve_kernel(const SolveParams p) {
     }
   }
   __syncthreads();  // ring + bpart are dead from here on (LIGHT: slots alias them)
+  if (!HEAVY && p.partial) {
+    // part of a long row: emit the partial normal equations; als_finish_kernel sums the parts and solves
+    if (worker && srow[g] >= 0) {
+      float* out = p.partial + (size_t)srow[g] * (SLOT + KP) + bid * BLK;
+#pragma unroll
+      for (int a = 0; a < TB; ++a)
+#pragma unroll
+        for (int b = 0; b < TB; b += 4)
+          *reinterpret_cast<float4*>(out + a * TB + b) = make_float4(acc[a][b], acc[a][b + 1], acc[a][b + 2], acc[a][b + 3]);
+    }
+    for (int o = tid; o < NG * KP; o += NT) {
+      const int gg = o / KP;
+      if (srow[gg] >= 0) p.partial[(size_t)srow[gg] * (SLOT + KP) + SLOT + (o % KP)] = bvec[o];
+    }
+    return;
+  }
   if (worker) {
 #pragma unroll
     for (int a = 0; a < TB; ++a)
@@ -622,6 +663,49 @@ als_solve_kernel(const SolveParams p) {
                                                  lm, p.dst + (size_t)(p.dst_row_offset + r) * KP,
                                                  p.fail);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Finish kernel for rows that were split into parts: fixed-order sum of the partial normal equations,
+// then the same Cholesky + solves. One warp per row (rank <= 64) or one CTA per row (rank > 64).
+// ------------------------------------------------------------------------------------------
+template <class Cfg, bool IMPLICIT>
+__global__ void __launch_bounds__(Cfg::WARP_CHOL ? 128 : Cfg::NT)
+als_finish_kernel(const SolveParams p, const int* __restrict__ row_part_ptr, int n_rows) {
+  constexpr int KP = Cfg::KP, SLOT = Cfg::SLOT;
+  extern __shared__ __align__(16) float fsm[];
+  if (Cfg::WARP_CHOL) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 4 + w;
+    if (r >= n_rows) return;
+    float* slot = fsm + w * (SLOT + 4 * KP);
+    float* bv = slot + SLOT;
+    float* colbuf = bv + KP;
+    float* dinv = colbuf + 2 * KP;
+    const int p0 = row_part_ptr[r], p1 = row_part_ptr[r + 1];
+    for (int o = lane; o < SLOT + KP; o += 32) {
+      float s = 0.f;
+      for (int q = p0; q < p1; ++q) s += p.partial[(size_t)q * (SLOT + KP) + o];
+      slot[o] = s;   // o >= SLOT lands in bv (contiguous)
+    }
+    __syncwarp();
+    chol_solve_warp<Cfg::WARP_CHOL ? KP : 16, Cfg::TB, Cfg::BLK, IMPLICIT>(
+        slot, bv, p.yty, p.lambda * p.nreg[r], p.k, colbuf, dinv, p.dst + (size_t)(p.dst_row_offset + r) * KP, p.fail);
+  } else {
+    const int r = blockIdx.x;
+    float* slot = fsm;
+    float* bv = slot + SLOT;
+    float* lm = bv + KP;
+    const int p0 = row_part_ptr[r], p1 = row_part_ptr[r + 1];
+    for (int o = threadIdx.x; o < SLOT + KP; o += Cfg::NT) {
+      float s = 0.f;
+      for (int q = p0; q < p1; ++q) s += p.partial[(size_t)q * (SLOT + KP) + o];
+      slot[o] = s;
+    }
+    __syncthreads();
+    chol_solve_cta<KP, Cfg::TB, Cfg::BLK, IMPLICIT, Cfg::NT>(slot, bv, p.yty, p.lambda * p.nreg[r], p.k, lm,
+                                                             p.dst + (size_t)(p.dst_row_offset + r) * KP, p.fail);
   }
 }
 

@@ -46,7 +46,7 @@ constexpr int STAGE_BYTES = STAGE_KB * KB_BYTES;      // 12288
 constexpr int NSTAGE = 4;
 constexpr int NRAW = 6;                          // raw ring: stages of cp.async gathers in flight per producer warp
 constexpr int MD = 8;                            // metadata (index/rating) look-ahead beyond the gather cursor, in stages
-constexpr int QN = 12;                           // metadata ring entries
+constexpr int QN = 10;                           // metadata ring entries
 constexpr int SEG = 21 * STAGE_RATINGS;          // 504 ratings per accumulation segment
 constexpr int NTEAM = 3;
 constexpr int NSLOT = 4;
@@ -80,7 +80,7 @@ struct Smem {
   alignas(1024) unsigned char stage[NSTAGE][STAGE_BYTES];
   alignas(16) float aslot[NTEAM][NSLOT][ASLOT];
   alignas(16) float bslot[NTEAM][NSLOT][KP];
-  alignas(16) float bstage[NTEAM][NSLOT][KP];
+  alignas(16) float bstage[NTEAM][2][NSLOT][KP];
   alignas(16) float bpart[STAGE_KB][KP];
   alignas(16) float4 raw[STAGE_KB][NRAW][4][32];   // per producer warp: gathered rows, [j][lane] -> conflict-free
   float rawval[STAGE_KB][NRAW][32];
@@ -90,13 +90,13 @@ struct Smem {
   unsigned int rawgrp[STAGE_KB][NRAW];
   alignas(16) float colbuf[NTEAM * NSLOT][2 * KP];
   alignas(16) float dinv[NTEAM * NSLOT][KP];
-  BatchDesc desc[NTEAM];
+  BatchDesc desc[NTEAM][2];   // double-buffered per team: batch n+1 is produced while the team still solves batch n
   alignas(8) unsigned long long full[NSTAGE];
   unsigned long long empty[NSTAGE];
-  unsigned long long descfull[NTEAM];
-  unsigned long long accfull[NTEAM];
-  unsigned long long teamdone[NTEAM];
-  unsigned long long bfull[NTEAM];
+  unsigned long long descfull[NTEAM][2];
+  unsigned long long accfull[NTEAM][2];
+  unsigned long long teamdone[NTEAM][2];
+  unsigned long long bfull[NTEAM][2];
   unsigned long long tmemfree[2];
   unsigned int tmem_base;
 };
@@ -250,12 +250,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       mbar_init(&sm.full[i], STAGE_KB);
       mbar_init(&sm.empty[i], 1);
     }
-    for (int t = 0; t < NTEAM; ++t) {
-      mbar_init(&sm.descfull[t], 1);
-      mbar_init(&sm.accfull[t], 1);
-      mbar_init(&sm.teamdone[t], NSLOT);
-      mbar_init(&sm.bfull[t], 1);
-    }
+    for (int t = 0; t < NTEAM; ++t)
+      for (int bf = 0; bf < 2; ++bf) {
+        mbar_init(&sm.descfull[t][bf], 1);
+        mbar_init(&sm.accfull[t][bf], 1);
+        mbar_init(&sm.teamdone[t][bf], NSLOT);
+        mbar_init(&sm.bfull[t][bf], 1);
+      }
     mbar_init(&sm.tmemfree[0], NSLOT);
     mbar_init(&sm.tmemfree[1], NSLOT);
     fence_barrier_init();
@@ -314,12 +315,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       }
       (void)out_of_rows;
       // returns false when team t has nothing left
-      auto team_free = [&](int t) -> bool { return mbar_test(&sm.teamdone[t], (nbatch_team[t] & 1) ^ 1); };
+      // batch n of team t lives in buffer n&1; the buffer is free once batch n-2 (its previous user) is done
+      auto team_free = [&](int t) -> bool {
+        const int n = nbatch_team[t];
+        return mbar_test(&sm.teamdone[t][n & 1], ((n >> 1) & 1) ^ 1);
+      };
       auto build = [&](int t) -> bool {
+        const int nbt = nbatch_team[t];
+        const int bf = nbt & 1;
         T_BEGIN();
-        mbar_wait(&sm.teamdone[t], (nbatch_team[t] & 1) ^ 1);  // previous batch of this team fully consumed
+        mbar_wait(&sm.teamdone[t][bf], ((nbt >> 1) & 1) ^ 1);
         T_END(0);
-        BatchDesc& d = sm.desc[t];
+        BatchDesc& d = sm.desc[t][bf];
         bool any = false;
         int ns = 0;
         for (int s = 0; s < NSLOT; ++s) {
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
         d.nstages = ns;
         d.exit = any ? 0 : 1;
         d.seq = any ? (int)(nbuilt++) : 0;
-        mbar_arrive(&sm.descfull[t]);
+        mbar_arrive(&sm.descfull[t][bf]);
         ++nbatch_team[t];
         if (!any) exited[t] = true;
         return any;
@@ -372,6 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       int b = 0;
       bool have[2] = {false, false};
       int team_of[2] = {0, 0};
+      int buf_of[2] = {0, 0};
       int cursor = 0;
       auto next_team = [&]() -> int {
         for (int k = 0; k < NTEAM; ++k) {
@@ -385,9 +393,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
         while (true) {
           const int t = next_team();
           if (t < 0) return true;
-          if (!allow_cur && have[cur] && (t == team_of[cur] || !team_free(t))) return false;  // do not stall the MMAs of `cur`
+          if (!allow_cur && have[cur] && !team_free(t)) return false;  // do not stall the MMAs of `cur`
           cursor = (t + 1) % NTEAM;
           team_of[nxt] = t;
+          buf_of[nxt] = nbatch_team[t] & 1;
           if (build(t)) { have[nxt] = true; return true; }
         }
       };
@@ -398,7 +407,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
         const bool settled = try_publish(cur, nxt, false);
         if (have[cur]) {
           const int t = team_of[cur];
-          const BatchDesc& d = sm.desc[t];
+          const BatchDesc& d = sm.desc[t][buf_of[cur]];
           const uint32_t set = nmma_batches & 1;                         // TMEM accumulator set of this batch
           T_BEGIN();
           mbar_wait(&sm.tmemfree[set], ((nmma_batches >> 1) & 1) ^ 1);   // batch b-2 (same set) has been drained
@@ -425,7 +434,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
             }
             umma_commit(&sm.empty[st]);
           }
-          umma_commit(&sm.accfull[t]);
+          umma_commit(&sm.accfull[t][buf_of[cur]]);
           ++nmma_batches;
         }
         if (!settled) try_publish(cur, nxt, true);
@@ -447,12 +456,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
     const int sgb = ((lane >> 2) & 1) + 2 * (lane >> 4);   // sg_j = sgb + 4 j
     const int kl = pw * KB_RATINGS + kr;                    // rating index inside a stage
     // cursor = (team t, stage index i of n) + which descriptors were consumed (scalars only)
-    uint32_t l_ex = 0, l_par = 0, c_ex = 0, c_par = 0;      // exited masks / per-team batch parity bits
-    int l_cur = 0, l_t = 0, l_i = 0, l_n = 0;               // look-ahead cursor
-    int c_cur = 0, c_t = 0, c_i = -1, c_n = 0;              // convert cursor (c_i = -1: before the first stage)
+    uint32_t l_ex = 0, l_par = 0, c_ex = 0, c_par = 0;      // exited masks / per-team batch counters (2 bits each, mod 4)
+    int l_cur = 0, l_t = 0, l_b = 0, l_i = 0, l_n = 0;      // look-ahead cursor (team, buffer, stage index, #stages)
+    int c_cur = 0, c_t = 0, c_b = 0, c_i = -1, c_n = 0;     // convert cursor (c_i = -1: before the first stage)
     bool l_done = false, c_done = false;
     // move a cursor to the first stage of the next batch; returns false if finished or (non-blocking) not published yet
-    auto next_batch = [&](uint32_t& ex, uint32_t& par, int& cur, int& t, int& n, bool& done, bool blocking) -> bool {
+    auto next_batch = [&](uint32_t& ex, uint32_t& par, int& cur, int& t, int& bf, int& n, bool& done, bool blocking) -> bool {
       while (true) {
         int nt = -1;
 #pragma unroll
@@ -461,14 +470,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
           if (nt < 0 && !((ex >> cand) & 1u)) nt = cand;
         }
         if (nt < 0) { done = true; return false; }
-        const uint32_t pb = (par >> nt) & 1u;
-        if (blocking) mbar_wait(&sm.descfull[nt], pb);
-        else if (!mbar_test(&sm.descfull[nt], pb)) return false;
-        par ^= 1u << nt;
+        const uint32_t cnt = (par >> (2 * nt)) & 3u;   // batches of team nt consumed so far, mod 4
+        const int nbf = (int)(cnt & 1u);
+        const uint32_t pb = (cnt >> 1) & 1u;
+        if (blocking) mbar_wait(&sm.descfull[nt][nbf], pb);
+        else if (!mbar_test(&sm.descfull[nt][nbf], pb)) return false;
+        par = (par & ~(3u << (2 * nt))) | (((cnt + 1u) & 3u) << (2 * nt));
         cur = (nt + 1) % NTEAM;
-        if (sm.desc[nt].exit) { ex |= 1u << nt; continue; }
+        if (sm.desc[nt][nbf].exit) { ex |= 1u << nt; continue; }
         t = nt;
-        n = sm.desc[nt].nstages;
+        bf = nbf;
+        n = sm.desc[nt][nbf].nstages;
         return true;
       }
     };
@@ -486,7 +498,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       cp_async_wait_dyn(pend);
       g_done = g_total - (pend < 8u ? pend : 8u);
     };
-    bool l_ready = next_batch(l_ex, l_par, l_cur, l_t, l_n, l_done, true);   // the first descriptor is always published
+    bool l_ready = next_batch(l_ex, l_par, l_cur, l_t, l_b, l_n, l_done, true);   // the first descriptor is always published
     l_i = 0;
     auto pump = [&]() {
       while (true) {
@@ -496,11 +508,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
         while (n_meta < n_issued + (uint32_t)MD) {
           if (!l_ready) {
             if (l_done) break;
-            l_ready = next_batch(l_ex, l_par, l_cur, l_t, l_n, l_done, false);
+            l_ready = next_batch(l_ex, l_par, l_cur, l_t, l_b, l_n, l_done, false);
             l_i = 0;
             if (!l_ready) break;
           }
-          const StageEnt se = sm.desc[l_t].st[l_i];
+          const StageEnt se = sm.desc[l_t][l_b].st[l_i];
           const int ms = n_meta % QN;
           if (kl < se.valid) {
             cp_async4(&sm.metaidx[pw][ms][lane], p.idx + se.beg + kl);
@@ -549,14 +561,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       // advance the convert cursor (blocking on the next descriptor only when its batch is exhausted)
       T_BEGIN();
       if (++c_i >= c_n) {
-        if (c_done || !next_batch(c_ex, c_par, c_cur, c_t, c_n, c_done, true)) { T_END(0); break; }
+        if (c_done || !next_batch(c_ex, c_par, c_cur, c_t, c_b, c_n, c_done, true)) { T_END(0); break; }
         c_i = 0;
       }
       T_END(0);
       T_BEGIN();
       pump();   // the blocking advance may have consumed a fresh descriptor the look-ahead was waiting for
       T_END(1);
-      const StageEnt se = sm.desc[c_t].st[c_i];
+      const StageEnt se = sm.desc[c_t][c_b].st[c_i];
       __syncwarp();
       T_BEGIN();
       wait_group_id(sm.rawgrp[pw][n_conv % NRAW]);   // the gathers of the stage at the convert cursor
@@ -625,10 +637,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
         }
         named_bar_sync(1, STAGE_KB * 32);
         if (pw == 0) {
-          for (int c = lane; c < KP; c += 32) sm.bstage[c_t][sslot][c] = (sm.bpart[0][c] + sm.bpart[1][c]) + sm.bpart[2][c];
+          for (int c = lane; c < KP; c += 32) sm.bstage[c_t][c_b][sslot][c] = (sm.bpart[0][c] + sm.bpart[1][c]) + sm.bpart[2][c];
           if (se.info & 8) {   // every right-hand side of this batch is in bstage[t]
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.bfull[c_t]);
+            if (lane == 0) mbar_arrive(&sm.bfull[c_t][c_b]);
           }
         }
 #pragma unroll
@@ -646,13 +658,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
     const int barid = 2 + t;
     int nb = 0;
     while (true) {
+      const int bf = nb & 1;
+      const uint32_t ph = (nb >> 1) & 1;
       T_BEGIN();
-      mbar_wait(&sm.descfull[t], nb & 1);
+      mbar_wait(&sm.descfull[t][bf], ph);
       T_END(0);
-      const BatchDesc& d = sm.desc[t];
+      const BatchDesc& d = sm.desc[t][bf];
       if (d.exit) break;
       T_BEGIN();
-      mbar_wait(&sm.accfull[t], nb & 1);
+      mbar_wait(&sm.accfull[t][bf], ph);
       T_END(1);
       tc_fence_after();
       T_BEGIN();
@@ -699,13 +713,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       T_END(2);
       // right-hand side of this segment
       T_BEGIN();
-      mbar_wait(&sm.bfull[t], nb & 1);
+      mbar_wait(&sm.bfull[t][bf], ph);
       T_END(3);
       {
         const int tt = (warp - 4) % 4 * 32 + lane;  // 0..127 within the team
         for (int o = tt; o < NSLOT * KP; o += 128) {
           const int s = o / KP, c = o % KP;
-          if (d.row[s] >= 0) sm.bslot[t][s][c] = d.first[s] ? sm.bstage[t][s][c] : sm.bslot[t][s][c] + sm.bstage[t][s][c];
+          if (d.row[s] >= 0) sm.bslot[t][s][c] = d.first[s] ? sm.bstage[t][bf][s][c] : sm.bslot[t][s][c] + sm.bstage[t][bf][s][c];
         }
       }
       tc_fence_before();
@@ -731,7 +745,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       }
       __syncwarp();
       T_END(5);
-      if (lane == 0) mbar_arrive(&sm.teamdone[t]);
+      if (lane == 0) mbar_arrive(&sm.teamdone[t][bf]);
       ++nb;
     }
   }

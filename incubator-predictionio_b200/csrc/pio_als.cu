@@ -25,8 +25,9 @@
 
 namespace pio {
 
-constexpr int HEAVY_T = 4096;     // FP32 path: rows with more ratings than this are solved one per CTA (split mode)
-constexpr int HEAVY_T_TC = 8192;  // tensor-core path (rank 33..64): longer rows stay on the FP32 split kernel
+constexpr int HEAVY_T = 4096;     // rows with more ratings than this are cut into parts (als_finish_kernel solves them)
+constexpr int HEAVY_T_TC = 8192;  // same threshold when the tensor-core path handles the shorter rows
+constexpr int PART = 2016;        // ratings per part (multiple of every CH and of the tensor-core stage size 24)
 
 static thread_local std::string g_create_error;
 
@@ -310,6 +311,12 @@ struct Side {
   float* F = nullptr;        // [n_internal][KP]
   int* cand_ext = nullptr;   // [n_internal]
   int n_active = 0, n_heavy = 0;
+  // parts of the n_heavy longest local rows
+  long long* part_beg = nullptr;
+  long long* part_end = nullptr;
+  int* row_part_ptr = nullptr;   // [n_heavy + 1]
+  float* partial = nullptr;      // [n_parts][SLOT + KP]
+  int n_parts = 0;
 };
 
 enum EvKind { EV_SOLVE = 0, EV_GRAM = 1, EV_COMM = 2 };
@@ -386,6 +393,8 @@ static void dfree(pio_als_handle* h, T*& p) {
 static void free_side(pio_als_handle* h, Side& s, bool keep_factors) {
   dfree(h, s.perm); dfree(h, s.inv); dfree(h, s.rpos); dfree(h, s.p2i); dfree(h, s.deg); dfree(h, s.npos); dfree(h, s.ptr);
   dfree(h, s.idx); dfree(h, s.val); dfree(h, s.nreg); dfree(h, s.cand_ext);
+  dfree(h, s.part_beg); dfree(h, s.part_end); dfree(h, s.row_part_ptr); dfree(h, s.partial);
+  s.n_parts = 0;
   if (!keep_factors) dfree(h, s.F);
 }
 
@@ -444,6 +453,30 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
   row.n_active = counts[0];
   row.n_heavy = counts[1];
   dfree(h, ptr_full);
+  if (row.n_heavy > 0) {
+    // cut the heavy rows (local rows [0, n_heavy), longest first) into parts of PART ratings
+    std::vector<long long> hp((size_t)row.n_heavy + 1);
+    CK(h, cudaMemcpyAsync(hp.data(), row.ptr, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    std::vector<long long> pb, pe;
+    std::vector<int> rpp((size_t)row.n_heavy + 1);
+    for (int r = 0; r < row.n_heavy; ++r) {
+      rpp[r] = (int)pb.size();
+      for (long long b = hp[r]; b < hp[r + 1]; b += PART) {
+        pb.push_back(b);
+        pe.push_back(b + PART < hp[r + 1] ? b + PART : hp[r + 1]);
+      }
+    }
+    rpp[row.n_heavy] = (int)pb.size();
+    row.n_parts = (int)pb.size();
+    CK(h, dalloc(h, &row.part_beg, pb.size()));
+    CK(h, dalloc(h, &row.part_end, pe.size()));
+    CK(h, dalloc(h, &row.row_part_ptr, rpp.size()));
+    CK(h, cudaMemcpyAsync(row.part_beg, pb.data(), sizeof(long long) * pb.size(), cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(row.part_end, pe.data(), sizeof(long long) * pe.size(), cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(row.row_part_ptr, rpp.data(), sizeof(int) * rpp.size(), cudaMemcpyHostToDevice, st));
+    CK(h, cudaStreamSynchronize(st));
+  }
   (void)W;
   return PIO_ALS_OK;
 }
@@ -639,20 +672,42 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
   p.dst_row_offset = h->cfg.world_rank * dst.R;
   const bool imp = h->cfg.implicit_prefs != 0;
   cudaError_t e = cudaSuccess;
-  // the few very long rows go to stream2 so their long-running CTAs overlap the light batches
-  const bool fork = dst.n_heavy > 0 && dst.n_active > dst.n_heavy;
+  p.wl_beg = nullptr;
+  p.wl_end = nullptr;
+  p.partial = nullptr;
+  p.n_items = 0;
+  // very long rows: their parts run as ordinary light batch items that emit partial normal equations
   if (dst.n_heavy > 0) {
-    p.row_begin = 0;
-    p.row_end = dst.n_heavy;
-    cudaStream_t hs = h->stream;
-    if (fork) {
-      if ((e = cudaEventRecord(h->ev_fork, h->stream)) != cudaSuccess) return e;
-      if ((e = cudaStreamWaitEvent(h->stream2, h->ev_fork, 0)) != cudaSuccess) return e;
-      hs = h->stream2;
+    if (!dst.partial) {
+      if ((e = cudaMallocAsync((void**)&dst.partial, sizeof(float) * (size_t)dst.n_parts * (Cfg::SLOT + Cfg::KP), h->stream)) != cudaSuccess) return e;
     }
-    e = imp ? launch_solve_one<Cfg, true, true>(h, p, dst.n_heavy, hs) : launch_solve_one<Cfg, false, true>(h, p, dst.n_heavy, hs);
+    SolveParams pp = p;
+    pp.wl_beg = dst.part_beg;
+    pp.wl_end = dst.part_end;
+    pp.partial = dst.partial;
+    pp.n_items = dst.n_parts;
+    pp.row_begin = 0;
+    pp.row_end = dst.n_heavy;
+    const int grid = (dst.n_parts + Cfg::NG - 1) / Cfg::NG;
+    e = imp ? launch_solve_one<Cfg, true, false>(h, pp, grid, h->stream) : launch_solve_one<Cfg, false, false>(h, pp, grid, h->stream);
     if (e != cudaSuccess) return e;
-    if (fork && (e = cudaEventRecord(h->ev_join, h->stream2)) != cudaSuccess) return e;
+    // finish: sum the parts of every heavy row in fixed order, then Cholesky
+    {
+      static bool fattr[64] = {};
+      const size_t fsmem = Cfg::WARP_CHOL ? sizeof(float) * 4 * (Cfg::SLOT + 4 * Cfg::KP)
+                                          : sizeof(float) * (Cfg::SLOT + Cfg::KP + Cfg::LM);
+      auto fk = imp ? als_finish_kernel<Cfg, true> : als_finish_kernel<Cfg, false>;
+      if (h->cfg.device < 64 && !fattr[h->cfg.device]) {
+        if ((e = cudaFuncSetAttribute(als_finish_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(als_finish_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)) != cudaSuccess) return e;
+        fattr[h->cfg.device] = true;
+      }
+      const int fgrid = Cfg::WARP_CHOL ? (dst.n_heavy + 3) / 4 : dst.n_heavy;
+      fk<<<fgrid, Cfg::WARP_CHOL ? 128 : Cfg::NT, fsmem, h->stream>>>(pp, dst.row_part_ptr, dst.n_heavy);
+      LAUNCHED(h);
+      ++h->st.solve_launches;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
   }
   const int nlight = dst.n_active - dst.n_heavy;
   if (nlight > 0) {
@@ -702,7 +757,6 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
       if (e != cudaSuccess) return e;
     }
   }
-  if (fork) e = cudaStreamWaitEvent(h->stream, h->ev_join, 0);
   return e;
 }
 

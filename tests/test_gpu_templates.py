@@ -124,3 +124,60 @@ def test_classification_template(tmp_path, monkeypatch, oracle):
     algo = cl.NaiveBayesAlgorithm(ep.algorithmParamsList[0][1])
     pred = [algo.predict(model, cl.Query(*map(float, r[1:]))).label for r in rows[:50]]
     assert pred == [float(v) for v in oracle.nb_predict(x[:50], opi, oth)]
+
+
+def test_ecommerce_template(tmp_path, monkeypatch, oracle):
+    """ECommAlgorithm: explicit ALS.train on rate events where the LATEST rating of a (user,item) pair wins
+    (genMLlibRating, ECommAlgorithm.scala:163-203) -- the reduceByKey runs on the GPU (dedup = keep_last)."""
+    monkeypatch.setenv("PIO_EVENTDATA_DIR", str(tmp_path / "events"))
+    monkeypatch.setenv("PIO_MODELDATA_DIR", str(tmp_path / "models"))
+    nu, ni = 120, 40
+    t0 = dt.datetime(2021, 1, 1, tzinfo=dt.timezone.utc)
+    sets = [dict(event="$set", entityType="user", entityId=f"u{k}", eventTime=t0.isoformat()) for k in range(nu)]
+    sets += [dict(event="$set", entityType="item", entityId=f"i{k}", eventTime=t0.isoformat(),
+                  properties={"categories": ["c%d" % (k % 3)]}) for k in range(ni)]
+    rng = np.random.default_rng(5)
+    evs = []
+    for e in range(2500):     # many repeated pairs with different times / ratings
+        evs.append(dict(event="rate", entityType="user", entityId=f"u{rng.integers(nu)}", targetEntityType="item",
+                        targetEntityId=f"i{rng.integers(ni)}", properties={"rating": float(rng.integers(1, 6))},
+                        eventTime=(t0 + dt.timedelta(seconds=int(rng.integers(0, 100000)))).isoformat()))
+    for e in range(300):
+        evs.append(dict(event="buy", entityType="user", entityId=f"u{rng.integers(nu)}", targetEntityType="item",
+                        targetEntityId=f"i{rng.integers(ni)}", eventTime=(t0 + dt.timedelta(seconds=e)).isoformat()))
+    s.import_events("Shop", sets + evs)
+    from pio_b200.templates import ecommerce as ec
+    eng = ec.ECommerceRecommendationEngine().apply()
+    ep = eng.jValueToEngineParams({"datasource": {"params": {"appName": "Shop"}},
+                                   "algorithms": [{"name": "ecomm", "params": {
+                                       "appName": "Shop", "unseenOnly": True, "seenEvents": ["buy"],
+                                       "similarEvents": ["view"], "rank": 8, "numIterations": 6, "lambda": 0.05,
+                                       "seed": 3}}]})
+    sc = w.WorkflowContext()
+    m = eng.prepareDeploy(sc, ep, "shop", eng.train(sc, ep, "shop"))[0]
+    # oracle with host-side latest-wins preparation
+    rates = [e for e in evs if e["event"] == "rate"]
+    um, im = m.userStringIntMap, m.itemStringIntMap
+    u = np.array([um(e["entityId"]) for e in rates], np.int32)
+    i = np.array([im(e["targetEntityId"]) for e in rates], np.int32)
+    r = np.array([e["properties"]["rating"] for e in rates], np.float32)
+    ts = np.array([int(dt.datetime.fromisoformat(e["eventTime"]).timestamp() * 1000) for e in rates], np.int64)
+    uu, ii, rr = oracle.dedup_coo(u, i, r, "keep_last", ts)
+    u0, i0 = synth.synth_init_factors(um.size, 8, 3, 0), synth.synth_init_factors(im.size, 8, 3, 1)
+    ouf, oitf, ouh, oih = oracle.als_train(um.size, im.size, uu, ii, rr, 8, 6, 0.05, False, 1.0, u0, i0)
+    assert np.linalg.norm(m.mf.userFeatures - ouf) / np.linalg.norm(ouf) <= 1e-4
+    assert np.linalg.norm(m.mf.productFeatures - oitf) / np.linalg.norm(oitf) <= 1e-4
+    algo = ec.ECommAlgorithm(ep.algorithmParamsList[0][1])
+    known = next(e["entityId"] for e in rates)
+    bought = {e["targetEntityId"] for e in evs if e["event"] == "buy" and e["entityId"] == known}
+    res = algo.predict(m, ec.Query(user=known, num=5))
+    assert res.itemScores and all(x.score > 0 for x in res.itemScores)
+    assert not (bought & {x.item for x in res.itemScores})                    # unseenOnly
+    res = algo.predict(m, ec.Query(user=known, num=40, categories={"c1"}))
+    assert all(int(x.item[1:]) % 3 == 1 for x in res.itemScores)
+    res = algo.predict(m, ec.Query(user="stranger", num=3))                   # unknown user, no recent views -> popularity
+    counts = {}
+    for e in evs:
+        if e["event"] == "buy":
+            counts[e["targetEntityId"]] = counts.get(e["targetEntityId"], 0) + 1
+    assert [x.score for x in res.itemScores] == sorted(counts.values(), reverse=True)[:3]
