@@ -44,9 +44,9 @@ constexpr int STAGE_KB = 3;                      // one K-block per producer war
 constexpr int STAGE_RATINGS = STAGE_KB * KB_RATINGS;  // 24
 constexpr int STAGE_BYTES = STAGE_KB * KB_BYTES;      // 12288
 constexpr int NSTAGE = 4;
-constexpr int NRAW = 6;                          // raw ring: stages of cp.async gathers in flight per producer warp
-constexpr int MD = 8;                            // metadata (index/rating) look-ahead beyond the gather cursor, in stages
-constexpr int QN = 10;                           // metadata ring entries
+constexpr int NRAW = 6;                          // raw ring: stages of gathered rows in flight
+constexpr int RAW_ROW = 288;                     // bytes per gathered row in the raw ring (256 + 32 pad: conflict-free LDS.128)
+constexpr int NCONV = 2;                         // converter warps (each owns every NCONV-th stage)
 constexpr int SEG = 21 * STAGE_RATINGS;          // 504 ratings per accumulation segment
 constexpr int NTEAM = 3;
 constexpr int NSLOT = 4;
@@ -81,13 +81,9 @@ struct Smem {
   alignas(16) float aslot[NTEAM][NSLOT][ASLOT];
   alignas(16) float bslot[NTEAM][NSLOT][KP];
   alignas(16) float bstage[NTEAM][2][NSLOT][KP];
-  alignas(16) float bpart[STAGE_KB][KP];
-  alignas(16) float4 raw[STAGE_KB][NRAW][4][32];   // per producer warp: gathered rows, [j][lane] -> conflict-free
-  float rawval[STAGE_KB][NRAW][32];
-  int metaidx[STAGE_KB][QN][32];
-  float metaval[STAGE_KB][QN][32];
-  unsigned int metagrp[STAGE_KB][QN];
-  unsigned int rawgrp[STAGE_KB][NRAW];
+  alignas(16) float bpart[NCONV][KP];
+  alignas(16) unsigned char raw[NRAW][STAGE_RATINGS * RAW_ROW];   // gathered source rows (cp.async.bulk destinations)
+  float rawval[NRAW][32];                                          // their ratings
   alignas(16) float colbuf[NTEAM * NSLOT][2 * KP];
   alignas(16) float dinv[NTEAM * NSLOT][KP];
   BatchDesc desc[NTEAM][2];   // double-buffered per team: batch n+1 is produced while the team still solves batch n
@@ -98,6 +94,8 @@ struct Smem {
   unsigned long long teamdone[NTEAM][2];
   unsigned long long bfull[NTEAM][2];
   unsigned long long tmemfree[2];
+  unsigned long long rawfull[NRAW];    // gather warp -> converters (transaction-count barrier)
+  unsigned long long rawempty[NRAW];   // converters -> gather warp
   unsigned int tmem_base;
 };
 
@@ -170,6 +168,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+// one contiguous global -> shared copy (UBLKCP); completion is signalled on the mbarrier's transaction count
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(s32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s32(smem_dst)), "l"(gsrc));
@@ -247,8 +254,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
 
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
-      mbar_init(&sm.full[i], STAGE_KB);
+      mbar_init(&sm.full[i], 1);
       mbar_init(&sm.empty[i], 1);
+    }
+    for (int i = 0; i < NRAW; ++i) {
+      mbar_init(&sm.rawfull[i], 1);
+      mbar_init(&sm.rawempty[i], 1);
     }
     for (int t = 0; t < NTEAM; ++t)
       for (int bf = 0; bf < 2; ++bf) {
@@ -445,211 +456,198 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
     __syncwarp();
   } else if (warp <= STAGE_KB) {
     // ================= producers =================
-    // Three positions walk the scheduler's flat stage lists in the same order:
-    //   look-ahead (metadata cp.async, MD stages beyond the gathers) -> gather issue (cp.async of source rows into
-    //   this warp's raw ring) -> convert (scale, hi/lo split, UMMA tile).  Only the convert position ever blocks
-    //   on a descriptor; the look-ahead just stops at a batch whose descriptor is not published yet.
-    const int pw = warp - 1;            // K-block inside the stage
-    // lane -> (rating kr inside the K-block, source float4 groups sg_j): a quarter-warp holds 4 ratings
-    // (kr%4 = 0..3) x 2 halves of one 32-byte chunk -> its 8 STS.128 hit 8 distinct 16-byte bank groups
-    const int kr = ((lane >> 3) & 1) * 4 + (lane & 3);
-    const int sgb = ((lane >> 2) & 1) + 2 * (lane >> 4);   // sg_j = sgb + 4 j
-    const int kl = pw * KB_RATINGS + kr;                    // rating index inside a stage
-    // cursor = (team t, stage index i of n) + which descriptors were consumed (scalars only)
-    uint32_t l_ex = 0, l_par = 0, c_ex = 0, c_par = 0;      // exited masks / per-team batch counters (2 bits each, mod 4)
-    int l_cur = 0, l_t = 0, l_b = 0, l_i = 0, l_n = 0;      // look-ahead cursor (team, buffer, stage index, #stages)
-    int c_cur = 0, c_t = 0, c_b = 0, c_i = -1, c_n = 0;     // convert cursor (c_i = -1: before the first stage)
-    bool l_done = false, c_done = false;
-    // move a cursor to the first stage of the next batch; returns false if finished or (non-blocking) not published yet
-    auto next_batch = [&](uint32_t& ex, uint32_t& par, int& cur, int& t, int& bf, int& n, bool& done, bool blocking) -> bool {
+    // warp 1 = gather warp: walks the scheduler's stage lists and, per stage, starts one 256-byte cp.async.bulk
+    //          copy per rating into the raw ring (completion counted on rawfull[]); source indices are loaded
+    //          two stages ahead into a register shift queue.
+    // warps 2,3 = converters: converter cw owns every stage with (stage number % NCONV == cw): it waits for the
+    //          raw rows, scales, splits hi/lo and writes all three K-blocks of the UMMA tile (three independent
+    //          pieces of work per dependency chain), then hands the stage to the MMA issuer.
+    // cursor over the published stage lists (scalars only)
+    uint32_t c_ex = 0, c_par = 0;
+    int c_cur = 0, c_t = 0, c_b = 0, c_i = -1, c_n = 0;
+    bool c_done = false;
+    auto next_batch = [&](bool blocking) -> bool {   // -> first stage of the next batch; false if finished / not published yet
       while (true) {
         int nt = -1;
 #pragma unroll
         for (int k = 0; k < NTEAM; ++k) {
-          const int cand = (cur + k) % NTEAM;
-          if (nt < 0 && !((ex >> cand) & 1u)) nt = cand;
+          const int cand = (c_cur + k) % NTEAM;
+          if (nt < 0 && !((c_ex >> cand) & 1u)) nt = cand;
         }
-        if (nt < 0) { done = true; return false; }
-        const uint32_t cnt = (par >> (2 * nt)) & 3u;   // batches of team nt consumed so far, mod 4
+        if (nt < 0) { c_done = true; return false; }
+        const uint32_t cnt = (c_par >> (2 * nt)) & 3u;   // batches of team nt consumed so far, mod 4
         const int nbf = (int)(cnt & 1u);
         const uint32_t pb = (cnt >> 1) & 1u;
         if (blocking) mbar_wait(&sm.descfull[nt][nbf], pb);
         else if (!mbar_test(&sm.descfull[nt][nbf], pb)) return false;
-        par = (par & ~(3u << (2 * nt))) | (((cnt + 1u) & 3u) << (2 * nt));
-        cur = (nt + 1) % NTEAM;
-        if (sm.desc[nt][nbf].exit) { ex |= 1u << nt; continue; }
-        t = nt;
-        bf = nbf;
-        n = sm.desc[nt][nbf].nstages;
+        c_par = (c_par & ~(3u << (2 * nt))) | (((cnt + 1u) & 3u) << (2 * nt));
+        c_cur = (nt + 1) % NTEAM;
+        if (sm.desc[nt][nbf].exit) { c_ex |= 1u << nt; continue; }
+        c_t = nt;
+        c_b = nbf;
+        c_n = sm.desc[nt][nbf].nstages;
+        c_i = 0;
         return true;
       }
     };
-    uint32_t n_meta = 0, n_issued = 0, n_conv = 0;   // stages whose metadata was requested / gathers issued / converted
-    uint32_t it = 0;                                  // global stage counter (UMMA ring)
-    uint32_t g_total = 0, g_done = 0;                 // cp.async groups committed / known complete (prefix)
-    float bacc[4][4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) bacc[j][c] = 0.f;
-    auto wait_group_id = [&](uint32_t gid) {   // make sure commit group gid has landed
-      if (gid < g_done) return;
-      const uint32_t pend = g_total - 1 - gid;
-      cp_async_wait_dyn(pend);
-      g_done = g_total - (pend < 8u ? pend : 8u);
+    auto advance = [&](bool blocking) -> bool {
+      if (c_done) return false;
+      if (c_i >= 0 && c_i + 1 < c_n) { ++c_i; return true; }
+      return next_batch(blocking);
     };
-    bool l_ready = next_batch(l_ex, l_par, l_cur, l_t, l_b, l_n, l_done, true);   // the first descriptor is always published
-    l_i = 0;
-    auto pump = [&]() {
-      while (true) {
-        // 1. metadata look-ahead: index + rating of future stages (4-byte cp.async, no register dependency)
-        bool requested = false;
-        long long tp1_ = timing ? clock64() : 0;
-        while (n_meta < n_issued + (uint32_t)MD) {
-          if (!l_ready) {
-            if (l_done) break;
-            l_ready = next_batch(l_ex, l_par, l_cur, l_t, l_b, l_n, l_done, false);
-            l_i = 0;
-            if (!l_ready) break;
-          }
-          const StageEnt se = sm.desc[l_t][l_b].st[l_i];
-          const int ms = n_meta % QN;
-          if (kl < se.valid) {
-            cp_async4(&sm.metaidx[pw][ms][lane], p.idx + se.beg + kl);
-            cp_async4(&sm.metaval[pw][ms][lane], p.val + se.beg + kl);
-          } else {
-            sm.metaidx[pw][ms][lane] = -1;
-            sm.metaval[pw][ms][lane] = 0.f;
-          }
-          sm.metagrp[pw][ms] = g_total;   // warp-uniform
-          ++n_meta;
-          requested = true;
-          if (++l_i >= l_n) l_ready = false;
+    if (warp == 1) {
+      // ---------------- gather warp ----------------
+      // queue of the next two stages (beg, valid, index, rating) in registers; q0 is issued next
+      long long qbeg0 = 0, qbeg1 = 0;
+      int qval0 = -1, qval1 = -1;      // valid count; -1 = empty queue slot
+      int qidx0 = -1, qidx1 = -1;
+      float qr0 = 0.f, qr1 = 0.f;
+      uint32_t n_g = 0;                // stages issued
+      bool more = true;
+      auto fetch = [&](long long& qb, int& qv, int& qi, float& qr) {   // pull the next stage (blocking) and start its index load
+        if (!more) { qv = -1; return; }
+        T_BEGIN();
+        more = advance(true);
+        T_END(0);
+        if (!more) { qv = -1; return; }
+        const StageEnt se = sm.desc[c_t][c_b].st[c_i];
+        qb = se.beg;
+        qv = se.valid;
+        qi = -1;
+        qr = 0.f;
+        if (lane < se.valid) {
+          qi = __ldg(p.idx + se.beg + lane);
+          qr = __ldg(p.val + se.beg + lane);
         }
-        if (timing) tacc[5] += clock64() - tp1_;
-        // 2. gathers of the next stage, from indices that have already landed (one commit group per stage)
-        if (n_issued >= n_meta || n_issued - n_conv >= (uint32_t)NRAW) {   // nothing to gather yet / raw ring full
-          if (requested) { cp_async_commit(); ++g_total; }
-          return;
-        }
-        const int ms = n_issued % QN;
+      };
+      fetch(qbeg0, qval0, qidx0, qr0);
+      fetch(qbeg1, qval1, qidx1, qr1);
+      while (qval0 >= 0) {
+        const int rs = n_g % NRAW;
+        T_BEGIN();
+        mbar_wait(&sm.rawempty[rs], ((n_g / NRAW) & 1) ^ 1);   // converters are done with this raw slot
+        T_END(1);
+        T_BEGIN();
+        if (lane < qval0)
+          bulk_copy_g2s(&sm.raw[rs][lane * RAW_ROW], p.src + (size_t)qidx0 * KP, KP * 4, &sm.rawfull[rs]);
+        sm.rawval[rs][lane] = qr0;
         __syncwarp();
-        const uint32_t mg = sm.metagrp[pw][ms];
-        if (mg >= g_total) { cp_async_commit(); ++g_total; }   // its metadata was requested just now (start-up only)
-        long long tp2_ = timing ? clock64() : 0;
-        wait_group_id(mg);                                      // no-op in steady state (MD stages old)
-        const int col = sm.metaidx[pw][ms][lane];
-        if (timing) tacc[6] += clock64() - tp2_ + (col & 0);
-        const int rs = n_issued % NRAW;
-        if (col >= 0) {
-          const float4* srcp = reinterpret_cast<const float4*>(p.src + (size_t)col * KP) + sgb;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) cp_async16(&sm.raw[pw][rs][j][lane], srcp + 4 * j);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) sm.raw[pw][rs][j][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        sm.rawval[pw][rs][lane] = sm.metaval[pw][ms][lane];
-        sm.rawgrp[pw][rs] = g_total;
-        cp_async_commit();
-        ++g_total;
-        ++n_issued;
+        if (lane == 0) mbar_arrive_expect_tx(&sm.rawfull[rs], (uint32_t)qval0 * KP * 4);
+        T_END(2);
+        ++n_g;
+        qbeg0 = qbeg1; qval0 = qval1; qidx0 = qidx1; qr0 = qr1;
+        fetch(qbeg1, qval1, qidx1, qr1);
       }
-    };
-    pump();
-    while (true) {
-      // advance the convert cursor (blocking on the next descriptor only when its batch is exhausted)
-      T_BEGIN();
-      if (++c_i >= c_n) {
-        if (c_done || !next_batch(c_ex, c_par, c_cur, c_t, c_b, c_n, c_done, true)) { T_END(0); break; }
-        c_i = 0;
-      }
-      T_END(0);
-      T_BEGIN();
-      pump();   // the blocking advance may have consumed a fresh descriptor the look-ahead was waiting for
-      T_END(1);
-      const StageEnt se = sm.desc[c_t][c_b].st[c_i];
-      __syncwarp();
-      T_BEGIN();
-      wait_group_id(sm.rawgrp[pw][n_conv % NRAW]);   // the gathers of the stage at the convert cursor
-      T_END(2);
-      const int slot = n_conv % NRAW;
-      const int st = it % NSTAGE;
-      const float cval = sm.rawval[pw][slot][lane];
-      float wb, sc;
-      if (IMPLICIT) {
-        const float c1 = p.alpha * fabsf(cval);
-        wb = cval > 0.f ? 1.f + c1 : 0.f;
-        sc = sqrtf(c1);
-      } else {
-        wb = cval;
-        sc = 1.f;
-      }
-      const bool kb_used = pw * KB_RATINGS < se.valid;
-      T_BEGIN();
-      mbar_wait(&sm.empty[st], ((it / NSTAGE) & 1) ^ 1);
-      T_END(3);
-      T_BEGIN();
-      if (kb_used) {
-        unsigned char* kbp = &sm.stage[st][0] + pw * KB_BYTES + kr * 128;
+    } else {
+      // ---------------- converters ----------------
+      const int cw = warp - 2;
+      // lane -> (rating kr inside a K-block, source float4 groups sg_j = sgb + 4 j): a quarter-warp holds 4 ratings
+      // (kr%4 = 0..3) x 2 halves of one 32-byte chunk -> its 8 STS.128 hit 8 distinct 16-byte bank groups
+      const int kr = ((lane >> 3) & 1) * 4 + (lane & 3);
+      const int sgb = ((lane >> 2) & 1) + 2 * (lane >> 4);
+      uint32_t it = 0;   // global stage counter (UMMA ring + raw ring + ownership)
+      float bacc[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int sg = sgb + 4 * j;
-          const int off = (sg >> 3) * 1024 + ((((sg & 7) >> 1) ^ (kr & 3)) * 32) + (sg & 1) * 16;
-          const float4 y = sm.raw[pw][slot][j][lane];
-          bacc[j][0] = fmaf(wb, y.x, bacc[j][0]);
-          bacc[j][1] = fmaf(wb, y.y, bacc[j][1]);
-          bacc[j][2] = fmaf(wb, y.z, bacc[j][2]);
-          bacc[j][3] = fmaf(wb, y.w, bacc[j][3]);
-          float4 x = y;
-          if (IMPLICIT) { x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; }
-          float4 hi, lo;
-          hi.x = tf32_round(x.x); hi.y = tf32_round(x.y); hi.z = tf32_round(x.z); hi.w = tf32_round(x.w);
-          lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
-          *reinterpret_cast<float4*>(kbp + off) = hi;          // columns 4sg..4sg+3 of the hi half
-          *reinterpret_cast<float4*>(kbp + 2048 + off) = lo;   // same columns of the lo half (mn + 64)
-        }
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.full[st]);
-      T_END(4);
-      ++n_conv;
-      ++it;
-      if (se.info & 4) {
-        // end of a segment: b = reduce over the 8 ratings of the warp (lanes with equal sgb), then over warps
-        const int sslot = se.info & 3;
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int c = 0; c < 4; ++c) bacc[j][c] = 0.f;
+      while (true) {
+        T_BEGIN();
+        const bool ok = advance(true);
+        T_END(0);
+        if (!ok) break;
+        const StageEnt se = sm.desc[c_t][c_b].st[c_i];
+        const bool mine = (it % NCONV) == (uint32_t)cw;
+        if (mine) {
+          const int rs = it % NRAW;
+          const int st = it % NSTAGE;
+          T_BEGIN();
+          mbar_wait(&sm.rawfull[rs], (it / NRAW) & 1);           // gathered rows have landed
+          T_END(1);
+          T_BEGIN();
+          mbar_wait(&sm.empty[st], ((it / NSTAGE) & 1) ^ 1);     // UMMA stage is free
+          T_END(2);
+          T_BEGIN();
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float v = bacc[j][c];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            bacc[j][c] = v;
+          for (int kb = 0; kb < STAGE_KB; ++kb) {
+            if (kb * KB_RATINGS < se.valid) {
+              const int r = kb * KB_RATINGS + kr;                // rating inside the stage
+              const bool live = r < se.valid;
+              const float cval = live ? sm.rawval[rs][r] : 0.f;
+              float wb, sc;
+              if (IMPLICIT) {
+                const float c1 = p.alpha * fabsf(cval);
+                wb = cval > 0.f ? 1.f + c1 : 0.f;
+                sc = sqrtf(c1);
+              } else {
+                wb = cval;
+                sc = 1.f;
+              }
+              const unsigned char* rrow = &sm.raw[rs][r * RAW_ROW];
+              unsigned char* kbp = &sm.stage[st][0] + kb * KB_BYTES + kr * 128;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int sg = sgb + 4 * j;
+                const int off = (sg >> 3) * 1024 + ((((sg & 7) >> 1) ^ (kr & 3)) * 32) + (sg & 1) * 16;
+                float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) y = *reinterpret_cast<const float4*>(rrow + sg * 16);
+                bacc[j][0] = fmaf(wb, y.x, bacc[j][0]);
+                bacc[j][1] = fmaf(wb, y.y, bacc[j][1]);
+                bacc[j][2] = fmaf(wb, y.z, bacc[j][2]);
+                bacc[j][3] = fmaf(wb, y.w, bacc[j][3]);
+                float4 x = y;
+                if (IMPLICIT) { x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; }
+                float4 hi, lo;
+                hi.x = tf32_round(x.x); hi.y = tf32_round(x.y); hi.z = tf32_round(x.z); hi.w = tf32_round(x.w);
+                lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
+                *reinterpret_cast<float4*>(kbp + off) = hi;          // columns 4sg..4sg+3 of the hi half
+                *reinterpret_cast<float4*>(kbp + 2048 + off) = lo;   // same columns of the lo half (mn + 64)
+              }
+            }
           }
-        named_bar_sync(1, STAGE_KB * 32);  // bpart free (previous segment's sum was read)
-        if (kr == 0) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&sm.full[st]);       // -> MMA issuer
+            mbar_arrive(&sm.rawempty[rs]);   // -> gather warp
+          }
+          T_END(3);
+        }
+        ++it;
+        if (se.info & 4) {
+          // end of a segment: every converter reduces its share of b over the 8 rating lanes, then the shares are added
+          const int sslot = se.info & 3;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(&sm.bpart[pw][(sgb + 4 * j) * 4]) = make_float4(bacc[j][0], bacc[j][1], bacc[j][2], bacc[j][3]);
-        }
-        named_bar_sync(1, STAGE_KB * 32);
-        if (pw == 0) {
-          for (int c = lane; c < KP; c += 32) sm.bstage[c_t][c_b][sslot][c] = (sm.bpart[0][c] + sm.bpart[1][c]) + sm.bpart[2][c];
-          if (se.info & 8) {   // every right-hand side of this batch is in bstage[t]
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.bfull[c_t][c_b]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float v = bacc[j][c];
+              v += __shfl_xor_sync(0xffffffffu, v, 1);
+              v += __shfl_xor_sync(0xffffffffu, v, 2);
+              v += __shfl_xor_sync(0xffffffffu, v, 8);
+              bacc[j][c] = v;
+            }
+          named_bar_sync(1, NCONV * 32);  // bpart free (previous segment's sum was read)
+          if (kr == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(&sm.bpart[cw][(sgb + 4 * j) * 4]) = make_float4(bacc[j][0], bacc[j][1], bacc[j][2], bacc[j][3]);
           }
+          named_bar_sync(1, NCONV * 32);
+          if (cw == 0) {
+            for (int c = lane; c < KP; c += 32) sm.bstage[c_t][c_b][sslot][c] = sm.bpart[0][c] + sm.bpart[1][c];
+            if (se.info & 8) {   // every right-hand side of this batch is in bstage[t][buf]
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&sm.bfull[c_t][c_b]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bacc[j][c] = 0.f;
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) bacc[j][c] = 0.f;
       }
     }
-    cp_async_wait<0>();
   } else {
     // ================= teams: drain + solve =================
     const int t = (warp - 4) / 4;
@@ -669,6 +667,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       mbar_wait(&sm.accfull[t][bf], ph);
       T_END(1);
       tc_fence_after();
+      // every warp of the team must have finished solving the previous batch before any A slot is overwritten
+      named_bar_sync(barid, 128);
       T_BEGIN();
       // ---- drain: D row r lives in TMEM lane 32*(r/16) + r%16: lanes 0..15 of warp quarter q hold rows 16q..16q+15
       const uint32_t set = (uint32_t)d.seq & 1u;
