@@ -28,9 +28,14 @@
 // between segments (bounds the length of any single tensor-core accumulation chain).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "als_kernels.cuh"
+
+#ifndef PIO_TC_TIMING
+#define PIO_TC_TIMING 0
+#endif
 
 namespace pio {
 namespace tc {
@@ -43,12 +48,16 @@ constexpr int KB_BYTES = KB_RATINGS * NCOL * 4;  // 4096
 constexpr int STAGE_KB = 3;                      // one K-block per producer warp
 constexpr int STAGE_RATINGS = STAGE_KB * KB_RATINGS;  // 24
 constexpr int STAGE_BYTES = STAGE_KB * KB_BYTES;      // 12288
-constexpr int NSTAGE = 4;
-constexpr int NRAW = 6;                          // raw ring: stages of gathered rows in flight
+constexpr int NSTAGE = 7;
+constexpr int NRAW = 7;                          // raw ring: stages of gathered rows in flight
 constexpr int RAW_ROW = 288;                     // bytes per gathered row in the raw ring (256 + 32 pad: conflict-free LDS.128)
-constexpr int NCONV = 2;                         // converter warps (each owns every NCONV-th stage)
+constexpr int NGATHER = 2;                       // gather warps (each owns every NGATHER-th stage)
+constexpr int NCONV = 5;                         // converter warps (each owns every NCONV-th stage)
+constexpr int CONV0 = 1 + NGATHER;               // first converter warp
+constexpr int TEAM0 = CONV0 + NCONV;             // first drain+solve warp (a multiple of 4: warp%4 = TMEM lane quarter = slot)
+static_assert(TEAM0 % 4 == 0, "team warps must start at a multiple of four");
 constexpr int SEG = 21 * STAGE_RATINGS;          // 504 ratings per accumulation segment
-constexpr int NTEAM = 3;
+constexpr int NTEAM = 2;
 constexpr int NSLOT = 4;
 constexpr int NTHREADS = 512;
 constexpr int H = 32;
@@ -107,18 +116,32 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(s32(bar)),
-      "r"(parity), "r"(200000u)   // suspend-time hint (ns): the waiting warp sleeps instead of polling
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(s32(bar)), "r"(parity), "r"(200000u)   // suspend-time hint (ns): the waiting warp sleeps instead of polling
       : "memory");
+  return ok != 0;
+}
+// Blocking wait with a watchdog: a protocol error must end the kernel with a diagnostic, never hang the GPU.
+__device__ __noinline__ void mbar_timeout(unsigned long long* bar, uint32_t parity) {
+  extern __shared__ __align__(1024) unsigned char tc_smem_base_[];
+  if ((threadIdx.x & 31) == 0) printf("pio tc kernel: mbarrier wait timed out: cta %d warp %d lane %d barrier word %d (full4 empty4 descfull6 accfull6 teamdone6 bfull6 tmemfree2 rawfull6 rawempty6) parity %u\n", (int)blockIdx.x,
+         (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), (int)(s32(bar) - s32(tc_smem_base_) - (uint32_t)offsetof(Smem, full)) / 8, parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) mbar_timeout(bar, parity);   // ~2 s
+  }
 }
 __device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity) {
   uint32_t ok;
@@ -168,6 +191,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// the mbarrier receives one arrival from this thread once all of its earlier cp.async copies have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(s32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
@@ -232,7 +259,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format F32 = 1 at [4,6),
 // a/b format TF32 = 2 at [7,10)/[10,13), a/b major MN = 1 at bits 15/16, N>>3 at [17,23), M>>4 at [24,29).
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((64u >> 4) << 24);
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // M = 128 ([hi|lo] columns), N = 64 (hi columns)
 
 static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget (227 KB) exceeded");
 
@@ -258,7 +285,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       mbar_init(&sm.empty[i], 1);
     }
     for (int i = 0; i < NRAW; ++i) {
-      mbar_init(&sm.rawfull[i], 1);
+      mbar_init(&sm.rawfull[i], 32);   // every lane of the gather warp: cp.async.mbarrier.arrive.noinc
       mbar_init(&sm.rawempty[i], 1);
     }
     for (int t = 0; t < NTEAM; ++t)
@@ -279,7 +306,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
   const uint32_t tmem = sm.tmem_base;
 
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const bool timing = tp.timing != nullptr;
+  // per-role cycle counters are compiled in only with -DPIO_TC_TIMING=1 (tools/tc_timing.py); the default build carries no
+  // instrumentation in the hot loops
+  const bool timing = PIO_TC_TIMING && tp.timing != nullptr;
   long long t0_ = 0;
 #define T_BEGIN() do { if (timing) t0_ = clock64(); } while (0)
 #define T_END(i) do { if (timing) tacc[i] += clock64() - t0_; } while (0)
@@ -290,171 +319,190 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
 
   if (warp == 0) {
     // ================= scheduler + MMA issuer =================
-    if (lane == 0) {
-      int l_row[NTEAM * NSLOT];
-      long long l_pos[NTEAM * NSLOT], l_end[NTEAM * NSLOT];
-      for (int i = 0; i < NTEAM * NSLOT; ++i) { l_row[i] = -1; l_pos[i] = 0; l_end[i] = 0; }
-      bool exited[NTEAM] = {false, false, false};
-      int nbatch_team[NTEAM] = {0, 0, 0};
-      bool out_of_rows = false;
-      uint32_t it = 0;       // global stage counter
-      uint32_t nmma_batches = 0;
-      uint32_t nbuilt = 0;   // batches with work, in publish order == MMA order
-      // Static row assignment (no atomics): rows are degree-sorted; groups of 12 consecutive rows are dealt to
-      // the CTAs in snake order, lane (t,s) of this CTA takes row  g*12 + t*4 + s  of its k-th group g.
-      // The row pointers of a lane's NEXT row are prefetched while the current one is processed.
-      const int per_cta = NTEAM * NSLOT;
-      const int nrows = p.row_end - p.row_begin;
-      const int ngroups = (nrows + per_cta - 1) / per_cta;
-      const int G = (int)gridDim.x;
-      int l_k[NTEAM * NSLOT];
-      bool l_first[NTEAM * NSLOT];
-      long long n_beg[NTEAM * NSLOT], n_end[NTEAM * NSLOT];
-      int n_row[NTEAM * NSLOT];
-      auto row_of = [&](int li, int k) -> int {
-        const long long g = (long long)k * G + ((k & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x);
-        if (g >= ngroups) return -1;
-        const long long r = (long long)p.row_begin + g * per_cta + li;
-        return r < p.row_end ? (int)r : -1;
-      };
-      for (int li = 0; li < NTEAM * NSLOT; ++li) {
-        l_k[li] = 0;
-        l_first[li] = false;
-        n_row[li] = row_of(li, 0);
-        n_beg[li] = n_end[li] = 0;
-        if (n_row[li] >= 0) { n_beg[li] = p.ptr[n_row[li]]; n_end[li] = p.ptr[n_row[li] + 1]; }
-      }
-      (void)out_of_rows;
-      // returns false when team t has nothing left
-      // batch n of team t lives in buffer n&1; the buffer is free once batch n-2 (its previous user) is done
-      auto team_free = [&](int t) -> bool {
-        const int n = nbatch_team[t];
-        return mbar_test(&sm.teamdone[t][n & 1], ((n >> 1) & 1) ^ 1);
-      };
-      auto build = [&](int t) -> bool {
-        const int nbt = nbatch_team[t];
-        const int bf = nbt & 1;
-        T_BEGIN();
-        mbar_wait(&sm.teamdone[t][bf], ((nbt >> 1) & 1) ^ 1);
-        T_END(0);
-        BatchDesc& d = sm.desc[t][bf];
-        bool any = false;
-        int ns = 0;
-        for (int s = 0; s < NSLOT; ++s) {
-          const int li = t * NSLOT + s;
-          if (l_row[li] >= 0 && l_pos[li] >= l_end[li]) l_row[li] = -1;
-          if (l_row[li] < 0 && n_row[li] >= 0) {
-            l_row[li] = n_row[li];
-            l_pos[li] = n_beg[li];
-            l_end[li] = n_end[li];
-            l_first[li] = true;
-            ++l_k[li];
-            n_row[li] = row_of(li, l_k[li]);   // prefetch the pointers of the row after this one
-            if (n_row[li] >= 0) { n_beg[li] = __ldg(p.ptr + n_row[li]); n_end[li] = __ldg(p.ptr + n_row[li] + 1); }
-          }
-          if (l_row[li] >= 0) {
-            long long e = l_pos[li] + SEG;
-            if (e > l_end[li]) e = l_end[li];
-            const int len = (int)(e - l_pos[li]);
-            d.row[s] = l_row[li];
-            d.first[s] = l_first[li] ? 1 : 0;
-            l_first[li] = false;
-            d.last[s] = e == l_end[li];
-            const int nst = (len + STAGE_RATINGS - 1) / STAGE_RATINGS;
-            for (int q = 0; q < nst; ++q) {
-              StageEnt& se = d.st[ns++];
-              se.beg = l_pos[li] + (long long)q * STAGE_RATINGS;
-              const int v = len - q * STAGE_RATINGS;
-              se.valid = v < STAGE_RATINGS ? v : STAGE_RATINGS;
-              se.info = s | (q == nst - 1 ? 4 : 0) | (q == 0 ? 16 : 0);
-            }
-            l_pos[li] = e;
-            any = true;
-          } else {
-            d.row[s] = -1;
-            d.first[s] = 0;
-            d.last[s] = 0;
-          }
+    // Warp-parallel: lane li = t*4+s (< 12) keeps the state of row lane (team t, slot s) in registers; every control
+    // decision is warp-uniform.  Static row assignment (no atomics): rows are degree-sorted; groups of 12 consecutive
+    // rows are dealt to the CTAs in snake order, lane li of this CTA takes row  g*12 + li  of its k-th group g.  The row
+    // pointers of a lane's NEXT row are prefetched while the current one is processed.
+    const int per_cta = NTEAM * NSLOT;
+    const int nrows = p.row_end - p.row_begin;
+    const int ngroups = (nrows + per_cta - 1) / per_cta;
+    const int G = (int)gridDim.x;
+    auto row_of = [&](int k) -> int {
+      const long long g = (long long)k * G + ((k & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x);
+      if (lane >= per_cta || g >= ngroups) return -1;
+      const long long r = (long long)p.row_begin + g * per_cta + lane;
+      return r < p.row_end ? (int)r : -1;
+    };
+    int my_row = -1, my_k = 0;
+    long long my_pos = 0, my_end = 0;
+    bool my_first = false;
+    int nx_row = row_of(0);
+    long long nx_beg = 0, nx_end = 0;
+    if (nx_row >= 0) { nx_beg = p.ptr[nx_row]; nx_end = p.ptr[nx_row + 1]; }
+    uint32_t exited = 0;
+    uint32_t nbp = 0;                // batches published per team, 8 bits each (only the low two bits are ever used)
+    uint32_t it = 0;                 // global stage counter
+    uint32_t nmma_batches = 0;
+    uint32_t nbuilt = 0;             // batches with work, in publish order == MMA order
+    auto nb_of = [&](int t) -> int { return (int)((nbp >> (8 * t)) & 3u); };
+    // batch n of team t lives in buffer n&1; the buffer is free once batch n-2 (its previous user) is done
+    auto team_free = [&](int t) -> bool {
+      const int n = nb_of(t);
+      return mbar_test(&sm.teamdone[t][n & 1], ((n >> 1) & 1) ^ 1);
+    };
+    // publish the next batch of team t; returns false when the team has nothing left (an exit descriptor is published)
+    auto build = [&](int t) -> bool {
+      const int nbt = nb_of(t);
+      const int bf = nbt & 1;
+      T_BEGIN();
+      mbar_wait(&sm.teamdone[t][bf], ((nbt >> 1) & 1) ^ 1);
+      T_END(0);
+      T_BEGIN();
+      BatchDesc& d = sm.desc[t][bf];
+      const bool mine = lane < per_cta && (lane >> 2) == t;
+      int len = 0;
+      long long beg = 0;
+      if (mine) {
+        if (my_row >= 0 && my_pos >= my_end) my_row = -1;
+        if (my_row < 0 && nx_row >= 0) {
+          my_row = nx_row;
+          my_pos = nx_beg;
+          my_end = nx_end;
+          my_first = true;
+          ++my_k;
+          nx_row = row_of(my_k);   // prefetch the pointers of the row after this one
+          if (nx_row >= 0) { nx_beg = __ldg(p.ptr + nx_row); nx_end = __ldg(p.ptr + nx_row + 1); }
         }
-        if (ns > 0) d.st[ns - 1].info |= 8;
+        const int s = lane & 3;
+        if (my_row >= 0) {
+          long long e = my_pos + SEG;
+          if (e > my_end) e = my_end;
+          len = (int)(e - my_pos);
+          beg = my_pos;
+          d.row[s] = my_row;
+          d.first[s] = my_first ? 1 : 0;
+          d.last[s] = e == my_end;
+          my_first = false;
+          my_pos = e;
+        } else {
+          d.row[s] = -1;
+          d.first[s] = 0;
+          d.last[s] = 0;
+        }
+      }
+      const int nst = (len + STAGE_RATINGS - 1) / STAGE_RATINGS;
+      int n_[NSLOT], l_[NSLOT];
+      long long b_[NSLOT];
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) {
+        n_[s] = __shfl_sync(0xffffffffu, nst, t * NSLOT + s);
+        l_[s] = __shfl_sync(0xffffffffu, len, t * NSLOT + s);
+        b_[s] = __shfl_sync(0xffffffffu, beg, t * NSLOT + s);
+      }
+      const int ns = n_[0] + n_[1] + n_[2] + n_[3];
+      for (int e = lane; e < ns; e += 32) {   // the flat stage list, one entry per lane and pass
+        int s = 0, q = e;
+#pragma unroll
+        for (int k = 0; k < NSLOT - 1; ++k)
+          if (s == k && q >= n_[k]) { q -= n_[k]; s = k + 1; }
+        const int ls = s == 0 ? l_[0] : (s == 1 ? l_[1] : (s == 2 ? l_[2] : l_[3]));
+        const int nn = s == 0 ? n_[0] : (s == 1 ? n_[1] : (s == 2 ? n_[2] : n_[3]));
+        const long long bs = s == 0 ? b_[0] : (s == 1 ? b_[1] : (s == 2 ? b_[2] : b_[3]));
+        StageEnt se;
+        se.beg = bs + (long long)q * STAGE_RATINGS;
+        const int v = ls - q * STAGE_RATINGS;
+        se.valid = v < STAGE_RATINGS ? v : STAGE_RATINGS;
+        se.info = s | (q == nn - 1 ? 4 : 0) | (q == 0 ? 16 : 0) | (e == ns - 1 ? 8 : 0);
+        d.st[e] = se;
+      }
+      const bool any = ns > 0;
+      if (lane == 0) {
         d.nstages = ns;
         d.exit = any ? 0 : 1;
-        d.seq = any ? (int)(nbuilt++) : 0;
-        mbar_arrive(&sm.descfull[t][bf]);
-        ++nbatch_team[t];
-        if (!any) exited[t] = true;
-        return any;
-      };
-      // software pipeline: the descriptor of batch b+1 is published before the MMAs of batch b are issued,
-      // unless b+1 belongs to the same team as b (then its teamdone can only complete after b's MMAs).
-      int b = 0;
-      bool have[2] = {false, false};
-      int team_of[2] = {0, 0};
-      int buf_of[2] = {0, 0};
-      int cursor = 0;
-      auto next_team = [&]() -> int {
-        for (int k = 0; k < NTEAM; ++k) {
-          const int t = (cursor + k) % NTEAM;
-          if (!exited[t]) return t;
-        }
-        return -1;
-      };
-      // returns true when publishing for slot `nxt` is settled (a batch was found or every team exited)
-      auto try_publish = [&](int cur, int nxt, bool allow_cur) -> bool {
-        while (true) {
-          const int t = next_team();
-          if (t < 0) return true;
-          if (!allow_cur && have[cur] && !team_free(t)) return false;  // do not stall the MMAs of `cur`
-          cursor = (t + 1) % NTEAM;
-          team_of[nxt] = t;
-          buf_of[nxt] = nbatch_team[t] & 1;
-          if (build(t)) { have[nxt] = true; return true; }
-        }
-      };
-      try_publish(1, 0, true);
+        d.seq = any ? (int)nbuilt : 0;
+      }
+      if (any) ++nbuilt;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.descfull[t][bf]);
+      nbp = (nbp & ~(0xffu << (8 * t))) | ((((nbp >> (8 * t)) + 1u) & 3u) << (8 * t));
+      if (!any) exited |= 1u << t;
+      T_END(3);
+      return any;
+    };
+    // software pipeline: the descriptor of batch b+1 is published before the MMAs of batch b are issued,
+    // unless b+1 belongs to the same team as b (then its teamdone can only complete after b's MMAs).
+    int b = 0;
+    bool have[2] = {false, false};
+    int team_of[2] = {0, 0};
+    int buf_of[2] = {0, 0};
+    int cursor = 0;
+    auto next_team = [&]() -> int {
+      for (int k = 0; k < NTEAM; ++k) {
+        const int t = (cursor + k) % NTEAM;
+        if (!((exited >> t) & 1u)) return t;
+      }
+      return -1;
+    };
+    // returns true when publishing for slot `nxt` is settled (a batch was found or every team exited)
+    auto try_publish = [&](int cur, int nxt, bool allow_cur) -> bool {
       while (true) {
-        const int cur = b & 1, nxt = cur ^ 1;
-        have[nxt] = false;
-        const bool settled = try_publish(cur, nxt, false);
-        if (have[cur]) {
-          const int t = team_of[cur];
-          const BatchDesc& d = sm.desc[t][buf_of[cur]];
-          const uint32_t set = nmma_batches & 1;                         // TMEM accumulator set of this batch
+        const int t = next_team();
+        if (t < 0) return true;
+        if (!allow_cur && have[cur] && !team_free(t)) return false;  // do not stall the MMAs of `cur`
+        cursor = (t + 1) % NTEAM;
+        team_of[nxt] = t;
+        buf_of[nxt] = nb_of(t) & 1;
+        if (build(t)) { have[nxt] = true; return true; }
+      }
+    };
+    try_publish(1, 0, true);
+    while (true) {
+      const int cur = b & 1, nxt = cur ^ 1;
+      have[nxt] = false;
+      const bool settled = try_publish(cur, nxt, false);
+      if (have[cur]) {
+        const int t = team_of[cur];
+        const BatchDesc& d = sm.desc[t][buf_of[cur]];
+        const uint32_t set = nmma_batches & 1;                         // TMEM accumulator set of this batch
+        T_BEGIN();
+        mbar_wait(&sm.tmemfree[set], ((nmma_batches >> 1) & 1) ^ 1);   // batch b-2 (same set) has been drained
+        T_END(1);
+        tc_fence_after();
+        const int nstg = d.nstages;
+        for (int i = 0; i < nstg; ++i, ++it) {
+          const int st = it % NSTAGE;
+          const int valid = d.st[i].valid;
+          const int info = d.st[i].info;
           T_BEGIN();
-          mbar_wait(&sm.tmemfree[set], ((nmma_batches >> 1) & 1) ^ 1);   // batch b-2 (same set) has been drained
-          T_END(1);
+          mbar_wait(&sm.full[st], (it / NSTAGE) & 1);
+          T_END(2);
           tc_fence_after();
-          const int nstg = d.nstages;
-          for (int i = 0; i < nstg; ++i, ++it) {
-            const int st = it % NSTAGE;
-            const int valid = d.st[i].valid;
-            const int info = d.st[i].info;
-            T_BEGIN();
-            mbar_wait(&sm.full[st], (it / NSTAGE) & 1);
-            T_END(2);
-            tc_fence_after();
+          T_BEGIN();
+          if (lane == 0) {
             const int nkb = (valid + KB_RATINGS - 1) / KB_RATINGS;
             const uint32_t base = s32(&sm.stage[st][0]);
             const uint32_t acc = tmem + set * (NSLOT * ACOL) + (info & 3) * ACOL;
             for (int kb = 0; kb < nkb; ++kb) {
-              const uint64_t dh = make_desc(base + kb * KB_BYTES);          // hi half: columns 0..63
-              const uint64_t dl = make_desc(base + kb * KB_BYTES + 2048);   // lo half
+              // A = all 128 staged columns [hi | lo] (M = 128), B = the 64 hi columns (N = 64):
+              // D rows 0..63 = hi^T hi, rows 64..127 = lo^T hi; the drain adds lo^T hi and its transpose to hi^T hi
+              const uint64_t dh = make_desc(base + kb * KB_BYTES);
               umma_tf32(acc, dh, dh, IDESC, ((info & 16) && kb == 0) ? 0u : 1u);
-              umma_tf32(acc, dl, dh, IDESC, 1u);
-              umma_tf32(acc, dh, dl, IDESC, 1u);
             }
             umma_commit(&sm.empty[st]);
           }
-          umma_commit(&sm.accfull[t][buf_of[cur]]);
-          ++nmma_batches;
+          __syncwarp();
+          T_END(4);
         }
-        if (!settled) try_publish(cur, nxt, true);
-        if (!have[nxt]) break;
-        ++b;
+        if (lane == 0) umma_commit(&sm.accfull[t][buf_of[cur]]);
+        __syncwarp();
+        ++nmma_batches;
       }
+      if (!settled) try_publish(cur, nxt, true);
+      if (!have[nxt]) break;
+      ++b;
     }
     __syncwarp();
-  } else if (warp <= STAGE_KB) {
+  } else if (warp < TEAM0) {
     // ================= producers =================
     // warp 1 = gather warp: walks the scheduler's stage lists and, per stage, starts one 256-byte cp.async.bulk
     //          copy per rating into the raw ring (completion counted on rawfull[]); source indices are loaded
@@ -495,52 +543,67 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       if (c_i >= 0 && c_i + 1 < c_n) { ++c_i; return true; }
       return next_batch(blocking);
     };
-    if (warp == 1) {
-      // ---------------- gather warp ----------------
-      // queue of the next two stages (beg, valid, index, rating) in registers; q0 is issued next
+    if (warp < CONV0) {
+      // ---------------- gather warps: warp gw issues every stage with (stage number % NGATHER == gw) ----------------
+      // queue of this warp's next two stages (global stage number, beg, valid, source index) in registers; q0 is issued next
+      const int gw = warp - 1;
       long long qbeg0 = 0, qbeg1 = 0;
       int qval0 = -1, qval1 = -1;      // valid count; -1 = empty queue slot
       int qidx0 = -1, qidx1 = -1;
-      float qr0 = 0.f, qr1 = 0.f;
-      uint32_t n_g = 0;                // stages issued
+      uint32_t qn0 = 0, qn1 = 0;
+      uint32_t n_seen = 0;             // stages walked so far (all warps' stages)
       bool more = true;
-      auto fetch = [&](long long& qb, int& qv, int& qi, float& qr) {   // pull the next stage (blocking) and start its index load
-        if (!more) { qv = -1; return; }
-        T_BEGIN();
-        more = advance(true);
-        T_END(0);
-        if (!more) { qv = -1; return; }
-        const StageEnt se = sm.desc[c_t][c_b].st[c_i];
-        qb = se.beg;
-        qv = se.valid;
-        qi = -1;
-        qr = 0.f;
-        if (lane < se.valid) {
-          qi = __ldg(p.idx + se.beg + lane);
-          qr = __ldg(p.val + se.beg + lane);
+      // pull this warp's next stage and start its index load; the look-ahead never blocks on a descriptor (the scheduler
+      // may hold the next batch back until the MMAs of the current one - which need the stage still queued here - are issued)
+      auto fetch = [&](uint32_t& qn, long long& qb, int& qv, int& qi, bool blocking) {
+        qv = -1;
+        while (more) {
+          T_BEGIN();
+          const bool ok = advance(blocking);
+          T_END(0);
+          if (!ok) {
+            if (c_done) more = false;
+            return;
+          }
+          const uint32_t n = n_seen++;
+          if ((n % NGATHER) != (uint32_t)gw) continue;
+          const StageEnt se = sm.desc[c_t][c_b].st[c_i];
+          qn = n;
+          qb = se.beg;
+          qv = se.valid;
+          qi = -1;
+          if (lane < se.valid) qi = __ldg(p.idx + se.beg + lane);
+          return;
         }
       };
-      fetch(qbeg0, qval0, qidx0, qr0);
-      fetch(qbeg1, qval1, qidx1, qr1);
-      while (qval0 >= 0) {
-        const int rs = n_g % NRAW;
+      while (true) {
+        if (qval0 < 0) {
+          if (qval1 >= 0) { qn0 = qn1; qbeg0 = qbeg1; qval0 = qval1; qidx0 = qidx1; qval1 = -1; }
+          else fetch(qn0, qbeg0, qval0, qidx0, true);    // nothing pending in this warp: safe to block
+          if (qval0 < 0) break;                          // finished
+        }
+        if (qval1 < 0) fetch(qn1, qbeg1, qval1, qidx1, false);
+        const int rs = qn0 % NRAW;
         T_BEGIN();
-        mbar_wait(&sm.rawempty[rs], ((n_g / NRAW) & 1) ^ 1);   // converters are done with this raw slot
+        mbar_wait(&sm.rawempty[rs], ((qn0 / NRAW) & 1) ^ 1);   // the converter is done with this raw slot
         T_END(1);
         T_BEGIN();
-        if (lane < qval0)
-          bulk_copy_g2s(&sm.raw[rs][lane * RAW_ROW], p.src + (size_t)qidx0 * KP, KP * 4, &sm.rawfull[rs]);
-        sm.rawval[rs][lane] = qr0;
-        __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(&sm.rawfull[rs], (uint32_t)qval0 * KP * 4);
+        // lane = (row parity, 16-byte chunk): one LDGSTS moves two whole 256-byte rows per warp instruction
+#pragma unroll
+        for (int i = 0; i < STAGE_RATINGS / 2; ++i) {
+          const int r = 2 * i + (lane >> 4);
+          const int si = __shfl_sync(0xffffffffu, qidx0, r);
+          if (2 * i < qval0 && si >= 0)
+            cp_async16(&sm.raw[rs][r * RAW_ROW + (lane & 15) * 16], p.src + (size_t)si * KP + (lane & 15) * 4);
+        }
+        if (lane < qval0) cp_async4(&sm.rawval[rs][lane], p.val + qbeg0 + lane);
+        cp_async_mbar_arrive_noinc(&sm.rawfull[rs]);
         T_END(2);
-        ++n_g;
-        qbeg0 = qbeg1; qval0 = qval1; qidx0 = qidx1; qr0 = qr1;
-        fetch(qbeg1, qval1, qidx1, qr1);
+        qval0 = -1;
       }
     } else {
       // ---------------- converters ----------------
-      const int cw = warp - 2;
+      const int cw = warp - CONV0;
       // lane -> (rating kr inside a K-block, source float4 groups sg_j = sgb + 4 j): a quarter-warp holds 4 ratings
       // (kr%4 = 0..3) x 2 halves of one 32-byte chunk -> its 8 STS.128 hit 8 distinct 16-byte bank groups
       const int kr = ((lane >> 3) & 1) * 4 + (lane & 3);
@@ -565,15 +628,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
           mbar_wait(&sm.rawfull[rs], (it / NRAW) & 1);           // gathered rows have landed
           T_END(1);
           T_BEGIN();
+          // all shared-memory loads of the stage first (12 independent LDS.128 + 3 ratings), then arithmetic + stores
+          float4 y[STAGE_KB][4];
+          float cv[STAGE_KB];
+#pragma unroll
+          for (int kb = 0; kb < STAGE_KB; ++kb) {
+            const int r = kb * KB_RATINGS + kr;                  // rating inside the stage
+            const bool live = r < se.valid;
+            cv[kb] = live ? sm.rawval[rs][r] : 0.f;
+            const unsigned char* rrow = &sm.raw[rs][r * RAW_ROW];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              y[kb][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (live) y[kb][j] = *reinterpret_cast<const float4*>(rrow + (sgb + 4 * j) * 16);
+            }
+          }
+          // the raw slot is in registers now: hand it back to the gather warps before converting
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.rawempty[rs]);
+          T_END(3);
+          T_BEGIN();
           mbar_wait(&sm.empty[st], ((it / NSTAGE) & 1) ^ 1);     // UMMA stage is free
           T_END(2);
           T_BEGIN();
 #pragma unroll
           for (int kb = 0; kb < STAGE_KB; ++kb) {
             if (kb * KB_RATINGS < se.valid) {
-              const int r = kb * KB_RATINGS + kr;                // rating inside the stage
-              const bool live = r < se.valid;
-              const float cval = live ? sm.rawval[rs][r] : 0.f;
+              const float cval = cv[kb];
               float wb, sc;
               if (IMPLICIT) {
                 const float c1 = p.alpha * fabsf(cval);
@@ -583,19 +664,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
                 wb = cval;
                 sc = 1.f;
               }
-              const unsigned char* rrow = &sm.raw[rs][r * RAW_ROW];
               unsigned char* kbp = &sm.stage[st][0] + kb * KB_BYTES + kr * 128;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int sg = sgb + 4 * j;
                 const int off = (sg >> 3) * 1024 + ((((sg & 7) >> 1) ^ (kr & 3)) * 32) + (sg & 1) * 16;
-                float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (live) y = *reinterpret_cast<const float4*>(rrow + sg * 16);
-                bacc[j][0] = fmaf(wb, y.x, bacc[j][0]);
-                bacc[j][1] = fmaf(wb, y.y, bacc[j][1]);
-                bacc[j][2] = fmaf(wb, y.z, bacc[j][2]);
-                bacc[j][3] = fmaf(wb, y.w, bacc[j][3]);
-                float4 x = y;
+                const float4 yy = y[kb][j];
+                bacc[j][0] = fmaf(wb, yy.x, bacc[j][0]);
+                bacc[j][1] = fmaf(wb, yy.y, bacc[j][1]);
+                bacc[j][2] = fmaf(wb, yy.z, bacc[j][2]);
+                bacc[j][3] = fmaf(wb, yy.w, bacc[j][3]);
+                float4 x = yy;
                 if (IMPLICIT) { x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; }
                 float4 hi, lo;
                 hi.x = tf32_round(x.x); hi.y = tf32_round(x.y); hi.z = tf32_round(x.z); hi.w = tf32_round(x.w);
@@ -607,11 +686,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&sm.full[st]);       // -> MMA issuer
-            mbar_arrive(&sm.rawempty[rs]);   // -> gather warp
-          }
-          T_END(3);
+          if (lane == 0) mbar_arrive(&sm.full[st]);       // -> MMA issuer
+          T_END(4);
         }
         ++it;
         if (se.info & 4) {
@@ -635,7 +711,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
           }
           named_bar_sync(1, NCONV * 32);
           if (cw == 0) {
-            for (int c = lane; c < KP; c += 32) sm.bstage[c_t][c_b][sslot][c] = sm.bpart[0][c] + sm.bpart[1][c];
+            for (int c = lane; c < KP; c += 32) {
+              float acc = sm.bpart[0][c];
+#pragma unroll
+              for (int w = 1; w < NCONV; ++w) acc += sm.bpart[w][c];   // fixed order
+              sm.bstage[c_t][c_b][sslot][c] = acc;
+            }
             if (se.info & 8) {   // every right-hand side of this batch is in bstage[t][buf]
               __syncwarp();
               if (lane == 0) mbar_arrive(&sm.bfull[c_t][c_b]);
@@ -650,8 +731,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
     }
   } else {
     // ================= teams: drain + solve =================
-    const int t = (warp - 4) / 4;
-    const int slot = (warp - 4) % 4;     // the row this warp solves
+    const int t = (warp - TEAM0) / 4;
+    const int slot = (warp - TEAM0) % 4;     // the row this warp solves
     const int q = warp & 3;              // TMEM lane quarter this warp may read
     const int barid = 2 + t;
     int nb = 0;
@@ -670,42 +751,78 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       // every warp of the team must have finished solving the previous batch before any A slot is overwritten
       named_bar_sync(barid, 128);
       T_BEGIN();
-      // ---- drain: D row r lives in TMEM lane 32*(r/16) + r%16: lanes 0..15 of warp quarter q hold rows 16q..16q+15
+      // ---- drain: the accumulator is 128 lanes x 64 columns: lane r < 64 = row r of hi^T hi, lane 64 + r = row r of
+      // lo^T hi (LH).  A = HH + LH + LH^T: warps q = 0,1 store/accumulate their HH rows, then warps q = 2,3 add the lower
+      // part of their LH rows, then (after a team barrier) its transpose - a fixed order, so the sums are deterministic.
       const uint32_t set = (uint32_t)d.seq & 1u;
-      {
-        // tcgen05.ld is warp-collective (.sync.aligned): all 32 lanes load, lanes 0..15 hold the rows
-        const bool holds = lane < 16;
-        const int drow = q * 16 + (lane & 15);
+      const int drow = (q & 1) * 32 + lane;
+      auto load_slot = [&](int s, float* v) {
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + set * (NSLOT * ACOL) + (uint32_t)(s * ACOL);
+        tmem_ld16_nowait(taddr, &v[0]);
+        tmem_ld16_nowait(taddr + 16, &v[16]);
+        tmem_ld16_nowait(taddr + 32, &v[32]);
+        tmem_ld16_nowait(taddr + 48, &v[48]);
+        tmem_ld_wait();
+      };
+      // row `drow` of a 64x64 block into the lower-triangle slot (columns <= drow), overwriting or accumulating
+      auto put_lower = [&](float* as, const float* v, bool overwrite) {
+        if (drow < H) {
+          float* rowp = as + drow * (drow + 1) / 2;
+#pragma unroll
+          for (int c = 0; c < H; ++c)
+            if (c <= drow) rowp[c] = overwrite ? v[c] : rowp[c] + v[c];
+        } else {
+          float4* r4 = reinterpret_cast<float4*>(as + OFF21 + (drow - H) * L21S);
+#pragma unroll
+          for (int c = 0; c < H; c += 4) {
+            float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            if (!overwrite) { const float4 e = r4[c / 4]; o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
+            r4[c / 4] = o;
+          }
+          float* rowp = as + OFF22 + (drow - H) * (drow - H + 1) / 2;
+#pragma unroll
+          for (int c = 0; c < H; ++c)
+            if (c <= drow - H) rowp[c] = overwrite ? v[H + c] : rowp[c] + v[H + c];
+        }
+      };
+      if (q < 2) {
 #pragma unroll 1
         for (int s = 0; s < NSLOT; ++s) {
           if (d.row[s] < 0) continue;
-          float* as = &sm.aslot[t][s][0];
-          const bool first = d.first[s] != 0;
-          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + set * (NSLOT * ACOL) + (uint32_t)(s * ACOL);
           float v[64];
-          tmem_ld16_nowait(taddr, &v[0]);
-          tmem_ld16_nowait(taddr + 16, &v[16]);
-          tmem_ld16_nowait(taddr + 32, &v[32]);
-          tmem_ld16_nowait(taddr + 48, &v[48]);
-          tmem_ld_wait();
-          if (!holds) continue;
+          load_slot(s, v);
+          put_lower(&sm.aslot[t][s][0], v, d.first[s] != 0);
+        }
+      }
+      named_bar_sync(barid, 128);
+      if (q >= 2) {
+#pragma unroll 1
+        for (int s = 0; s < NSLOT; ++s) {
+          if (d.row[s] < 0) continue;
+          float v[64];
+          load_slot(s, v);
+          put_lower(&sm.aslot[t][s][0], v, false);
+        }
+      }
+      named_bar_sync(barid, 128);
+      if (q >= 2) {
+#pragma unroll 1
+        for (int s = 0; s < NSLOT; ++s) {
+          if (d.row[s] < 0) continue;
+          float v[64];
+          load_slot(s, v);
+          float* as = &sm.aslot[t][s][0];
+          // transpose: LH[drow][c] (c >= drow) goes to A[c][drow]; consecutive lanes -> consecutive addresses
           if (drow < H) {
-            float* rowp = as + drow * (drow + 1) / 2;
 #pragma unroll
             for (int c = 0; c < H; ++c)
-              if (c <= drow) rowp[c] = first ? v[c] : rowp[c] + v[c];
+              if (c >= drow) as[c * (c + 1) / 2 + drow] += v[c];
+#pragma unroll
+            for (int c = H; c < KP; ++c) as[OFF21 + (c - H) * L21S + drow] += v[c];
           } else {
-            float4* r4 = reinterpret_cast<float4*>(as + OFF21 + (drow - H) * L21S);
 #pragma unroll
-            for (int c = 0; c < H; c += 4) {
-              float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-              if (!first) { const float4 e = r4[c / 4]; o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
-              r4[c / 4] = o;
-            }
-            float* rowp = as + OFF22 + (drow - H) * (drow - H + 1) / 2;
-#pragma unroll
-            for (int c = 0; c < H; ++c)
-              if (c <= drow - H) rowp[c] = first ? v[H + c] : rowp[c] + v[H + c];
+            for (int c = H; c < KP; ++c)
+              if (c >= drow) as[OFF22 + (c - H) * (c - H + 1) / 2 + (drow - H)] += v[c];
           }
         }
       }
@@ -716,7 +833,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       mbar_wait(&sm.bfull[t][bf], ph);
       T_END(3);
       {
-        const int tt = (warp - 4) % 4 * 32 + lane;  // 0..127 within the team
+        const int tt = (warp - TEAM0) % 4 * 32 + lane;  // 0..127 within the team
         for (int o = tt; o < NSLOT * KP; o += 128) {
           const int s = o / KP, c = o % KP;
           if (d.row[s] >= 0) sm.bslot[t][s][c] = d.first[s] ? sm.bstage[t][bf][s][c] : sm.bslot[t][s][c] + sm.bstage[t][bf][s][c];

@@ -346,6 +346,7 @@ struct pio_als_handle {
   float* d_dbg = nullptr;     // PIO_ALS_TC_DEBUG=1: A/b dump of the last tensor-core half-step
   size_t dbg_rows = 0;
   bool use_tc = false;        // rank in 33..64 and PIO_ALS_TC != 0
+  double tc_min_deg = 0.0;    // PIO_ALS_TC_MIN_DEG: only sides whose rows average at least this many ratings use it
   int heavy_t = 0;
   bool have_ratings = false, have_init = false, trained = false;
   ncclComm_t comm = nullptr;
@@ -713,7 +714,8 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
   if (nlight > 0) {
     p.row_begin = dst.n_heavy;
     p.row_end = dst.n_active;
-    if (h->use_tc && Cfg::KP == 64) {
+    const double avg_deg = dst.n_active > 0 ? (double)dst.nnz_local / dst.n_active : 0.0;
+    if (h->use_tc && Cfg::KP == 64 && avg_deg >= h->tc_min_deg) {
       // Gramian on tcgen05 (als_tc_kernel.cuh): persistent, one CTA per SM, rows claimed dynamically
       static bool attr_set[64] = {};
       const size_t smem = sizeof(tc::Smem) + 1024;
@@ -880,6 +882,7 @@ static int create_common(pio_als_handle* h) {
     const char* env = getenv("PIO_ALS_TC");
     h->use_tc = h->KP == 64 && env && env[0] == '1';
     h->heavy_t = h->use_tc ? HEAVY_T_TC : HEAVY_T;
+    if (const char* md = getenv("PIO_ALS_TC_MIN_DEG")) h->tc_min_deg = atof(md);
   }
   h->gram_blocks = 2 * h->sm_count;
   if (cudaMallocAsync((void**)&h->yty, sizeof(float) * h->KP * h->KP, h->stream) != cudaSuccess ||

@@ -4,7 +4,7 @@ sys.path.insert(0, "/root/repo")
 import numpy as np, torch
 import pio_b200
 from pio_b200 import native
-nu, ni, nnz, k = 100000, 20000, 5000000, 64
+nu, ni, nnz, k = int(os.environ.get('TC_NU', 100000)), int(os.environ.get('TC_NI', 20000)), int(os.environ.get('TC_NNZ', 5000000)), 64
 du = torch.empty(nnz, dtype=torch.int32, device="cuda"); di = torch.empty_like(du); dr = torch.empty(nnz, dtype=torch.float32, device="cuda")
 native.synth_ratings_device(0, nu, ni, nnz, 3, True, 0, du.data_ptr(), di.data_ptr(), dr.data_ptr())
 m = native.NativeALS(k, nu, ni, lam=0.01, implicit=True, init_mode=native.INIT_HASH, seed=3)
@@ -18,9 +18,10 @@ t = buf.reshape(148, 16, 8).astype(np.float64)
 tot = t[:, :, 7].mean()
 print("rc", rc, "(last tc launch = user side) mean kernel cycles per CTA", tot)
 np.set_printoptions(precision=1, suppress=True, linewidth=200)
-names = {0: ["sched: wait teamdone", "wait tmemfree", "wait full"],
-         1: ["prod: cc advance(desc wait)", "pump", "wait gathers", "wait empty", "convert+store", "pump.meta-lookahead", "pump.wait-meta"],
+names = {0: ["sched: wait teamdone", "wait tmemfree", "wait full", "build", "mma issue"],
+         1: ["gather: advance(desc)", "wait rawempty", "issue bulk copies"],
+         2: ["conv: advance(desc)", "wait rawfull", "wait empty", "load raw", "convert+store"],
          4: ["team: wait desc", "wait accfull", "drain", "wait bfull", "team barrier", "dump+solve"]}
-for w, nm in ((0, names[0]), (1, names[1]), (2, names[1]), (3, names[1]), (4, names[4]), (5, names[4]), (8, names[4]), (12, names[4])):
+for w, nm in ((0, names[0]), (1, names[1]), (2, names[1]), (3, names[2]), (5, names[2]), (7, names[2]), (8, names[4]), (9, names[4]), (12, names[4])):
     pct = t[:, w, :len(nm)].mean(0) / tot * 100
     print(f"warp {w:2d}:", ", ".join(f"{n} {p:.1f}%" for n, p in zip(nm, pct)))
