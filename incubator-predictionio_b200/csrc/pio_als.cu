@@ -311,6 +311,8 @@ struct Side {
   float* F = nullptr;        // [n_internal][KP]
   int* cand_ext = nullptr;   // [n_internal]
   int n_active = 0, n_heavy = 0;
+  bool use_tc = false;       // this side's short rows go through the tensor-core kernel (decided from GLOBAL counts: every rank agrees)
+  int heavy_t = 0;           // rows with more ratings than this are cut into parts
   // parts of the n_heavy longest local rows
   long long* part_beg = nullptr;
   long long* part_end = nullptr;
@@ -347,7 +349,6 @@ struct pio_als_handle {
   size_t dbg_rows = 0;
   bool use_tc = false;        // rank in 33..64 and PIO_ALS_TC != 0
   double tc_min_deg = 0.0;    // PIO_ALS_TC_MIN_DEG: only sides whose rows average at least this many ratings use it
-  int heavy_t = 0;
   bool have_ratings = false, have_init = false, trained = false;
   ncclComm_t comm = nullptr;
   std::string err;
@@ -444,9 +445,13 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
     LAUNCHED(h);
   }
   CK(h, cudaMemsetAsync(h->d_counts, 0, 2 * sizeof(int), st));
+  // kernel choice from global numbers only (ratings after dedup / rows of this side), so that every rank of a sharded
+  // run and the single-GPU run take the same path for the same row
+  row.use_tc = h->use_tc && h->KP == 64 && row.n > 0 && (double)nnz / (double)row.n >= h->tc_min_deg;
+  row.heavy_t = row.use_tc ? HEAVY_T_TC : HEAVY_T;
   local_rows_kernel<<<nblk(row.R + 1, 256), 256, 0, st>>>(ptr_full, rk * row.R, row.R, be[0], row.inv, row.deg,
                                                            row.npos, h->cfg.implicit_prefs, row.ptr, row.nreg,
-                                                           h->d_counts, h->heavy_t);
+                                                           h->d_counts, row.heavy_t);
   LAUNCHED(h);
   int counts[2];
   CK(h, cudaMemcpyAsync(counts, h->d_counts, sizeof counts, cudaMemcpyDeviceToHost, st));
@@ -714,8 +719,7 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
   if (nlight > 0) {
     p.row_begin = dst.n_heavy;
     p.row_end = dst.n_active;
-    const double avg_deg = dst.n_active > 0 ? (double)dst.nnz_local / dst.n_active : 0.0;
-    if (h->use_tc && Cfg::KP == 64 && avg_deg >= h->tc_min_deg) {
+    if (dst.use_tc && Cfg::KP == 64) {
       // Gramian on tcgen05 (als_tc_kernel.cuh): persistent, one CTA per SM, rows claimed dynamically
       static bool attr_set[64] = {};
       const size_t smem = sizeof(tc::Smem) + 1024;
@@ -880,8 +884,10 @@ static int create_common(pio_als_handle* h) {
   {
     // tensor-core Gramian (als_tc_kernel.cuh): parity-green but not yet faster than the FP32 kernel -> opt-in
     const char* env = getenv("PIO_ALS_TC");
-    h->use_tc = h->KP == 64 && env && env[0] == '1';
-    h->heavy_t = h->use_tc ? HEAVY_T_TC : HEAVY_T;
+    // default: sides whose rows average >= 256 ratings (the item side of the headline workload) accumulate their
+    // Gramians on tcgen05; PIO_ALS_TC=0 disables it, PIO_ALS_TC=1 forces it for every side (PIO_ALS_TC_MIN_DEG overrides)
+    h->use_tc = h->KP == 64 && !(env && env[0] == '0');
+    h->tc_min_deg = (env && env[0] == '1') ? 0.0 : 256.0;
     if (const char* md = getenv("PIO_ALS_TC_MIN_DEG")) h->tc_min_deg = atof(md);
   }
   h->gram_blocks = 2 * h->sm_count;

@@ -98,14 +98,40 @@ def test_config_c1_recommendation_template(native, oracle):
     assert np.abs(pg - po).max() <= 1e-3 * max(1.0, np.abs(po).max())
 
 
-def test_heavy_rows_split_mode(native, oracle):
-    """Items with far more than 4096 ratings take the one-row-per-CTA split path."""
+@pytest.mark.parametrize("tc", ["0", None])
+def test_heavy_rows_split_mode(native, oracle, monkeypatch, tc):
+    """Items with far more ratings than the heavy-row threshold are cut into 2016-rating parts (part launch +
+    als_finish_kernel).  tc="0": FP32 kernel for the shorter rows; tc=None: the default selection, which sends this
+    item side (10000 ratings per row on average) through the tcgen05 kernel."""
+    if tc is None:
+        monkeypatch.delenv("PIO_ALS_TC", raising=False)
+    else:
+        monkeypatch.setenv("PIO_ALS_TC", tc)
     nu, ni, nnz = 20000, 40, 400000
     u, i, r = synth.synth_ratings(nu, ni, nnz, seed=9, implicit=True)
     _, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 3, 0.05, True, 1.0)
     assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
     _, g, o = run_both(native, oracle, nu, ni, u, i, r, 10, 3, 0.05, False, 1.0)
     assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
+
+
+def test_default_kernel_selection_mixed_sides(native, oracle, monkeypatch):
+    """Default build, rank 64: the item side (rows average >= 256 ratings) accumulates its Gramians on the tensor
+    cores, the user side (20 ratings per row) stays on the FP32 kernel; both within tolerance of the oracle, and the
+    all-FP32 run (PIO_ALS_TC=0) agrees with the mixed one to the same tolerance."""
+    monkeypatch.delenv("PIO_ALS_TC", raising=False)
+    monkeypatch.delenv("PIO_ALS_TC_MIN_DEG", raising=False)
+    nu, ni, nnz = 20000, 300, 400000
+    for implicit in (True, False):
+        u, i, r = synth.synth_ratings(nu, ni, nnz, seed=21, implicit=implicit)
+        _, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 4, 0.05, implicit, 1.0)
+        eu, ei = frob_rel(g[0], o[0]), frob_rel(g[1], o[1])
+        assert eu <= TOL and ei <= TOL, (implicit, eu, ei)
+        monkeypatch.setenv("PIO_ALS_TC", "0")
+        _, g0, _ = run_both(native, oracle, nu, ni, u, i, r, 64, 4, 0.05, implicit, 1.0)
+        monkeypatch.delenv("PIO_ALS_TC")
+        assert frob_rel(g0[0], g[0]) <= TOL and frob_rel(g0[1], g[1]) <= TOL
+        assert not np.array_equal(g0[1], g[1])   # the two kernels really are different code paths
 
 
 def test_ragged_and_empty_rows(native, oracle):
