@@ -346,3 +346,9 @@ def nccl_id_2(native, rank, world):
 
 if __name__ == "__main__":
     main()
+    try:   # leave the torch.distributed group cleanly (no teardown warning after the JSON line)
+        import torch.distributed as _dist
+        if _dist.is_available() and _dist.is_initialized():
+            _dist.destroy_process_group()
+    except Exception:
+        pass

@@ -718,7 +718,9 @@ constexpr int GRAM_ROWS = 32;
 
 template <int KP>
 __global__ void __launch_bounds__(GRAM_THREADS)
-gram_partial_kernel(const float* __restrict__ X, int n_rows, double* __restrict__ partial) {
+gram_partial_kernel(const float* __restrict__ X, const int* __restrict__ p2i, int n_rows, double* __restrict__ partial) {
+  // rows are visited in degree-rank position order (p2i: position -> internal id), which does not depend on how the
+  // rows are dealt to ranks: a sharded run sums YtY in exactly the order of the single-GPU run
   constexpr int TM = KP / 16;
   __shared__ __align__(16) float tile[GRAM_ROWS * KP];
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
@@ -735,7 +737,7 @@ gram_partial_kernel(const float* __restrict__ X, int n_rows, double* __restrict_
     for (int o = tid; o < GRAM_ROWS * KP / 4; o += GRAM_THREADS) {
       const int rr = o / (KP / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rr < nr) v = reinterpret_cast<const float4*>(X + (size_t)(base + rr) * KP)[o % (KP / 4)];
+      if (rr < nr) v = reinterpret_cast<const float4*>(X + (size_t)__ldg(p2i + base + rr) * KP)[o % (KP / 4)];
       reinterpret_cast<float4*>(tile)[o] = v;
     }
     __syncthreads();

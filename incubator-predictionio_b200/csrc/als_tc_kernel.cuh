@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
     // warp 1 = gather warp: walks the scheduler's stage lists and, per stage, starts one 256-byte cp.async.bulk
     //          copy per rating into the raw ring (completion counted on rawfull[]); source indices are loaded
     //          two stages ahead into a register shift queue.
-    // warps 2,3 = converters: converter cw owns every stage with (stage number % NCONV == cw): it waits for the
+    // converters: converter cw owns the stages whose number inside their segment is cw mod NCONV: it waits for the
     //          raw rows, scales, splits hi/lo and writes all three K-blocks of the UMMA tile (three independent
     //          pieces of work per dependency chain), then hands the stage to the MMA issuer.
     // cursor over the published stage lists (scalars only)
@@ -608,7 +608,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
       // (kr%4 = 0..3) x 2 halves of one 32-byte chunk -> its 8 STS.128 hit 8 distinct 16-byte bank groups
       const int kr = ((lane >> 3) & 1) * 4 + (lane & 3);
       const int sgb = ((lane >> 2) & 1) + 2 * (lane >> 4);
-      uint32_t it = 0;   // global stage counter (UMMA ring + raw ring + ownership)
+      uint32_t it = 0;   // global stage counter (UMMA ring + raw ring)
+      uint32_t qs = 0;   // stage number inside the current segment: decides the owner, so that the grouping of a row's
+                         // right-hand-side partial sums depends on the row alone (not on what else this CTA processes)
       float bacc[4][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -620,7 +622,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
         T_END(0);
         if (!ok) break;
         const StageEnt se = sm.desc[c_t][c_b].st[c_i];
-        const bool mine = (it % NCONV) == (uint32_t)cw;
+        if (se.info & 16) qs = 0;
+        const bool mine = (qs % NCONV) == (uint32_t)cw;
+        ++qs;
         if (mine) {
           const int rs = it % NRAW;
           const int st = it % NSTAGE;

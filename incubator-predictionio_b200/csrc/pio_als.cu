@@ -783,10 +783,10 @@ static cudaError_t launch_solve(pio_als_handle* h, Side& dst, const Side& src) {
 static cudaError_t launch_gram(pio_als_handle* h, const Side& src) {
   const int nb = h->gram_blocks;
   switch (h->KP) {
-    case 16: gram_partial_kernel<16><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.n_internal, h->gram_partial); break;
-    case 32: gram_partial_kernel<32><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.n_internal, h->gram_partial); break;
-    case 64: gram_partial_kernel<64><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.n_internal, h->gram_partial); break;
-    default: gram_partial_kernel<128><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.n_internal, h->gram_partial); break;
+    case 16: gram_partial_kernel<16><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial); break;
+    case 32: gram_partial_kernel<32><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial); break;
+    case 64: gram_partial_kernel<64><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial); break;
+    default: gram_partial_kernel<128><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial); break;
   }
   LAUNCHED(h);
   const int n = h->KP * h->KP;

@@ -45,7 +45,10 @@ WORKER = textwrap.dedent("""
             s.set_init(u0)
             s.run(3)
             suf, sitf, suh, sih = s.get_factors()
-            assert np.array_equal(uf, suf) and np.array_equal(itf, sitf), "sharded != single GPU"
+            du, di = float(np.abs(uf - suf).max()), float(np.abs(itf - sitf).max())
+            assert np.array_equal(uf, suf) and np.array_equal(itf, sitf), (
+                "sharded != single GPU: rank %d implicit %s: max |du| %.3g (%d rows differ), max |di| %.3g (%d rows differ)"
+                % (rk, implicit, du, int((uf != suf).any(1).sum()), di, int((itf != sitf).any(1).sum())))
             assert np.array_equal(uh, suh) and np.array_equal(ih, sih)
             assert m.stats()["last_comm_ms"] > 0
         dist.barrier()
