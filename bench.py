@@ -89,10 +89,10 @@ class ClockSampler:
 
 
 def traffic_from_profiles(workload):
-    """dram__bytes_read+write of the solve launches of one iteration, from the committed ncu capture (null if none)."""
+    """dram__bytes_read+write of ONE launch of the dominant kernel, from the committed ncu --set full capture (null if none)."""
     p = ROOT / "profiles" / "traffic.json"
     try:
-        return json.loads(p.read_text())[workload]["dram_bytes_per_iteration"]
+        return json.loads(p.read_text())[workload]["dram_bytes_per_launch"]
     except Exception:
         return None
 
@@ -295,29 +295,57 @@ def main():
     if rank != 0:
         return
 
-    # ---- roofline of the dominant kernel (als_solve_kernel) ---------------------------------
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    # One iteration = item half-step + user half-step; each is (YtY) + one solve launch for the rows up to the
+    # heavy-row threshold (+ a part launch and a finish launch for longer rows).  The dominant kernel is the solve
+    # launch of the slower half-step; its time is the CUDA-event time of that half-step's solve launches (measured
+    # inside pio_als_run on the launching stream), its work the algorithmic FLOPs / bytes of that side.
     hbm_peak, bf16_peak, peak_src = measured_peaks()
-    b_alg, f_solve, f_gram = algorithmic_work(st["n_users_active"] if world == 1 else nu,
-                                              st["n_items_active"] if world == 1 else ni, nnz_eff, k, implicit)
-    solve_s = solve_ms / 1e3
-    tflops = f_solve * args.steps / solve_s / 1e12 / max(world, 1)
-    gbs = b_alg * args.steps / solve_s / 1e9 / max(world, 1)
+    nua = st["n_users_active"] if world == 1 else nu
+    nia = st["n_items_active"] if world == 1 else ni
+    b_alg, f_solve, f_gram = algorithmic_work(nua, nia, nnz_eff, k, implicit)
+    ph = m.phase_ms()
+    side_flops = {"user": 2 * nnz_eff * (k * (k + 1) + 2 * k) / 2 + nua * (k ** 3 / 3 + 2 * k * k),
+                  "item": 2 * nnz_eff * (k * (k + 1) + 2 * k) / 2 + nia * (k ** 3 / 3 + 2 * k * k)}
+    side_bytes = {"user": 8 * nnz_eff + 4 * nua * k + 4 * nia * k, "item": 8 * nnz_eff + 4 * nia * k + 4 * nua * k}
+    side_ms = {"user": ph["user_solve_ms"] / args.steps, "item": ph["item_solve_ms"] / args.steps}
+    side_tc = {"user": ph["user_side_tensor_core"], "item": ph["item_side_tensor_core"]}
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    tf32_peak = bf16_peak / 2.0
+
+    def side_obj(sd):
+        tf = side_flops[sd] / (side_ms[sd] / 1e3) / 1e12 / max(world, 1)
+        gb = side_bytes[sd] / (side_ms[sd] / 1e3) / 1e9 / max(world, 1)
+        o = {"kernel": ("tc::als_solve_tc_kernel (tcgen05 split-TF32 Gramian + warp Cholesky)" if side_tc[sd] else
+                        "als_solve_kernel (gather + FP32 Gramian + warp Cholesky)") + f", {sd} half-step",
+             "ms_per_launch": side_ms[sd], "algorithmic_flops": side_flops[sd], "algorithmic_bytes": side_bytes[sd],
+             "achieved_tflops": tf, "achieved_gbs": gb, "frac_of_fp32_fma_peak": tf / fp32_peak,
+             "frac_of_hbm_peak": gb / hbm_peak}
+        if side_tc[sd]:
+            o["frac_of_tf32_tensor_peak"] = tf / tf32_peak
+        return o
+
+    dom = "user" if side_ms["user"] >= side_ms["item"] else "item"
+    other = "item" if dom == "user" else "user"
+    d = side_obj(dom)
     roofline = {
-        "kernel": "als_solve_kernel (gather + Gramian + Cholesky, fp32 FFMA)",
-        "bound": "fp32_fma", "achieved": tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tflops / fp32_peak,
-        "peak_source": "nominal 148 SM x 128 FFMA lanes x 2 x 1.965 GHz (CUDA-core FP32; MEASURED_PEAKS.json has no FP32 entry)",
+        "kernel": d["kernel"],
+        "bound": "fp32_fma" if not side_tc[dom] else "tensor",
+        "achieved": d["achieved_tflops"], "peak": fp32_peak if not side_tc[dom] else tf32_peak, "unit": "TFLOP/s",
+        "frac": d["achieved_tflops"] / (fp32_peak if not side_tc[dom] else tf32_peak),
+        "peak_source": ("nominal 148 SM x 128 FFMA lanes x 2 x 1.965 GHz (CUDA-core FP32; MEASURED_PEAKS.json has no "
+                        "FP32 entry)") if not side_tc[dom] else f"{peak_src} dense bf16 / 2 (tf32)",
+        "ms_per_launch": d["ms_per_launch"],
         "traffic": traffic_from_profiles(args.workload),
-        "traffic_unit": "bytes per iteration (the kernel's 3 launches), from the committed ncu capture",
+        "traffic_unit": "dram bytes of this launch, from the committed ncu --set full capture (profiles/traffic.json)",
         "per_gpu": True,
-        "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src,
-                "algorithmic_bytes_per_iteration": b_alg},
-        "tensor": {"achieved": tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tflops / bf16_peak,
-                   "peak_source": peak_src, "note": "kernel does not use the tensor pipe (fp32-accuracy Gramian)"},
+        "hbm": {"achieved": d["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": d["achieved_gbs"] / hbm_peak,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": d["algorithmic_bytes"]},
+        "other_half_step": side_obj(other),
         "solve_ms_per_iteration": solve_ms / args.steps, "gram_ms_per_iteration": gram_ms / args.steps,
         "comm_ms_per_iteration": comm_ms / args.steps,
         "launches_per_iteration": solve_launches / max(args.steps, 1),
-        "algorithmic_flops_per_iteration": f_solve,
+        "algorithmic_flops_per_iteration": f_solve, "algorithmic_bytes_per_iteration": b_alg,
     }
     out = {"metric": "ALS iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,

@@ -321,7 +321,7 @@ struct Side {
   int n_parts = 0;
 };
 
-enum EvKind { EV_SOLVE = 0, EV_GRAM = 1, EV_COMM = 2 };
+enum EvKind { EV_SOLVE = 0, EV_GRAM = 1, EV_COMM = 2, EV_SOLVE_USER = 3, EV_NKIND = 4 };   // EV_SOLVE = item half-step
 struct EvPair {
   cudaEvent_t a, b;
   int kind;
@@ -353,6 +353,7 @@ struct pio_als_handle {
   ncclComm_t comm = nullptr;
   std::string err;
   pio_als_stats st{};
+  double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // pio_als_get_phase_ms
   std::deque<EvPair> ev_pool;  // deque: references stay valid while the pool grows
   size_t ev_used = 0;
   std::mutex mu;
@@ -804,7 +805,7 @@ static int half_step(pio_als_handle* h, Side& dst, const Side& src) {
     cudaEventRecord(e.b, st);
   }
   {
-    EvPair& e = next_ev(h, EV_SOLVE);
+    EvPair& e = next_ev(h, &dst == &h->U ? EV_SOLVE_USER : EV_SOLVE);
     cudaEventRecord(e.a, st);
     CK(h, launch_solve(h, dst, src));
     cudaEventRecord(e.b, st);
@@ -1068,7 +1069,7 @@ int pio_als_run(pio_als_handle* h, int n_iters) {
   int nfail = 0;
   CK(h, cudaMemcpyAsync(&nfail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(h, cudaStreamSynchronize(st));
-  double ms[3] = {0, 0, 0};
+  double ms[EV_NKIND] = {0, 0, 0, 0};
   float t = 0;
   for (size_t i = 0; i < h->ev_used; ++i) {
     EvPair& e = h->ev_pool[i];
@@ -1076,12 +1077,26 @@ int pio_als_run(pio_als_handle* h, int n_iters) {
     if (e.kind >= 0) ms[e.kind] += t;
     else h->st.last_run_ms = t;
   }
-  h->st.last_solve_ms = ms[EV_SOLVE];
+  h->st.last_solve_ms = ms[EV_SOLVE] + ms[EV_SOLVE_USER];
+  h->phase_ms[0] = ms[EV_SOLVE];
+  h->phase_ms[1] = ms[EV_SOLVE_USER];
+  h->phase_ms[2] = ms[EV_GRAM];
+  h->phase_ms[3] = ms[EV_COMM];
+  h->phase_ms[6] = (double)n_iters;
   h->st.last_gram_ms = ms[EV_GRAM];
   h->st.last_comm_ms = ms[EV_COMM];
   h->trained = true;
   if (nfail)
     return fail(h, PIO_ALS_ERR_NUMERIC, "%d normal equations were not positive definite (MLlib: dppsv info != 0)", nfail);
+  return PIO_ALS_OK;
+}
+
+int pio_als_get_phase_ms(pio_als_handle* h, double out[8]) {
+  if (!h || !out) return PIO_ALS_ERR_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (int i = 0; i < 8; ++i) out[i] = h->phase_ms[i];
+  out[4] = h->I.use_tc ? 1.0 : 0.0;
+  out[5] = h->U.use_tc ? 1.0 : 0.0;
   return PIO_ALS_OK;
 }
 

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "pio_als_abi_version", "pio_als_device_count", "pio_als_nccl_unique_id", "pio_als_create",
     "pio_als_destroy", "pio_als_last_error", "pio_als_set_ratings_coo", "pio_als_set_ratings_coo_device",
     "pio_als_set_init", "pio_als_run", "pio_als_get_factors", "pio_als_train", "pio_als_recommend",
-    "pio_als_similar", "pio_als_save", "pio_als_load", "pio_als_get_stats",
+    "pio_als_similar", "pio_als_save", "pio_als_load", "pio_als_get_stats", "pio_als_get_phase_ms",
     "pio_als_synth_ratings_device", "pio_nb_train", "pio_nb_predict",
 ]
 
@@ -259,6 +259,13 @@ class NativeALS:
         st = Stats()
         self._check(lib().pio_als_get_stats(self._h, C.byref(st)))
         return {name: getattr(st, name) for name, _ in Stats._fields_ if name != "reserved"}
+
+    def phase_ms(self) -> dict:
+        """Device-time breakdown of the last run (pio_als_get_phase_ms)."""
+        out = (C.c_double * 8)()
+        self._check(lib().pio_als_get_phase_ms(self._h, out))
+        return {"item_solve_ms": out[0], "user_solve_ms": out[1], "gram_ms": out[2], "comm_ms": out[3],
+                "item_side_tensor_core": bool(out[4]), "user_side_tensor_core": bool(out[5]), "iterations": int(out[6])}
 
 
 def synth_ratings_device(device, n_users, n_items, nnz, seed, implicit, start, d_user, d_item, d_rating):
