@@ -187,11 +187,14 @@ __device__ __forceinline__ void chol_solve_warp(float* slot, const float* bvec, 
     bAv -= la * yj;
     bBv -= lm * yj;
     __syncwarp();
+    // the scaled column is read back as broadcast LDS.128 (one wavefront per four columns)
 #pragma unroll
-    for (int c = j + 1; c < H; ++c) {
-      const float x = cb_[c];
-      ra[c] -= la * x;
-      rm[c] -= lm * x;
+    for (int g = (j + 1) / 4; g < H / 4; ++g) {
+      const float4 x = reinterpret_cast<const float4*>(cb_)[g];
+      if (4 * g + 0 > j) { ra[4 * g + 0] -= la * x.x; rm[4 * g + 0] -= lm * x.x; }
+      if (4 * g + 1 > j) { ra[4 * g + 1] -= la * x.y; rm[4 * g + 1] -= lm * x.y; }
+      if (4 * g + 2 > j) { ra[4 * g + 2] -= la * x.z; rm[4 * g + 2] -= lm * x.z; }
+      if (4 * g + 3 > j) { ra[4 * g + 3] -= la * x.w; rm[4 * g + 3] -= lm * x.w; }
     }
   }
   __syncwarp();
@@ -250,7 +253,13 @@ __device__ __forceinline__ void chol_solve_warp(float* slot, const float* bvec, 
     bBv -= l2 * yj;
     __syncwarp();
 #pragma unroll
-    for (int c = j + 1; c < H; ++c) r2[c] -= l2 * cb_[c];
+    for (int g = (j + 1) / 4; g < H / 4; ++g) {
+      const float4 x = reinterpret_cast<const float4*>(cb_)[g];
+      if (4 * g + 0 > j) r2[4 * g + 0] -= l2 * x.x;
+      if (4 * g + 1 > j) r2[4 * g + 1] -= l2 * x.y;
+      if (4 * g + 2 > j) r2[4 * g + 2] -= l2 * x.z;
+      if (4 * g + 3 > j) r2[4 * g + 3] -= l2 * x.w;
+    }
   }
   __syncwarp();
   float* L22 = slot + OFF22;

@@ -268,6 +268,9 @@ struct TcParams {
   int* counter;  // next row to claim (starts at sp.row_begin)
   long long* timing;  // debug only (PIO_ALS_TC_TIMING=1): [grid][16 warps][8] cycle counters, else null
   float* dbg;    // debug only (PIO_ALS_TC_DEBUG=1): per local row ASLOT + KP floats (A as drained, b), else null
+  float* out;    // split mode: per local row ASLOT + KP floats (packed lower triangle of the Gramian, then b); the rows
+                 // are solved afterwards by als_solve_packed_kernel with every warp of the SM; null = solve in this kernel
+  int out_row0;  // local row stored at out[0] (the buffer covers one tile of rows)
 };
 
 template <bool IMPLICIT>
@@ -858,7 +861,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
         for (int c = lane; c < KP; c += 32) o[ASLOT + c] = sm.bslot[t][slot][c];
         __syncwarp();
       }
-      if (r >= 0 && d.last[slot]) {
+      if (r >= 0 && d.last[slot] && tp.out) {
+        // split mode: hand the finished normal equations to the solver kernel (coalesced 16-byte stores)
+        float4* o4 = reinterpret_cast<float4*>(tp.out + (size_t)(r - tp.out_row0) * (ASLOT + KP));
+        const float4* a4 = reinterpret_cast<const float4*>(&sm.aslot[t][slot][0]);
+        for (int c = lane; c < ASLOT / 4; c += 32) o4[c] = a4[c];
+        const float4* b4 = reinterpret_cast<const float4*>(&sm.bslot[t][slot][0]);
+        if (lane < KP / 4) o4[ASLOT / 4 + lane] = b4[lane];
+      } else if (r >= 0 && d.last[slot]) {
         const float ridge = p.lambda * p.nreg[r];
         chol_solve_warp<KP, 8, 72, IMPLICIT, true>(&sm.aslot[t][slot][0], &sm.bslot[t][slot][0], p.yty, ridge, p.k,
                                                    &sm.colbuf[t * NSLOT + slot][0], &sm.dinv[t * NSLOT + slot][0],
@@ -877,6 +887,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) als_solve_tc_kernel(const TcParam
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---- split mode, second half: one warp per row solves the normal equations the tensor-core kernel left in `in`
+// (ASLOT + KP floats per local row). 128-thread CTAs, four per SM by registers: all 16 resident warps factorise.
+constexpr int SOLVE_WARPS = 4;
+constexpr int SOLVE_SMEM_PER_WARP = ASLOT + KP + 2 * KP + KP;   // slot, b, column double buffer, 1/diag
+template <bool IMPLICIT>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32, 3) als_solve_packed_kernel(const SolveParams p, const float* __restrict__ in, int in_row0) {
+  extern __shared__ __align__(16) float solve_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* slot = solve_smem + warp * SOLVE_SMEM_PER_WARP;
+  float* bv = slot + ASLOT;
+  float* colbuf = bv + KP;
+  float* dinv = colbuf + 2 * KP;
+  const int nwarps = gridDim.x * SOLVE_WARPS;
+  for (int r = p.row_begin + blockIdx.x * SOLVE_WARPS + warp; r < p.row_end; r += nwarps) {
+    const float4* src = reinterpret_cast<const float4*>(in + (size_t)(r - in_row0) * (ASLOT + KP));
+    float4* dst4 = reinterpret_cast<float4*>(slot);
+    for (int c = lane; c < (ASLOT + KP) / 4; c += 32) cp_async16(dst4 + c, src + c);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    chol_solve_warp<KP, 8, 72, IMPLICIT, true>(slot, bv, p.yty, p.lambda * p.nreg[r], p.k, colbuf, dinv,
+                                               p.dst + (size_t)(p.dst_row_offset + r) * KP, p.fail);
+    __syncwarp();
+  }
 }
 
 }  // namespace tc

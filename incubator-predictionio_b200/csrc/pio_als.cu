@@ -27,6 +27,7 @@ namespace pio {
 
 constexpr int HEAVY_T = 4096;     // rows with more ratings than this are cut into parts (als_finish_kernel solves them)
 constexpr int HEAVY_T_TC = 8192;  // same threshold when the tensor-core path handles the shorter rows
+constexpr int TC_TILE_ROWS = 1 << 20;  // split mode: rows whose normal equations are buffered at once (9.1 KB per row)
 constexpr int PART = 2016;        // ratings per part (multiple of every CH and of the tensor-core stage size 24)
 
 static thread_local std::string g_create_error;
@@ -348,6 +349,9 @@ struct pio_als_handle {
   float* d_dbg = nullptr;     // PIO_ALS_TC_DEBUG=1: A/b dump of the last tensor-core half-step
   size_t dbg_rows = 0;
   bool use_tc = false;        // rank in 33..64 and PIO_ALS_TC != 0
+  bool tc_split = false;      // PIO_ALS_TC_SPLIT=1: the tensor-core kernel only accumulates, a second kernel solves (measured: no gain)
+  float* tc_out = nullptr;    // split mode: normal equations of one tile of rows ([rows][ASLOT + KP])
+  size_t tc_out_rows = 0;
   double tc_min_deg = 0.0;    // PIO_ALS_TC_MIN_DEG: only sides whose rows average at least this many ratings use it
   bool have_ratings = false, have_init = false, trained = false;
   ncclComm_t comm = nullptr;
@@ -721,22 +725,29 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
     p.row_begin = dst.n_heavy;
     p.row_end = dst.n_active;
     if (dst.use_tc && Cfg::KP == 64) {
-      // Gramian on tcgen05 (als_tc_kernel.cuh): persistent, one CTA per SM, rows claimed dynamically
+      // Gramians on tcgen05 (als_tc_kernel.cuh): persistent, one CTA per SM, rows assigned statically.
+      // Split mode (PIO_ALS_TC_SPLIT=1, off by default): the kernel only accumulates and stores the normal equations of a
+      // tile of rows; a second kernel solves them with every warp of the SM.  Measured at C2: item side 15.0 vs 15.4 ms
+      // fused, user side 39.7 vs 38.2 ms fused (the one-warp 64x64 Cholesky is latency-bound, ~50-70 k cycles per row,
+      // so twelve solver warps per SM at 168 registers do not beat eight fused ones overlapped with the MMAs).
       static bool attr_set[64] = {};
       const size_t smem = sizeof(tc::Smem) + 1024;
+      const size_t ssmem = sizeof(float) * tc::SOLVE_WARPS * tc::SOLVE_SMEM_PER_WARP;
       auto kern = imp ? tc::als_solve_tc_kernel<true> : tc::als_solve_tc_kernel<false>;
+      auto skern = imp ? tc::als_solve_packed_kernel<true> : tc::als_solve_packed_kernel<false>;
       if (h->cfg.device < 64 && !attr_set[h->cfg.device]) {
         if ((e = cudaFuncSetAttribute(tc::als_solve_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(tc::als_solve_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(tc::als_solve_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(tc::als_solve_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem)) != cudaSuccess) return e;
         attr_set[h->cfg.device] = true;
       }
-      set_int_kernel<<<1, 1, 0, h->stream>>>(h->d_counter, p.row_begin);
-      LAUNCHED(h);
       tc::TcParams tp;
-      tp.sp = p;
       tp.counter = h->d_counter;
       tp.dbg = nullptr;
       tp.timing = nullptr;
+      tp.out = nullptr;
+      tp.out_row0 = 0;
       if (getenv("PIO_ALS_TC_TIMING")) {
         if (!h->d_timing && (e = cudaMalloc((void**)&h->d_timing, (size_t)h->sm_count * 16 * 8 * sizeof(long long))) != cudaSuccess) return e;
         cudaMemsetAsync(h->d_timing, 0, (size_t)h->sm_count * 16 * 8 * sizeof(long long), h->stream);
@@ -752,12 +763,40 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
         tp.dbg = h->d_dbg;
       }
       const int per_cta = tc::NTEAM * tc::NSLOT;
-      int grid = (nlight + per_cta - 1) / per_cta;
-      if (grid > h->sm_count) grid = h->sm_count;
-      kern<<<grid, tc::NTHREADS, smem, h->stream>>>(tp);
-      LAUNCHED(h);
-      ++h->st.solve_launches;
-      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      const int tile = h->tc_split ? TC_TILE_ROWS : nlight;
+      if (h->tc_split) {
+        const size_t need = (size_t)(nlight < tile ? nlight : tile);
+        if (h->tc_out_rows < need) {
+          if (h->tc_out) cudaFree(h->tc_out);
+          h->tc_out = nullptr;
+          h->tc_out_rows = 0;
+          if ((e = cudaMalloc((void**)&h->tc_out, need * (tc::ASLOT + tc::KP) * sizeof(float))) != cudaSuccess) return e;
+          h->tc_out_rows = need;
+        }
+      }
+      for (int t0 = p.row_begin; t0 < p.row_end; t0 += tile) {
+        SolveParams q = p;
+        q.row_begin = t0;
+        q.row_end = t0 + tile < p.row_end ? t0 + tile : p.row_end;
+        const int nrows = q.row_end - q.row_begin;
+        tp.sp = q;
+        tp.out = h->tc_split ? h->tc_out : nullptr;
+        tp.out_row0 = t0;
+        int grid = (nrows + per_cta - 1) / per_cta;
+        if (grid > h->sm_count) grid = h->sm_count;
+        kern<<<grid, tc::NTHREADS, smem, h->stream>>>(tp);
+        LAUNCHED(h);
+        ++h->st.solve_launches;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (h->tc_split) {
+          int sgrid = (nrows + tc::SOLVE_WARPS - 1) / tc::SOLVE_WARPS;
+          if (sgrid > 4 * h->sm_count) sgrid = 4 * h->sm_count;
+          skern<<<sgrid, tc::SOLVE_WARPS * 32, ssmem, h->stream>>>(q, h->tc_out, t0);
+          LAUNCHED(h);
+          ++h->st.solve_launches;
+          if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+      }
     } else {
       const int grid = (nlight + Cfg::NG - 1) / Cfg::NG;
       e = imp ? launch_solve_one<Cfg, true, false>(h, p, grid, h->stream) : launch_solve_one<Cfg, false, false>(h, p, grid, h->stream);
@@ -890,6 +929,7 @@ static int create_common(pio_als_handle* h) {
     h->use_tc = h->KP == 64 && !(env && env[0] == '0');
     h->tc_min_deg = (env && env[0] == '1') ? 0.0 : 256.0;
     if (const char* md = getenv("PIO_ALS_TC_MIN_DEG")) h->tc_min_deg = atof(md);
+    if (const char* sp = getenv("PIO_ALS_TC_SPLIT")) h->tc_split = sp[0] == '1';
   }
   h->gram_blocks = 2 * h->sm_count;
   if (cudaMallocAsync((void**)&h->yty, sizeof(float) * h->KP * h->KP, h->stream) != cudaSuccess ||
@@ -945,6 +985,9 @@ void pio_als_destroy(pio_als_handle* h) {
     dfree(h, h->d_counts);
     dfree(h, h->d_counter);
     cudaStreamSynchronize(h->stream);
+    if (h->tc_out) cudaFree(h->tc_out);
+    if (h->d_dbg) cudaFree(h->d_dbg);
+    if (h->d_timing) cudaFree(h->d_timing);
     for (auto& e : h->ev_pool) {
       cudaEventDestroy(e.a);
       cudaEventDestroy(e.b);

@@ -85,6 +85,19 @@ def test_tensor_core_gramian_path(native, oracle, monkeypatch, implicit):
     assert eu <= TOL and ei <= TOL, (eu, ei)
 
 
+def test_tensor_core_split_mode_matches_fused(native, oracle, monkeypatch):
+    """PIO_ALS_TC_SPLIT=1: the tcgen05 kernel stores the normal equations and als_solve_packed_kernel solves them;
+    same arithmetic as the fused kernel -> bit-identical factors."""
+    monkeypatch.setenv("PIO_ALS_TC", "1")
+    nu, ni, nnz = 30000, 60, 500000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=11, implicit=True)
+    _, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 3, 0.05, True, 1.0)
+    monkeypatch.setenv("PIO_ALS_TC_SPLIT", "1")
+    _, g2, _ = run_both(native, oracle, nu, ni, u, i, r, 64, 3, 0.05, True, 1.0)
+    assert np.array_equal(g[0], g2[0]) and np.array_equal(g[1], g2[1])
+    assert frob_rel(g2[0], o[0]) <= TOL and frob_rel(g2[1], o[1]) <= TOL
+
+
 def test_config_c1_recommendation_template(native, oracle):
     """BASELINE.json configs[0]: rank 10, 10k x 1k, 100k ratings, explicit, lambda 0.01, 20 iterations, seed 3."""
     nu, ni, nnz = 10000, 1000, 100000
