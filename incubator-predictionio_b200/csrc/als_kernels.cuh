@@ -555,12 +555,12 @@ als_solve_kernel(const SolveParams p) {
     }
     if (IMPLICIT) __syncthreads();
     if (worker) {
-      long long rem = mylen - (long long)c * CH;
-      const int cnt = rem <= 0 ? 0 : (rem < CH ? (int)rem : CH);
+      // every staged row of the chunk is consumed unconditionally: rows past the end of a segment were zero-filled by
+      // issue(), and without a per-rating branch the operand loads of rating i+1 overlap the FMAs of rating i
       const float4* rowp = reinterpret_cast<const float4*>(sbuf + (g * CH) * KP);
+      if (mylen - (long long)c * CH > 0) {
 #pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        if (i < cnt) {
+        for (int i = 0; i < CH; ++i) {
           const float4* rp = rowp + i * F4ROW;
           float P[TB], Q[TB];
           if (TB == 8) {
