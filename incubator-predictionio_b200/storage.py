@@ -150,15 +150,19 @@ class BiMap:
 
     def __init__(self, m: Dict, _inv: Optional["BiMap"] = None):
         self._m = dict(m)
+        # `val inverse` is built eagerly in the reference (BiMap.scala:33-39): a map with duplicated values fails at
+        # construction (require -> IllegalArgumentException; ValueError here), and inverse.inverse is this object
+        if _inv is None:
+            rev = {v: k for k, v in self._m.items()}
+            if len(rev) != len(self._m):
+                raise ValueError("Failed to create reversed map. Cannot have duplicated values.")
+            _inv = BiMap.__new__(BiMap)
+            _inv._m = rev
+            _inv._i = self
         self._i = _inv
 
     @property
     def inverse(self) -> "BiMap":
-        if self._i is None:
-            rev = {v: k for k, v in self._m.items()}
-            if len(rev) != len(self._m):
-                raise ValueError("Failed to create reversed map. Cannot have duplicated values.")
-            self._i = BiMap(rev, self)
         return self._i
 
     def get(self, k):
