@@ -6,6 +6,8 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
+if str(ROOT / "tests") not in sys.path:   # helper modules next to the tests (lowrank_cases.py)
+    sys.path.insert(0, str(ROOT / "tests"))
 
 import pio_b200  # noqa: E402,F401  (registers the package under an importable name)
 

@@ -98,6 +98,19 @@ def test_tensor_core_split_mode_matches_fused(native, oracle, monkeypatch):
     assert frob_rel(g2[0], o[0]) <= TOL and frob_rel(g2[1], o[1]) <= TOL
 
 
+def test_low_rank_recovery_cases(native, oracle):
+    """MLlib-suite style recovery checks (tests/lowrank_cases.py) through the C ABI: the CUDA path reaches the same
+    targets as the oracle and stays within tolerance of it."""
+    import lowrank_cases as L
+    for name, nu, ni, rank, noise, iters, reg, implicit, metric, target in L.CASES:
+        tr, te = L.gen(nu, ni, rank, noise, implicit)
+        _, g, o = run_both(native, oracle, nu, ni, tr[0], tr[1], tr[2], rank, iters, reg, implicit, 1.0)
+        v = L.score(metric, g[0], g[1], te, g[2], g[3])
+        assert L.passes(metric, v, target), (name, metric, v, target)
+        vo = L.score(metric, o[0], o[1], te, o[2], o[3])
+        assert abs(v - vo) <= 1e-3 * max(1.0, abs(vo)), (name, v, vo)
+
+
 def test_config_c1_recommendation_template(native, oracle):
     """BASELINE.json configs[0]: rank 10, 10k x 1k, 100k ratings, explicit, lambda 0.01, 20 iterations, seed 3."""
     nu, ni, nnz = 10000, 1000, 100000

@@ -131,3 +131,15 @@ def test_naive_bayes_formulas(oracle):
     assert np.allclose(theta[0], np.log((s0 + 1) / (s0.sum() + 3)))
     scores = pi[None, :] + x.astype(np.float64) @ theta.T
     assert oracle.nb_predict(x, pi, theta).tolist() == scores.argmax(1).tolist()
+
+
+def test_low_rank_recovery_cases(oracle):
+    """MLlib-suite style recovery checks (tests/lowrank_cases.py) on the fp64-accumulating oracle."""
+    import lowrank_cases as L
+    for name, nu, ni, rank, noise, iters, reg, implicit, metric, target in L.CASES:
+        tr, te = L.gen(nu, ni, rank, noise, implicit)
+        u0 = synth.synth_init_factors(nu, rank, 5, 0)
+        i0 = synth.synth_init_factors(ni, rank, 5, 1)
+        uf, itf, hu, hi = oracle.als_train(nu, ni, tr[0], tr[1], tr[2], rank, iters, reg, implicit, 1.0, u0, i0)
+        v = L.score(metric, uf, itf, te, hu, hi)
+        assert L.passes(metric, v, target), (name, metric, v, target)
