@@ -1197,18 +1197,32 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
   if (!h->U.F || !h->I.F || !h->I.cand_ext) return fail(h, PIO_ALS_ERR_STATE, "no model");
   CK(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = h->stream;
-  const int KP = h->KP, k = h->cfg.rank;
+  const int KP = h->KP;
   int* d_users = nullptr;
   float* d_xq = nullptr;
   uint8_t *d_valid = nullptr, *d_mask = nullptr;
   ScoreIdx* d_cand = nullptr;
   int *d_oi = nullptr, *d_oc = nullptr;
   float* d_os = nullptr;
-  const int ntiles = (h->I.n_internal + TK_TILE - 1) / TK_TILE;
+  // batched scoring: groups of SB_QB queries share every staged item tile; GX persistent CTAs per group
+  const int ngroups = (n + SB_QB - 1) / SB_QB;
+  const int ntiles = (h->I.n_internal + SB_THREADS - 1) / SB_THREADS;
+  int gx = (2 * h->sm_count + ngroups - 1) / ngroups;
+  if (gx > (ntiles + 7) / 8) gx = (ntiles + 7) / 8;   // at least eight tiles per CTA: the pools must warm up
+  if (gx < 1) gx = 1;
+  const size_t sb_smem = sizeof(double) * (size_t)KP * SB_QB + sb_tile_bytes(KP) +
+                         (sizeof(double) + sizeof(int)) * (size_t)SB_QB * topk;
+  {
+    static size_t attr_smem[64] = {};
+    if (h->cfg.device < 64 && attr_smem[h->cfg.device] < sb_smem) {
+      CK(h, cudaFuncSetAttribute(score_dot_topk_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_smem));
+      attr_smem[h->cfg.device] = sb_smem;
+    }
+  }
   CK(h, dalloc(h, &d_users, (size_t)n));
   CK(h, dalloc(h, &d_xq, (size_t)n * KP));
   CK(h, dalloc(h, &d_valid, (size_t)n));
-  CK(h, dalloc(h, &d_cand, (size_t)n * ntiles * topk));
+  CK(h, dalloc(h, &d_cand, (size_t)n * gx * topk));
   CK(h, dalloc(h, &d_oi, (size_t)n * topk));
   CK(h, dalloc(h, &d_os, (size_t)n * topk));
   CK(h, dalloc(h, &d_oc, (size_t)n));
@@ -1219,15 +1233,17 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
   }
   gather_rows_kernel<<<n, 64, 0, st>>>(h->U.F, KP, d_users, n, h->U.perm, h->U.deg, h->U.n, d_xq, d_valid);
   LAUNCHED(h);
-  // grid.y is limited to 65535 queries per launch
-  for (int q0 = 0; q0 < n; q0 += 32768) {
-    const int nq = n - q0 < 32768 ? n - q0 : 32768;
-    score_dot_topk_kernel<<<dim3(ntiles, nq), TK_THREADS, sizeof(float) * k, st>>>(
-        h->I.F, h->I.n_internal, KP, k, d_xq + (size_t)q0 * KP, d_valid + q0, h->I.cand_ext, d_mask, topk,
-        d_cand + (size_t)q0 * ntiles * topk);
+  // grid.y is limited to 65535 query groups per launch
+  for (int g0 = 0; g0 < ngroups; g0 += 32768) {
+    const int ng = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
+    const int q0 = g0 * SB_QB;
+    const int nq = n - q0 < ng * SB_QB ? n - q0 : ng * SB_QB;
+    score_dot_topk_batched_kernel<<<dim3(gx, ng), SB_THREADS, sb_smem, st>>>(
+        h->I.F, h->I.n_internal, KP, d_xq + (size_t)q0 * KP, d_valid + q0, nq, h->I.cand_ext, d_mask, topk,
+        d_cand + (size_t)q0 * gx * topk);
     LAUNCHED(h);
   }
-  topk_merge_kernel<<<n, TK_THREADS, 0, st>>>(d_cand, ntiles * topk, topk, d_oi, d_os, d_oc);
+  topk_merge_kernel<<<n, TK_THREADS, 0, st>>>(d_cand, gx * topk, topk, d_oi, d_os, d_oc);
   LAUNCHED(h);
   CK(h, cudaMemcpyAsync(out_items, d_oi, sizeof(int) * (size_t)n * topk, cudaMemcpyDeviceToHost, st));
   CK(h, cudaMemcpyAsync(out_scores, d_os, sizeof(float) * (size_t)n * topk, cudaMemcpyDeviceToHost, st));
@@ -1277,18 +1293,39 @@ int pio_als_similar(pio_als_handle* h, const int32_t* query_items, int nq, int t
       CK(h, dalloc(h, &d_mask, (size_t)h->I.n));
       CK(h, cudaMemcpyAsync(d_mask, item_mask, (size_t)h->I.n, cudaMemcpyHostToDevice, st));
     }
-    const int ntiles = (h->I.n_internal + TK_TILE - 1) / TK_TILE;
+    // batched kernel (query vectors resident in shared memory) unless the query is too large for it
+    const int nqv = (int)keep.size();
+    const int nqp = (nqv + SC_G - 1) / SC_G * SC_G;
+    constexpr int SC_WARPS = SB_THREADS / 32;   // one candidate pool per warp
+    const size_t sc_smem = sizeof(double) * ((size_t)KP * nqp + nqp) + sizeof(float) * (size_t)SB_THREADS * (KP + 4) +
+                           (sizeof(double) + sizeof(int)) * (size_t)SC_WARPS * topk + sizeof(int) * (size_t)nq + 16;
+    const bool batched = sc_smem <= 100 * 1024;
+    int ntiles = (h->I.n_internal + TK_TILE - 1) / TK_TILE;
+    if (batched) {
+      const int nt = (h->I.n_internal + SB_THREADS - 1) / SB_THREADS;
+      ntiles = 2 * h->sm_count < (nt + 7) / 8 ? 2 * h->sm_count : (nt + 7) / 8;   // = CTAs (>= 8 tiles each)
+      static size_t attr_smem[64] = {};
+      if (h->cfg.device < 64 && attr_smem[h->cfg.device] < sc_smem) {
+        CK(h, cudaFuncSetAttribute(score_cos_topk_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+        attr_smem[h->cfg.device] = sc_smem;
+      }
+    }
     ScoreIdx* d_cand = nullptr;
     int *d_oi = nullptr, *d_oc = nullptr;
     float* d_os = nullptr;
-    CK(h, dalloc(h, &d_cand, (size_t)ntiles * topk));
+    const int npools = batched ? ntiles * SC_WARPS : ntiles;   // candidate lists of topk entries left for the merge
+    CK(h, dalloc(h, &d_cand, (size_t)npools * topk));
     CK(h, dalloc(h, &d_oi, (size_t)topk));
     CK(h, dalloc(h, &d_os, (size_t)topk));
     CK(h, dalloc(h, &d_oc, 1));
-    score_cos_topk_kernel<<<ntiles, TK_THREADS, 0, st>>>(h->I.F, h->I.n_internal, KP, k, d_qc, d_q, nq, (int)keep.size(),
-                                                         h->I.cand_ext, d_mask, topk, d_cand);
+    if (batched)
+      score_cos_topk_batched_kernel<<<ntiles, SB_THREADS, sc_smem, st>>>(h->I.F, h->I.n_internal, KP, k, d_qc, d_q, nq, nqv,
+                                                                         h->I.cand_ext, d_mask, topk, d_cand);
+    else
+      score_cos_topk_kernel<<<ntiles, TK_THREADS, 0, st>>>(h->I.F, h->I.n_internal, KP, k, d_qc, d_q, nq, nqv,
+                                                           h->I.cand_ext, d_mask, topk, d_cand);
     LAUNCHED(h);
-    topk_merge_kernel<<<1, TK_THREADS, 0, st>>>(d_cand, ntiles * topk, topk, d_oi, d_os, d_oc);
+    topk_merge_kernel<<<1, TK_THREADS, 0, st>>>(d_cand, npools * topk, topk, d_oi, d_os, d_oc);
     LAUNCHED(h);
     CK(h, cudaMemcpyAsync(out_items, d_oi, sizeof(int) * topk, cudaMemcpyDeviceToHost, st));
     CK(h, cudaMemcpyAsync(out_scores, d_os, sizeof(float) * topk, cudaMemcpyDeviceToHost, st));

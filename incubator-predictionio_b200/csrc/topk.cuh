@@ -71,38 +71,339 @@ __device__ __forceinline__ void block_select_topk(double (&sc)[TK_ITEMS], int (&
   }
 }
 
-// grid: (n_tiles, n_queries). xq: query vectors [n_queries][KP] (device, zero padded);
-// qvalid[q] == 0 -> no candidates. cand: [n_queries][n_tiles][topk].
-__global__ void __launch_bounds__(TK_THREADS)
-score_dot_topk_kernel(const float* __restrict__ Y, int n_items, int kp, int k,
-                      const float* __restrict__ xq, const uint8_t* __restrict__ qvalid,
-                      const int* __restrict__ cand_ext, const uint8_t* __restrict__ mask,
-                      int topk, ScoreIdx* __restrict__ cand) {
-  extern __shared__ float sx[];
-  const int q = blockIdx.y;
-  for (int t = threadIdx.x; t < k; t += TK_THREADS) sx[t] = xq[(size_t)q * kp + t];
-  __syncthreads();
-  double sc[TK_ITEMS];
-  int ix[TK_ITEMS];
-  const bool qok = qvalid[q] != 0;
-#pragma unroll
-  for (int j = 0; j < TK_ITEMS; ++j) {
-    const int i = blockIdx.x * TK_TILE + j * TK_THREADS + threadIdx.x;
-    sc[j] = 0.0;
-    ix[j] = -1;
-    const int ext = (qok && i < n_items) ? cand_ext[i] : -1;  // external id, -1 = owns no factor
-    if (ext >= 0 && !(mask && mask[ext])) {
-      const float* y = Y + (size_t)i * kp;
-      double s = 0.0;
-      for (int t = 0; t < k; ++t) s += (double)sx[t] * (double)y[t];
-      sc[j] = s;
-      ix[j] = ext;
-    }
-  }
-  block_select_topk(sc, ix, topk, cand + ((size_t)q * gridDim.x + blockIdx.x) * topk);
+// ---- batched dot-product scoring -------------------------------------------------------------------------------
+// grid: (GX persistent CTAs striding over 256-item tiles, query groups of SB_QB queries).  A tile of the item factor
+// matrix is staged once (coalesced cp.async, padded rows -> conflict-free LDS.128) and scored against all SB_QB queries
+// of the group from registers: the matrix is read n_queries / SB_QB times instead of n_queries times.  Each query
+// keeps a top-k pool in shared memory for the whole scan; an item is offered to it only if it beats the pool's current
+// worst entry (rare after the first tiles), under a per-query lock - no per-tile block-wide selection rounds.
+// xq: [n_queries][kp] (zero padded), qvalid[q] == 0 -> no candidates.  cand: [n_queries][GX][topk], unsorted, i = -1 = empty.
+constexpr int SB_THREADS = 256;
+constexpr int SB_QB = 16;
+// staged tile [SB_THREADS][kp + 4] floats, large enough to be reused for the [SB_QB][SB_THREADS] fp64 score exchange + ids
+__host__ __device__ inline size_t sb_tile_bytes(int kp) {
+  const size_t a = sizeof(float) * (size_t)SB_THREADS * (kp + 4);
+  const size_t b = sizeof(double) * (size_t)SB_QB * SB_THREADS + sizeof(int) * SB_THREADS;
+  return a > b ? a : b;
 }
 
-// one query = a set of item vectors. qf: [nqv][KP] vectors of the query items that own a factor
+__device__ __forceinline__ void sb_cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+
+// A top-k pool in shared memory shared by the whole CTA: unsorted (score, id) entries, the index / score of its worst
+// entry and a spin lock.  Called by all 32 lanes of a warp (want = this lane has a candidate).  The unlocked pre-check
+// is conservative (thr only rises; ties go on to the locked re-check), so the final pool holds exactly the best topk
+// under better(): higher score first, smaller external id on equal scores.
+__device__ __forceinline__ void pool_offer(bool want, double s, int ext, int topk, double* hs, int* hi, double* thr,
+                                           int* cnt, int* worst, int* lock) {
+  const int lane = threadIdx.x & 31;
+  if (want) {
+    const int c = *reinterpret_cast<volatile int*>(cnt);
+    if (c >= topk) want = s >= *reinterpret_cast<volatile double*>(thr);
+  }
+  unsigned m = __ballot_sync(0xffffffffu, want);
+  while (m) {
+    const int leader = __ffs(m) - 1;
+    m &= m - 1;
+    if (lane == leader) {
+      while (atomicCAS(lock, 0, 1) != 0) {}
+      __threadfence_block();
+      volatile double* ps = hs;
+      volatile int* pi = hi;
+      int c = *reinterpret_cast<volatile int*>(cnt);
+      bool changed = false;
+      if (c < topk) {
+        ps[c] = s;
+        pi[c] = ext;
+        ++c;
+        *reinterpret_cast<volatile int*>(cnt) = c;
+        changed = c == topk;
+      } else {
+        const int w = *reinterpret_cast<volatile int*>(worst);
+        if (better(s, ext, ps[w], pi[w])) {
+          ps[w] = s;
+          pi[w] = ext;
+          changed = true;
+        }
+      }
+      if (changed) {   // the pool is full: find its new worst entry
+        int w = 0;
+        for (int t = 1; t < topk; ++t)
+          if (better(ps[w], pi[w], ps[t], pi[t])) w = t;
+        *reinterpret_cast<volatile int*>(worst) = w;
+        *reinterpret_cast<volatile double*>(thr) = ps[w];
+      }
+      __threadfence_block();
+      atomicExch(lock, 0);
+    }
+    __syncwarp();
+  }
+}
+
+// A top-k pool owned by ONE warp (entries in shared memory, bookkeeping in warp-uniform registers): no lock, no atomics.
+// All 32 lanes call; candidates are taken in lane order.  The worst entry is found cooperatively (each lane scans the
+// entries lane, lane+32, ..., then a butterfly reduction), so an insertion costs ~100 cycles instead of a serial scan.
+struct WarpPool {
+  double thr;   // score of the worst entry (valid once cnt == topk)
+  int wid;      // its external id
+  int worst;    // its slot
+  int cnt;
+};
+__device__ __forceinline__ void wpool_find_worst(WarpPool& wp, int topk, const double* ps, const int* pi) {
+  const int lane = threadIdx.x & 31;
+  double ws = 0.0;
+  int wi = -1, wslot = -1;
+  for (int t = lane; t < topk; t += 32) {
+    const double s = ps[t];
+    const int i = pi[t];
+    if (wslot < 0 || better(ws, wi, s, i)) { ws = s; wi = i; wslot = t; }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double os = __shfl_xor_sync(0xffffffffu, ws, d);
+    const int oi = __shfl_xor_sync(0xffffffffu, wi, d);
+    const int oslot = __shfl_xor_sync(0xffffffffu, wslot, d);
+    if (oslot >= 0 && (wslot < 0 || better(ws, wi, os, oi))) { ws = os; wi = oi; wslot = oslot; }
+  }
+  wp.thr = ws;
+  wp.wid = wi;
+  wp.worst = wslot;
+}
+__device__ __forceinline__ void wpool_offer(WarpPool& wp, bool want, double s, int ext, int topk, double* ps, int* pi) {
+  const int lane = threadIdx.x & 31;
+  want = want && (wp.cnt < topk || s >= wp.thr);
+  unsigned m = __ballot_sync(0xffffffffu, want);
+  while (m) {
+    const int leader = __ffs(m) - 1;
+    m &= m - 1;
+    const double cs = __shfl_sync(0xffffffffu, s, leader);
+    const int ce = __shfl_sync(0xffffffffu, ext, leader);
+    if (wp.cnt < topk) {
+      if (lane == 0) { ps[wp.cnt] = cs; pi[wp.cnt] = ce; }
+      ++wp.cnt;
+      __syncwarp();
+      if (wp.cnt == topk) wpool_find_worst(wp, topk, ps, pi);
+    } else if (better(cs, ce, wp.thr, wp.wid)) {
+      if (lane == 0) { ps[wp.worst] = cs; pi[wp.worst] = ce; }
+      __syncwarp();
+      wpool_find_worst(wp, topk, ps, pi);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SB_THREADS, 2)
+score_dot_topk_batched_kernel(const float* __restrict__ Y, int n_items, int kp,
+                              const float* __restrict__ xq, const uint8_t* __restrict__ qvalid, int n_queries,
+                              const int* __restrict__ cand_ext, const uint8_t* __restrict__ mask,
+                              int topk, ScoreIdx* __restrict__ cand) {
+  extern __shared__ __align__(16) unsigned char sb_smem[];
+  const int row = kp + 4;                                         // floats per staged row (16-byte skew per row)
+  double* xd = reinterpret_cast<double*>(sb_smem);                // [kp][SB_QB]
+  float* tile = reinterpret_cast<float*>(xd + (size_t)kp * SB_QB);   // [SB_THREADS][row]; reused for the score exchange
+  const size_t tile_bytes = sb_tile_bytes(kp);
+  double* hs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tile) + tile_bytes);   // [SB_QB][topk]
+  int* hi = reinterpret_cast<int*>(hs + (size_t)SB_QB * topk);    // [SB_QB][topk]
+  double* scs = reinterpret_cast<double*>(tile);                  // [SB_QB][SB_THREADS] scores of the current tile
+  int* sext = reinterpret_cast<int*>(scs + (size_t)SB_QB * SB_THREADS);   // [SB_THREADS] their external ids
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q0 = blockIdx.y * SB_QB;
+  for (int o = tid; o < kp * SB_QB; o += SB_THREADS) {
+    const int t = o / SB_QB, q = o % SB_QB;
+    xd[o] = (q0 + q < n_queries) ? (double)xq[(size_t)(q0 + q) * kp + t] : 0.0;
+  }
+  // warp w owns the pools of queries w*QPW .. w*QPW+QPW-1 of the group
+  constexpr int QPW = SB_QB / (SB_THREADS / 32);
+  WarpPool wp[QPW];
+#pragma unroll
+  for (int j = 0; j < QPW; ++j) { wp[j].thr = 0.0; wp[j].wid = -1; wp[j].worst = 0; wp[j].cnt = 0; }
+  unsigned qmask = 0;   // queries of this group that take candidates
+  for (int q = 0; q < SB_QB; ++q)
+    if (q0 + q < n_queries && qvalid[q0 + q]) qmask |= 1u << q;
+  const int ntiles = (n_items + SB_THREADS - 1) / SB_THREADS;
+  const int f4row = kp / 4;
+  for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const int base = tl * SB_THREADS;
+    __syncthreads();   // the previous tile has been consumed (and xd / pools are initialised)
+    for (int o = tid; o < SB_THREADS * f4row; o += SB_THREADS) {
+      const int r = o / f4row, c4 = o % f4row;
+      float* d = tile + (size_t)r * row + c4 * 4;
+      if (base + r < n_items) sb_cp_async16(d, Y + (size_t)(base + r) * kp + c4 * 4);
+      else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    const int i = base + tid;
+    int ext = (i < n_items) ? cand_ext[i] : -1;    // external id, -1 = owns no factor
+    if (ext >= 0 && mask && mask[ext]) ext = -1;
+    double acc[SB_QB];
+#pragma unroll
+    for (int q = 0; q < SB_QB; ++q) acc[q] = 0.0;
+    if (ext >= 0 && qmask) {
+      const float4* yrow = reinterpret_cast<const float4*>(tile + (size_t)tid * row);
+      for (int c4 = 0; c4 < f4row; ++c4) {
+        const float4 y4 = yrow[c4];
+        const float ye[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double yd = (double)ye[e];
+          const double2* xr = reinterpret_cast<const double2*>(xd + (size_t)(c4 * 4 + e) * SB_QB);
+#pragma unroll
+          for (int q = 0; q < SB_QB; q += 2) {
+            const double2 x2 = xr[q / 2];
+            acc[q] = fma(x2.x, yd, acc[q]);       // index order t = 0..k-1, like blas.ddot over Array[Double]
+            acc[q + 1] = fma(x2.y, yd, acc[q + 1]);
+          }
+        }
+      }
+    }
+    // exchange: every thread publishes its SB_QB scores, then each warp feeds the pools it owns (no locks)
+    __syncthreads();   // the staged rows are dead
+#pragma unroll
+    for (int q = 0; q < SB_QB; ++q) scs[q * SB_THREADS + tid] = acc[q];
+    sext[tid] = ext;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < QPW; ++j) {
+      const int q = warp * QPW + j;
+      if ((qmask >> q) & 1u) {
+        for (int it = lane; it < SB_THREADS; it += 32) {
+          const int e = sext[it];
+          wpool_offer(wp[j], e >= 0, scs[q * SB_THREADS + it], e, topk, hs + (size_t)q * topk, hi + (size_t)q * topk);
+        }
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < QPW; ++j) {
+    const int q = warp * QPW + j;
+    if (q0 + q < n_queries) {
+      for (int t = lane; t < topk; t += 32) {
+        ScoreIdx e;
+        e.s = t < wp[j].cnt ? hs[(size_t)q * topk + t] : 0.0;
+        e.i = t < wp[j].cnt ? hi[(size_t)q * topk + t] : -1;
+        cand[((size_t)(q0 + q) * gridDim.x + blockIdx.x) * topk + t] = e;
+      }
+    }
+  }
+}
+
+// ---- similarproduct scoring, same structure: one query = nqv item vectors -------------------------------------
+// qf: [nqv][kp] vectors of the query items that own a factor (query order kept); qid: all nq_all query item ids
+// (external) - every one of them is excluded from the candidates (ALSAlgorithm.scala:243-245).  score_i = sum over the
+// query vectors, in query order, of d / (sqrt(n1) * sqrt(n2)) with d, n1, n2 accumulated in fp64 in index order
+// (ALSAlgorithm.scala:220-234), kept only if > 0.  cand: [gridDim.x][warps][topk].
+constexpr int SC_G = 8;   // query vectors scored per pass over a staged row
+
+__global__ void __launch_bounds__(SB_THREADS, 2)
+score_cos_topk_batched_kernel(const float* __restrict__ Y, int n_items, int kp, int k,
+                              const float* __restrict__ qf, const int* __restrict__ qid, int nq_all, int nqv,
+                              const int* __restrict__ cand_ext, const uint8_t* __restrict__ mask,
+                              int topk, ScoreIdx* __restrict__ cand) {
+  extern __shared__ __align__(16) unsigned char sb_smem[];
+  const int row = kp + 4;
+  const int nqp = (nqv + SC_G - 1) / SC_G * SC_G;
+  double* xd = reinterpret_cast<double*>(sb_smem);                     // [kp][nqp]
+  double* s1 = xd + (size_t)kp * nqp;                                   // [nqp] sqrt(n1) of every query vector
+  float* tile = reinterpret_cast<float*>(s1 + nqp);                    // [SB_THREADS][row]
+  double* hs = reinterpret_cast<double*>(tile + (size_t)SB_THREADS * row);   // [warps][topk] one pool per warp
+  int* hi = reinterpret_cast<int*>(hs + (size_t)(SB_THREADS / 32) * topk);   // [warps][topk]
+  int* sq = hi + (size_t)(SB_THREADS / 32) * topk;                      // [nq_all] excluded ids
+  const int tid = threadIdx.x;
+  for (int o = tid; o < kp * nqp; o += SB_THREADS) {
+    const int c = o / nqp, t = o % nqp;
+    xd[o] = (t < nqv) ? (double)qf[(size_t)t * kp + c] : 0.0;
+  }
+  for (int t = tid; t < nqp; t += SB_THREADS) {
+    double n1 = 0.0;
+    if (t < nqv)
+      for (int c = 0; c < k; ++c) {
+        const double a = (double)qf[(size_t)t * kp + c];
+        n1 += a * a;
+      }
+    s1[t] = sqrt(n1);
+  }
+  for (int t = tid; t < nq_all; t += SB_THREADS) sq[t] = qid[t];
+  const int lane = tid & 31, warp = tid >> 5;
+  WarpPool wp;
+  wp.thr = 0.0; wp.wid = -1; wp.worst = 0; wp.cnt = 0;
+  double* ps = hs + (size_t)warp * topk;
+  int* pi = hi + (size_t)warp * topk;
+  const int ntiles = (n_items + SB_THREADS - 1) / SB_THREADS;
+  const int f4row = kp / 4;
+  for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const int base = tl * SB_THREADS;
+    __syncthreads();
+    for (int o = tid; o < SB_THREADS * f4row; o += SB_THREADS) {
+      const int r = o / f4row, c4 = o % f4row;
+      float* d = tile + (size_t)r * row + c4 * 4;
+      if (base + r < n_items) sb_cp_async16(d, Y + (size_t)(base + r) * kp + c4 * 4);
+      else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    const int i = base + tid;
+    int ext = (i < n_items) ? cand_ext[i] : -1;
+    if (ext >= 0 && mask && mask[ext]) ext = -1;
+    if (ext >= 0)
+      for (int t = 0; t < nq_all; ++t)
+        if (sq[t] == ext) { ext = -1; break; }
+    double score = 0.0;
+    if (ext >= 0) {
+      const float4* yrow = reinterpret_cast<const float4*>(tile + (size_t)tid * row);
+      double n2 = 0.0;
+      for (int c4 = 0; c4 < f4row; ++c4) {
+        const float4 y4 = yrow[c4];
+        const double b0 = (double)y4.x, b1 = (double)y4.y, b2 = (double)y4.z, b3 = (double)y4.w;
+        n2 = fma(b0, b0, n2);   // padded columns are zero; b * b is exact in fp64, so fma == the reference's n2 += b * b
+        n2 = fma(b1, b1, n2);
+        n2 = fma(b2, b2, n2);
+        n2 = fma(b3, b3, n2);
+      }
+      const double s2 = sqrt(n2);
+      for (int g = 0; g < nqp; g += SC_G) {
+        double d[SC_G];
+#pragma unroll
+        for (int j = 0; j < SC_G; ++j) d[j] = 0.0;
+        for (int c4 = 0; c4 < f4row; ++c4) {
+          const float4 y4 = yrow[c4];
+          const float ye[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const double yd = (double)ye[e];
+            const double2* xr = reinterpret_cast<const double2*>(xd + (size_t)(c4 * 4 + e) * nqp + g);
+#pragma unroll
+            for (int j = 0; j < SC_G; j += 2) {
+              const double2 x2 = xr[j / 2];
+              d[j] = fma(x2.x, yd, d[j]);
+              d[j + 1] = fma(x2.y, yd, d[j + 1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < SC_G; ++j)
+          if (g + j < nqv) {
+            const double n1n2 = s1[g + j] * s2;
+            score += (n1n2 == 0.0) ? 0.0 : d[j] / n1n2;
+          }
+      }
+    }
+    wpool_offer(wp, ext >= 0 && score > 0.0, score, ext, topk, ps, pi);   // each warp pools the items it scored
+  }
+  __syncwarp();
+  for (int t = lane; t < topk; t += 32) {
+    ScoreIdx e;
+    e.s = t < wp.cnt ? ps[t] : 0.0;
+    e.i = t < wp.cnt ? pi[t] : -1;
+    cand[((size_t)blockIdx.x * (SB_THREADS / 32) + warp) * topk + t] = e;
+  }
+}
+
+// (fallback for very large queries) one query = a set of item vectors. qf: [nqv][KP] vectors of the query items that own a factor
 // (query order kept); qid: all nq_all query item ids (external) -- every one of them is excluded
 // from the candidates (ALSAlgorithm.scala:243-245 `!queryList.contains(i)`).
 __global__ void __launch_bounds__(TK_THREADS)
@@ -143,50 +444,47 @@ score_cos_topk_kernel(const float* __restrict__ Y, int n_items, int kp, int k,
   block_select_topk(sc, ix, topk, cand + (size_t)blockIdx.x * topk);
 }
 
-// grid: n_queries. Merges n_tiles*topk candidates per query -> final topk.
+// grid: n_queries. Merges n_cand unsorted candidates per query (i = -1: empty) -> final topk, best first.
+// The candidates are offered to one shared-memory pool (almost all are rejected by the threshold pre-check once it is
+// full); the survivors are ordered by rank counting (ids are distinct, so better() is a total order).
 __global__ void __launch_bounds__(TK_THREADS)
 topk_merge_kernel(const ScoreIdx* __restrict__ cand, int n_cand, int topk, int* __restrict__ out_items,
                   float* __restrict__ out_scores, int* __restrict__ out_count) {
-  __shared__ ScoreIdx best[TK_MAXK];
+  __shared__ double hs[TK_MAXK];
+  __shared__ int hi[TK_MAXK];
+  __shared__ double hthr;
+  __shared__ int hcnt, hworst, hlock;
   const ScoreIdx* c = cand + (size_t)blockIdx.x * n_cand;
-  // candidates may exceed TK_TILE: fold them through repeated selection rounds
-  double sc[TK_ITEMS];
-  int ix[TK_ITEMS];
-  __shared__ ScoreIdx carry[TK_MAXK];
-  int ncarry = 0;
-  for (int base = 0; base < n_cand || base == 0; base += TK_TILE - TK_MAXK) {
-    // slots [0, ncarry) of this round come from carry, the rest from cand[base...]
-#pragma unroll
-    for (int j = 0; j < TK_ITEMS; ++j) {
-      const int slot = j * TK_THREADS + threadIdx.x;
-      sc[j] = 0.0;
-      ix[j] = -1;
-      if (slot < ncarry) {
-        sc[j] = carry[slot].s;
-        ix[j] = carry[slot].i;
-      } else {
-        const int o = base + slot - ncarry;
-        if (slot - ncarry < TK_TILE - TK_MAXK && o < n_cand) { sc[j] = c[o].s; ix[j] = c[o].i; }
-      }
-    }
-    __syncthreads();
-    block_select_topk(sc, ix, topk, best);
-    __syncthreads();
-    for (int t = threadIdx.x; t < topk; t += TK_THREADS) carry[t] = best[t];
-    ncarry = topk;
-    __syncthreads();
-    if (base + (TK_TILE - TK_MAXK) >= n_cand) break;
-  }
-  int cnt = 0;
-  for (int t = threadIdx.x; t < topk; t += TK_THREADS) {
-    const ScoreIdx b = best[t];
-    out_items[(size_t)blockIdx.x * topk + t] = b.i;
-    out_scores[(size_t)blockIdx.x * topk + t] = b.i >= 0 ? (float)b.s : 0.f;
-  }
   if (threadIdx.x == 0) {
-    for (int t = 0; t < topk; ++t) cnt += best[t].i >= 0;
-    if (out_count) out_count[blockIdx.x] = cnt;
+    hcnt = 0;
+    hworst = 0;
+    hlock = 0;
+    hthr = 0.0;
   }
+  __syncthreads();
+  for (int base = 0; base < n_cand; base += TK_THREADS) {
+    const int o = base + threadIdx.x;
+    ScoreIdx e;
+    e.s = 0.0;
+    e.i = -1;
+    if (o < n_cand) e = c[o];
+    pool_offer(e.i >= 0, e.s, e.i, topk, hs, hi, &hthr, &hcnt, &hworst, &hlock);
+  }
+  __syncthreads();
+  const int cnt = hcnt;
+  for (int t = threadIdx.x; t < topk; t += TK_THREADS) {
+    if (t >= cnt) {   // fewer candidates than topk: the tail stays empty
+      out_items[(size_t)blockIdx.x * topk + t] = -1;
+      out_scores[(size_t)blockIdx.x * topk + t] = 0.f;
+    }
+    if (t < cnt) {
+      int rank = 0;
+      for (int u = 0; u < cnt; ++u) rank += (u != t) && better(hs[u], hi[u], hs[t], hi[t]);
+      out_items[(size_t)blockIdx.x * topk + rank] = hi[t];
+      out_scores[(size_t)blockIdx.x * topk + rank] = (float)hs[t];
+    }
+  }
+  if (threadIdx.x == 0 && out_count) out_count[blockIdx.x] = cnt;
 }
 
 // ------------------------------------------------------------------------------------------
