@@ -144,28 +144,64 @@ rs_scatter_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__
     rnk[r] = prev + __popc(peers & lt);
   }
   __syncthreads();
-  {  // per digit: exclusive prefix over warps, seeded with the global (digit, block) offset
+  // per digit: exclusive prefix over the warps (position inside the digit's run of this tile), the tile-local start of
+  // the run (exclusive scan over the digits) and the global start of the run
+  __shared__ uint32_t lstart[256];
+  __shared__ uint32_t goff[256];
+  __shared__ uint32_t wtot[RS_WARPS];
+  {
     const unsigned d = threadIdx.x;
-    uint32_t run = offs[(size_t)d * nblocks + blockIdx.x];
+    uint32_t run = 0;
 #pragma unroll
     for (int ww = 0; ww < RS_WARPS; ++ww) {
       const uint32_t t = wcnt[ww][d];
       wcnt[ww][d] = run;
       run += t;
     }
+    goff[d] = offs[(size_t)d * nblocks + blockIdx.x];
+    const uint32_t incl = warp_incl_scan(run);
+    if (lane == 31) wtot[w] = incl;
+    __syncthreads();
+    uint32_t pre = 0;
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ++ww)
+      if (ww < w) pre += wtot[ww];
+    lstart[d] = pre + incl - run;
   }
   __syncthreads();
+  // tile-local sort into shared memory ...
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  uint64_t* skey = reinterpret_cast<uint64_t*>(rs_smem);            // [RS_TILE]
+  uint32_t* sval = reinterpret_cast<uint32_t*>(skey + RS_TILE);     // [RS_TILE]
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; ++r) {
     const size_t idx = wbase + (size_t)r * 32 + lane;
     if (idx < n) {
       const unsigned d = (unsigned)(key[r] >> shift) & 255u;
-      const size_t pos = (size_t)wcnt[w][d] + rnk[r];
-      kout[pos] = key[r];
-      vout[pos] = val[r];
+      const uint32_t lp = lstart[d] + wcnt[w][d] + rnk[r];
+      skey[lp] = key[r];
+      sval[lp] = val[r];
+    }
+  }
+  __syncthreads();
+  // ... then out in tile order: consecutive threads write consecutive elements of a digit's run (coalesced), instead
+  // of every lane scattering 12 bytes to its own address
+  const size_t tbase = (size_t)blockIdx.x * RS_TILE;
+  const uint32_t cnt = (uint32_t)(n - tbase < (size_t)RS_TILE ? n - tbase : (size_t)RS_TILE);
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    const uint32_t pidx = (uint32_t)r * RS_THREADS + threadIdx.x;
+    if (pidx < cnt) {
+      const uint64_t kk = skey[pidx];
+      const unsigned d = (unsigned)(kk >> shift) & 255u;
+      const size_t pos = (size_t)goff[d] + (pidx - lstart[d]);
+      kout[pos] = kk;
+      vout[pos] = sval[pidx];
     }
   }
 }
+
+constexpr size_t RS_SCATTER_SMEM = (size_t)RS_TILE * (sizeof(uint64_t) + sizeof(uint32_t));   // 48 KB
 
 // Sorts by key bits [0, nbits). Buffers a = input (clobbered), b = scratch. *result_in_b tells
 // where the sorted data ended up.
@@ -177,6 +213,8 @@ inline cudaError_t radix_sort_pairs(uint64_t* ka, uint32_t* va, uint64_t* kb, ui
   uint32_t* hist = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&hist, (size_t)256 * nblocks * sizeof(uint32_t), st);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
+  if (e != cudaSuccess) return e;
   bool in_b = false;
   for (int shift = 0; shift < nbits; shift += 8) {
     uint64_t* ki = in_b ? kb : ka;
@@ -187,7 +225,7 @@ inline cudaError_t radix_sort_pairs(uint64_t* ka, uint32_t* va, uint64_t* kb, ui
     if (launches) ++*launches;
     e = scan_exclusive_u32(hist, hist, (size_t)256 * nblocks, st, launches);
     if (e != cudaSuccess) return e;
-    rs_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, hist, nblocks);
+    rs_scatter_kernel<<<nblocks, RS_THREADS, RS_SCATTER_SMEM, st>>>(ki, vi, ko, vo, n, shift, hist, nblocks);
     if (launches) ++*launches;
     in_b = !in_b;
   }
