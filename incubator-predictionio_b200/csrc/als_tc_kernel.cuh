@@ -26,7 +26,11 @@
 // A batch = up to four (row, rating-segment) pairs, one per TMEM accumulator (64 columns each);
 // rows longer than SEG ratings are accumulated segment by segment with fp32 adds in shared memory
 // between segments (bounds the length of any single tensor-core accumulation chain).
-#pragma once
+// This header is included once per role partition (pio_als.cu): TC_NS names the namespace, TC_NTEAM / TC_NCONV /
+// TC_NGATHER / TC_NSTAGE / TC_NRAW fix how the sixteen warps and the shared memory of the CTA are divided.
+#ifndef TC_NS
+#error "define TC_NS, TC_NTEAM, TC_NCONV, TC_NGATHER, TC_NSTAGE, TC_NRAW before including als_tc_kernel.cuh"
+#endif
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -38,7 +42,7 @@
 #endif
 
 namespace pio {
-namespace tc {
+namespace TC_NS {
 
 constexpr int KP = 64;
 constexpr int NCOL = 128;                        // staged columns per rating: [hi | lo]
@@ -48,18 +52,19 @@ constexpr int KB_BYTES = KB_RATINGS * NCOL * 4;  // 4096
 constexpr int STAGE_KB = 3;                      // one K-block per producer warp
 constexpr int STAGE_RATINGS = STAGE_KB * KB_RATINGS;  // 24
 constexpr int STAGE_BYTES = STAGE_KB * KB_BYTES;      // 12288
-constexpr int NSTAGE = 7;
-constexpr int NRAW = 7;                          // raw ring: stages of gathered rows in flight
+constexpr int NSTAGE = TC_NSTAGE;                 // UMMA stage ring
+constexpr int NRAW = TC_NRAW;                          // raw ring: stages of gathered rows in flight
 constexpr int RAW_ROW = 288;                     // bytes per gathered row in the raw ring (256 + 32 pad: conflict-free LDS.128)
-constexpr int NGATHER = 2;                       // gather warps (each owns every NGATHER-th stage)
-constexpr int NCONV = 5;                         // converter warps (each owns every NCONV-th stage)
+constexpr int NGATHER = TC_NGATHER;                       // gather warps (each owns every NGATHER-th stage)
+constexpr int NCONV = TC_NCONV;                         // converter warps (each owns every NCONV-th stage)
 constexpr int CONV0 = 1 + NGATHER;               // first converter warp
 constexpr int TEAM0 = CONV0 + NCONV;             // first drain+solve warp (a multiple of 4: warp%4 = TMEM lane quarter = slot)
 static_assert(TEAM0 % 4 == 0, "team warps must start at a multiple of four");
 constexpr int SEG = 21 * STAGE_RATINGS;          // 504 ratings per accumulation segment
-constexpr int NTEAM = 2;
+constexpr int NTEAM = TC_NTEAM;                   // drain + solve teams of four warps
 constexpr int NSLOT = 4;
 constexpr int NTHREADS = 512;
+static_assert((TEAM0 + 4 * NTEAM) * 32 == NTHREADS, "the role partition must fill the sixteen warps of the CTA");
 constexpr int H = 32;
 constexpr int L21S = H + 4;
 constexpr int OFF21 = H * (H + 1) / 2;           // 528
@@ -915,5 +920,20 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32, 3) als_solve_packed_kernel(c
   }
 }
 
-}  // namespace tc
+// what the host launcher needs to know about this role partition
+struct Api {
+  using Params = TcParams;
+  static constexpr int kPerCta = NTEAM * NSLOT;       // rows in flight per CTA (one group of the static assignment)
+  static constexpr int kThreads = NTHREADS;
+  static constexpr size_t kSmem = sizeof(Smem) + 1024;
+  static constexpr int kRowFloats = ASLOT + KP;       // split mode / debug dump: floats per row
+  static constexpr int kSolveWarps = SOLVE_WARPS;
+  static constexpr size_t kSolveSmem = sizeof(float) * SOLVE_WARPS * SOLVE_SMEM_PER_WARP;
+  static void (*kernel(bool imp))(const TcParams) { return imp ? als_solve_tc_kernel<true> : als_solve_tc_kernel<false>; }
+  static void (*solver(bool imp))(const SolveParams, const float*, int) {
+    return imp ? als_solve_packed_kernel<true> : als_solve_packed_kernel<false>;
+  }
+};
+
+}  // namespace TC_NS
 }  // namespace pio

@@ -19,7 +19,22 @@
 #include <vector>
 
 #include "als_kernels.cuh"
+// the tcgen05 half-step kernel; the header is parametrised by the role partition of its sixteen warps.  Measured at C2:
+// 2 gather + 5 converter warps + 2 solve teams (below) beats 1 + 2 + 3 teams on long rows AND on short rows (user side
+// 38 ms vs 86 ms: two converter warps cannot feed the MMAs), so only this partition is instantiated.
+#define TC_NS tc
+#define TC_NTEAM 2
+#define TC_NCONV 5
+#define TC_NGATHER 2
+#define TC_NSTAGE 7
+#define TC_NRAW 7
 #include "als_tc_kernel.cuh"
+#undef TC_NS
+#undef TC_NTEAM
+#undef TC_NCONV
+#undef TC_NGATHER
+#undef TC_NSTAGE
+#undef TC_NRAW
 #include "sort_scan.cuh"
 #include "topk.cuh"
 
@@ -666,6 +681,79 @@ static cudaError_t launch_solve_one(pio_als_handle* h, const SolveParams& p, int
   return cudaGetLastError();
 }
 
+// Gramians on tcgen05 (als_tc_kernel.cuh): persistent, one CTA per SM, rows assigned statically.  A = role partition.
+// Split mode (PIO_ALS_TC_SPLIT=1, off by default): the kernel only accumulates and stores the normal equations of a
+// tile of rows; a second kernel solves them with every warp of the SM.  Measured at C2: item side 15.0 vs 15.4 ms fused,
+// user side 39.7 vs 38.2 ms fused (the one-warp 64x64 Cholesky is latency-bound, ~50-70 k cycles per row, so twelve
+// solver warps per SM at 168 registers do not beat the fused ones overlapped with the MMAs).
+template <class A>
+static cudaError_t launch_tc(pio_als_handle* h, Side& dst, const SolveParams& p, bool imp, int nlight) {
+  cudaError_t e = cudaSuccess;
+  static bool attr_set[64] = {};
+  if (h->cfg.device < 64 && !attr_set[h->cfg.device]) {
+    if ((e = cudaFuncSetAttribute(A::kernel(true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A::kSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(A::kernel(false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A::kSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(A::solver(true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A::kSolveSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(A::solver(false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A::kSolveSmem)) != cudaSuccess) return e;
+    attr_set[h->cfg.device] = true;
+  }
+  typename A::Params tp;
+  tp.counter = h->d_counter;
+  tp.dbg = nullptr;
+  tp.timing = nullptr;
+  tp.out = nullptr;
+  tp.out_row0 = 0;
+  if (getenv("PIO_ALS_TC_TIMING")) {
+    if (!h->d_timing && (e = cudaMalloc((void**)&h->d_timing, (size_t)h->sm_count * 16 * 8 * sizeof(long long))) != cudaSuccess) return e;
+    cudaMemsetAsync(h->d_timing, 0, (size_t)h->sm_count * 16 * 8 * sizeof(long long), h->stream);
+    tp.timing = h->d_timing;
+  }
+  if (getenv("PIO_ALS_TC_DEBUG")) {
+    if (h->dbg_rows < (size_t)dst.R) {
+      if (h->d_dbg) cudaFree(h->d_dbg);
+      if ((e = cudaMalloc((void**)&h->d_dbg, (size_t)dst.R * A::kRowFloats * sizeof(float))) != cudaSuccess) return e;
+      h->dbg_rows = dst.R;
+    }
+    cudaMemsetAsync(h->d_dbg, 0, (size_t)dst.R * A::kRowFloats * sizeof(float), h->stream);
+    tp.dbg = h->d_dbg;
+  }
+  const int tile = h->tc_split ? TC_TILE_ROWS : nlight;
+  if (h->tc_split) {
+    const size_t need = (size_t)(nlight < tile ? nlight : tile);
+    if (h->tc_out_rows < need) {
+      if (h->tc_out) cudaFree(h->tc_out);
+      h->tc_out = nullptr;
+      h->tc_out_rows = 0;
+      if ((e = cudaMalloc((void**)&h->tc_out, need * A::kRowFloats * sizeof(float))) != cudaSuccess) return e;
+      h->tc_out_rows = need;
+    }
+  }
+  for (int t0 = p.row_begin; t0 < p.row_end; t0 += tile) {
+    SolveParams q = p;
+    q.row_begin = t0;
+    q.row_end = t0 + tile < p.row_end ? t0 + tile : p.row_end;
+    const int nrows = q.row_end - q.row_begin;
+    tp.sp = q;
+    tp.out = h->tc_split ? h->tc_out : nullptr;
+    tp.out_row0 = t0;
+    int grid = (nrows + A::kPerCta - 1) / A::kPerCta;
+    if (grid > h->sm_count) grid = h->sm_count;
+    A::kernel(imp)<<<grid, A::kThreads, A::kSmem, h->stream>>>(tp);
+    LAUNCHED(h);
+    ++h->st.solve_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (h->tc_split) {
+      int sgrid = (nrows + A::kSolveWarps - 1) / A::kSolveWarps;
+      if (sgrid > 4 * h->sm_count) sgrid = 4 * h->sm_count;
+      A::solver(imp)<<<sgrid, A::kSolveWarps * 32, A::kSolveSmem, h->stream>>>(q, h->tc_out, t0);
+      LAUNCHED(h);
+      ++h->st.solve_launches;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+  }
+  return e;
+}
+
 template <class Cfg>
 static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& src) {
   SolveParams p;
@@ -725,78 +813,8 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
     p.row_begin = dst.n_heavy;
     p.row_end = dst.n_active;
     if (dst.use_tc && Cfg::KP == 64) {
-      // Gramians on tcgen05 (als_tc_kernel.cuh): persistent, one CTA per SM, rows assigned statically.
-      // Split mode (PIO_ALS_TC_SPLIT=1, off by default): the kernel only accumulates and stores the normal equations of a
-      // tile of rows; a second kernel solves them with every warp of the SM.  Measured at C2: item side 15.0 vs 15.4 ms
-      // fused, user side 39.7 vs 38.2 ms fused (the one-warp 64x64 Cholesky is latency-bound, ~50-70 k cycles per row,
-      // so twelve solver warps per SM at 168 registers do not beat eight fused ones overlapped with the MMAs).
-      static bool attr_set[64] = {};
-      const size_t smem = sizeof(tc::Smem) + 1024;
-      const size_t ssmem = sizeof(float) * tc::SOLVE_WARPS * tc::SOLVE_SMEM_PER_WARP;
-      auto kern = imp ? tc::als_solve_tc_kernel<true> : tc::als_solve_tc_kernel<false>;
-      auto skern = imp ? tc::als_solve_packed_kernel<true> : tc::als_solve_packed_kernel<false>;
-      if (h->cfg.device < 64 && !attr_set[h->cfg.device]) {
-        if ((e = cudaFuncSetAttribute(tc::als_solve_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(tc::als_solve_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(tc::als_solve_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(tc::als_solve_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem)) != cudaSuccess) return e;
-        attr_set[h->cfg.device] = true;
-      }
-      tc::TcParams tp;
-      tp.counter = h->d_counter;
-      tp.dbg = nullptr;
-      tp.timing = nullptr;
-      tp.out = nullptr;
-      tp.out_row0 = 0;
-      if (getenv("PIO_ALS_TC_TIMING")) {
-        if (!h->d_timing && (e = cudaMalloc((void**)&h->d_timing, (size_t)h->sm_count * 16 * 8 * sizeof(long long))) != cudaSuccess) return e;
-        cudaMemsetAsync(h->d_timing, 0, (size_t)h->sm_count * 16 * 8 * sizeof(long long), h->stream);
-        tp.timing = h->d_timing;
-      }
-      if (getenv("PIO_ALS_TC_DEBUG")) {
-        if (h->dbg_rows < (size_t)dst.R) {
-          if (h->d_dbg) cudaFree(h->d_dbg);
-          if ((e = cudaMalloc((void**)&h->d_dbg, (size_t)dst.R * (tc::ASLOT + tc::KP) * sizeof(float))) != cudaSuccess) return e;
-          h->dbg_rows = dst.R;
-        }
-        cudaMemsetAsync(h->d_dbg, 0, (size_t)dst.R * (tc::ASLOT + tc::KP) * sizeof(float), h->stream);
-        tp.dbg = h->d_dbg;
-      }
-      const int per_cta = tc::NTEAM * tc::NSLOT;
-      const int tile = h->tc_split ? TC_TILE_ROWS : nlight;
-      if (h->tc_split) {
-        const size_t need = (size_t)(nlight < tile ? nlight : tile);
-        if (h->tc_out_rows < need) {
-          if (h->tc_out) cudaFree(h->tc_out);
-          h->tc_out = nullptr;
-          h->tc_out_rows = 0;
-          if ((e = cudaMalloc((void**)&h->tc_out, need * (tc::ASLOT + tc::KP) * sizeof(float))) != cudaSuccess) return e;
-          h->tc_out_rows = need;
-        }
-      }
-      for (int t0 = p.row_begin; t0 < p.row_end; t0 += tile) {
-        SolveParams q = p;
-        q.row_begin = t0;
-        q.row_end = t0 + tile < p.row_end ? t0 + tile : p.row_end;
-        const int nrows = q.row_end - q.row_begin;
-        tp.sp = q;
-        tp.out = h->tc_split ? h->tc_out : nullptr;
-        tp.out_row0 = t0;
-        int grid = (nrows + per_cta - 1) / per_cta;
-        if (grid > h->sm_count) grid = h->sm_count;
-        kern<<<grid, tc::NTHREADS, smem, h->stream>>>(tp);
-        LAUNCHED(h);
-        ++h->st.solve_launches;
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (h->tc_split) {
-          int sgrid = (nrows + tc::SOLVE_WARPS - 1) / tc::SOLVE_WARPS;
-          if (sgrid > 4 * h->sm_count) sgrid = 4 * h->sm_count;
-          skern<<<sgrid, tc::SOLVE_WARPS * 32, ssmem, h->stream>>>(q, h->tc_out, t0);
-          LAUNCHED(h);
-          ++h->st.solve_launches;
-          if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        }
-      }
+      e = launch_tc<tc::Api>(h, dst, p, imp, nlight);
+      if (e != cudaSuccess) return e;
     } else {
       const int grid = (nlight + Cfg::NG - 1) / Cfg::NG;
       e = imp ? launch_solve_one<Cfg, true, false>(h, p, grid, h->stream) : launch_solve_one<Cfg, false, false>(h, p, grid, h->stream);
