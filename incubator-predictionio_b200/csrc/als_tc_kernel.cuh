@@ -242,10 +242,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// hi part of the split: the top 10 mantissa bits by truncation (one LOP3 on the full-rate integer pipe; cvt.rna.tf32
+// goes through the quarter-rate conversion pipe, 48 per lane and stage).  x - hi is exact and has at most 13 significant
+// bits, so the split loses nothing; the tensor core's own truncation of lo costs 2^-21 relative, the dropped lo*lo
+// term 2^-20.
 __device__ __forceinline__ float tf32_round(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
 
 // shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): MN-major,
