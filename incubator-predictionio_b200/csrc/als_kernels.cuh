@@ -12,7 +12,7 @@
 //    NG rows of one CTA batch have near-equal length;
 //  * the upper triangle of the KPxKP Gramian is tiled in TBxTB register blocks, one block per
 //    thread, G = NB(NB+1)/2 threads ("group") per row; a CTA runs NG groups = NG rows at once
-//    (LIGHT) or NG slices of one very long row (HEAVY, reduced through shared memory);
+//    or NG parts of very long rows (work-list mode: the partial normal equations go to global memory);
 //  * gathered source rows are staged by cp.async (16 B per thread) into a 3-deep shared-memory
 //    ring; a short in-place pass scales them by sqrt(c1) (implicit) and accumulates b;
 //  * each warp then factorises one row's matrix with the rows held in registers
@@ -66,12 +66,12 @@ struct SolveCfg {
   static constexpr bool WARP_CHOL = KP <= 64;
   static constexpr int LM = WARP_CHOL ? 0 : KP * (KP + 1);  // cooperative Cholesky scratch
 
-  __host__ __device__ static constexpr int region0(bool heavy) {
-    return heavy ? (NSTAGE + 1) * STAGE + NG * SLOT
-                 : ((NSTAGE + 1) * STAGE > NG * SLOT ? (NSTAGE + 1) * STAGE : NG * SLOT);
+  // the Cholesky slots alias the (dead) staging ring and b partials
+  __host__ __device__ static constexpr int region0() {
+    return (NSTAGE + 1) * STAGE > NG * SLOT ? (NSTAGE + 1) * STAGE : NG * SLOT;
   }
-  __host__ __device__ static constexpr size_t smem_bytes(bool heavy) {
-    return sizeof(float) * (size_t)(region0(heavy) + NG * KP + NW * 2 * KP + NW * KP +
+  __host__ __device__ static constexpr size_t smem_bytes() {
+    return sizeof(float) * (size_t)(region0() + NG * KP + NW * 2 * KP + NW * KP +
                                     NSTAGE * ROWS + LM) +
            sizeof(long long) * 2 * NG + sizeof(int) * NG + 16;
   }
@@ -371,20 +371,19 @@ __device__ void chol_solve_cta(const float* slot, const float* bvec, const float
 // ------------------------------------------------------------------------------------------
 // The half-step kernel.
 // ------------------------------------------------------------------------------------------
-template <class Cfg, bool IMPLICIT, bool HEAVY>
-__global__ void __launch_bounds__(Cfg::NT, (HEAVY || !Cfg::WARP_CHOL) ? 1 : 2)
+template <class Cfg, bool IMPLICIT>
+__global__ void __launch_bounds__(Cfg::NT, Cfg::WARP_CHOL ? 2 : 1)
 als_solve_kernel(const SolveParams p) {
   constexpr int KP = Cfg::KP, TB = Cfg::TB, NB = Cfg::NB, G = Cfg::G, NG = Cfg::NG, CH = Cfg::CH;
   constexpr int NT = Cfg::NT, NW = Cfg::NW, ROWS = Cfg::ROWS, F4ROW = Cfg::F4ROW;
   constexpr int STAGE = Cfg::STAGE, STAGE_F4 = Cfg::STAGE_F4, NF = Cfg::NF, NSTAGE = Cfg::NSTAGE;
   constexpr int BLK = Cfg::BLK, SLOT = Cfg::SLOT;
-  constexpr int FLUSH = 64;  // HEAVY: chunks between register->smem flushes (two-level summation)
 
   extern __shared__ __align__(16) float smem[];
   float* stage = smem;
   float* bpart = stage + NSTAGE * STAGE;
-  float* slots = HEAVY ? bpart + STAGE : smem;
-  float* bvec = smem + Cfg::region0(HEAVY);
+  float* slots = smem;   // aliases the ring: written only after the last chunk has been consumed
+  float* bvec = smem + Cfg::region0();
   float* colbuf = bvec + NG * KP;
   float* dinvb = colbuf + NW * 2 * KP;
   float* mval = dinvb + NW * KP;
@@ -406,7 +405,7 @@ als_solve_kernel(const SolveParams p) {
   }
 
   if (tid < NG) {
-    if (!HEAVY && p.partial) {
+    if (p.partial) {
       const int item = blockIdx.x * NG + tid;
       if (item < p.n_items) {
         segb[tid] = p.wl_beg[item];
@@ -417,7 +416,7 @@ als_solve_kernel(const SolveParams p) {
         sege[tid] = 0;
         srow[tid] = -1;
       }
-    } else if (!HEAVY) {
+    } else {
       const int r = p.row_begin + blockIdx.x * NG + tid;
       if (r < p.row_end) {
         segb[tid] = p.ptr[r];
@@ -428,25 +427,10 @@ als_solve_kernel(const SolveParams p) {
         sege[tid] = 0;
         srow[tid] = -1;
       }
-    } else {
-      const int r = p.row_begin + blockIdx.x;
-      const long long b = p.ptr[r], e = p.ptr[r + 1];
-      const long long d = e - b;
-      long long L = (d + NG - 1) / NG;
-      L = (L + CH - 1) / CH * CH;
-      long long sb = b + (long long)tid * L;
-      if (sb > e) sb = e;
-      long long se = sb + L;
-      if (se > e) se = e;
-      segb[tid] = sb;
-      sege[tid] = se;
-      srow[tid] = r;
     }
   }
-  // zero the b partials (and the slots when they do not alias the ring)
+  // zero the b partials
   for (int o = tid; o < STAGE; o += NT) bpart[o] = 0.f;
-  if (HEAVY)
-    for (int o = tid; o < NG * SLOT; o += NT) slots[o] = 0.f;
   __syncthreads();
 
   long long maxlen = 0;
@@ -580,40 +564,22 @@ als_solve_kernel(const SolveParams p) {
             for (int b = 0; b < TB; ++b) acc[a][b] = fmaf(P[a], Q[b], acc[a][b]);
         }
       }
-      if (HEAVY && ((c + 1) % FLUSH == 0)) {
-#pragma unroll
-        for (int a = 0; a < TB; ++a)
-#pragma unroll
-          for (int b = 0; b < TB; ++b) {
-            myslot[a * TB + b] += acc[a][b];
-            acc[a][b] = 0.f;
-          }
-      }
     }
   }
   cp_async_wait<0>();
   __syncthreads();
 
   // ---- b: fixed-order reduction of the per-staged-row partials ----------------------------
-  if (!HEAVY) {
-    for (int o = tid; o < NG * KP; o += NT) {
-      const int gg = o / KP, col = o % KP;
-      const int pos = f4slot<TB, NB>(col >> 2) * 4 + (col & 3);
-      float s = 0.f;
+  for (int o = tid; o < NG * KP; o += NT) {
+    const int gg = o / KP, col = o % KP;
+    const int pos = f4slot<TB, NB>(col >> 2) * 4 + (col & 3);
+    float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < CH; ++i) s += bpart[(gg * CH + i) * KP + pos];
-      bvec[o] = s;
-    }
-  } else {
-    for (int col = tid; col < KP; col += NT) {
-      const int pos = f4slot<TB, NB>(col >> 2) * 4 + (col & 3);
-      float s = 0.f;
-      for (int q = 0; q < ROWS; ++q) s += bpart[q * KP + pos];
-      bvec[col] = s;
-    }
+    for (int i = 0; i < CH; ++i) s += bpart[(gg * CH + i) * KP + pos];
+    bvec[o] = s;
   }
-  __syncthreads();  // ring + bpart are dead from here on (LIGHT: slots alias them)
-  if (!HEAVY && p.partial) {
+  __syncthreads();  // ring + bpart are dead from here on (the slots alias them)
+  if (p.partial) {
     // part of a long row: emit the partial normal equations; als_finish_kernel sums the parts and solves
     if (worker && srow[g] >= 0) {
       float* out = p.partial + (size_t)srow[g] * (SLOT + KP) + bid * BLK;
@@ -633,24 +599,12 @@ als_solve_kernel(const SolveParams p) {
 #pragma unroll
     for (int a = 0; a < TB; ++a)
 #pragma unroll
-      for (int b = 0; b < TB; ++b) {
-        if (HEAVY) myslot[a * TB + b] += acc[a][b];
-        else myslot[a * TB + b] = acc[a][b];
-      }
+      for (int b = 0; b < TB; ++b) myslot[a * TB + b] = acc[a][b];
   }
   __syncthreads();
-  if (HEAVY) {
-    for (int o = tid; o < SLOT; o += NT) {
-      float s = slots[o];
-#pragma unroll 1
-      for (int q = 1; q < NG; ++q) s += slots[q * SLOT + o];
-      slots[o] = s;
-    }
-    __syncthreads();
-  }
 
   // ---- Cholesky + triangular solves ---------------------------------------------------------
-  constexpr int NMAT = HEAVY ? 1 : NG;
+  constexpr int NMAT = NG;
   if (Cfg::WARP_CHOL) {
     const int w = tid >> 5;
     for (int m = w; m < NMAT; m += NW) {

@@ -351,8 +351,6 @@ struct pio_als_handle {
   pio_als_config cfg;
   int KP = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;   // heavy-row solve kernel runs here, concurrently with the light one
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   Side U, I;
   float* yty = nullptr;
   double* gram_partial = nullptr;
@@ -664,12 +662,12 @@ static int init_hash(pio_als_handle* h) {
 }
 
 // ---- solve dispatch ---------------------------------------------------------------------------
-template <class Cfg, bool IMPLICIT, bool HEAVY>
+template <class Cfg, bool IMPLICIT>
 static cudaError_t launch_solve_one(pio_als_handle* h, const SolveParams& p, int grid, cudaStream_t st) {
   static bool attr_set[64] = {};
   int dev = h->cfg.device;
-  auto kern = als_solve_kernel<Cfg, IMPLICIT, HEAVY>;
-  const size_t smem = Cfg::smem_bytes(HEAVY);
+  auto kern = als_solve_kernel<Cfg, IMPLICIT>;
+  const size_t smem = Cfg::smem_bytes();
   if (dev < 64 && !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -788,7 +786,7 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
     pp.row_begin = 0;
     pp.row_end = dst.n_heavy;
     const int grid = (dst.n_parts + Cfg::NG - 1) / Cfg::NG;
-    e = imp ? launch_solve_one<Cfg, true, false>(h, pp, grid, h->stream) : launch_solve_one<Cfg, false, false>(h, pp, grid, h->stream);
+    e = imp ? launch_solve_one<Cfg, true>(h, pp, grid, h->stream) : launch_solve_one<Cfg, false>(h, pp, grid, h->stream);
     if (e != cudaSuccess) return e;
     // finish: sum the parts of every heavy row in fixed order, then Cholesky
     {
@@ -817,7 +815,7 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
       if (e != cudaSuccess) return e;
     } else {
       const int grid = (nlight + Cfg::NG - 1) / Cfg::NG;
-      e = imp ? launch_solve_one<Cfg, true, false>(h, p, grid, h->stream) : launch_solve_one<Cfg, false, false>(h, p, grid, h->stream);
+      e = imp ? launch_solve_one<Cfg, true>(h, p, grid, h->stream) : launch_solve_one<Cfg, false>(h, p, grid, h->stream);
       if (e != cudaSuccess) return e;
     }
   }
@@ -927,10 +925,7 @@ static int create_common(pio_als_handle* h) {
   h->sm_count = pr.multiProcessorCount;
   h->st.sm_count = pr.multiProcessorCount;
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaSetDevice");
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
     return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaStreamCreate");
   // keep freed blocks in the pool (ingest allocates and frees multi-GB scratch repeatedly)
   cudaMemPool_t pool;
@@ -1011,9 +1006,6 @@ void pio_als_destroy(pio_als_handle* h) {
       cudaEventDestroy(e.b);
     }
     if (h->comm) nccl_api().CommDestroy(h->comm);
-    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
     cudaStreamDestroy(h->stream);
   }
   delete h;
