@@ -105,9 +105,8 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback"
 
 
-def cpu_baseline_sample(nu, ni, nnz, k, implicit, target_s=12.0, d_coo=None):
-    """Time the oracle (CPU restatement of the MLlib algorithm) on a strided sample of destination
-    rows of the SAME workload and scale to one full iteration."""
+def cpu_baseline_prepare(nu, ni, nnz, k, implicit, d_coo=None):
+    """Load the oracle, generate (or take) the workload's ratings and build both CSR orientations - done once."""
     from oracle import als_oracle as o
     from pio_b200 import synth
     try:  # use a host-native build for the timed baseline when gcc is on the box
@@ -121,43 +120,57 @@ def cpu_baseline_sample(nu, ni, nnz, k, implicit, target_s=12.0, d_coo=None):
             o._lib.oracle_num_threads.restype = ctypes.c_int
     except Exception:
         pass
-    cores = o.num_threads()
     if d_coo is not None:
         u, i, r = d_coo
     else:
         u, i, r = synth.synth_ratings(nu, ni, nnz, seed=SEED, implicit=implicit)
-    if implicit:
-        pass  # duplicates kept as separate ratings for the CPU sample (same arithmetic per rating)
+    # duplicates are kept as separate ratings for the CPU sample (same arithmetic per rating)
     uptr, ucol, uval = o.csr_build(nu, u, i, r)
     iptr, icol, ival = o.csr_build(ni, i, u, r)
     uf = synth.synth_init_factors(min(nu, 1 << 16), k, SEED, 0)
     uf = np.ascontiguousarray(np.resize(uf, (nu, k)))
     itf = synth.synth_init_factors(min(ni, 1 << 16), k, SEED, 1)
     itf = np.ascontiguousarray(np.resize(itf, (ni, k)))
-    yty = o.gram(uf) if implicit else None
+    prep = {"o": o, "nu": nu, "ni": ni, "implicit": implicit, "user": (uptr, ucol, uval), "item": (iptr, icol, ival),
+            "uf": uf, "itf": itf, "yty": o.gram(uf) if implicit else None, "cores": o.num_threads()}
 
-    def timed(ptr, col, val, src, dst, n, stride):
+    def timed(side, stride):
+        ptr, col, val = prep[side]
+        src, dst, n = (itf, uf.copy(), nu) if side == "user" else (uf, itf.copy(), ni)
         t0 = time.perf_counter()
-        o.half_step(ptr, col, val, src, dst, LAMBDA, implicit, ALPHA, yty, 0, n, stride)
+        o.half_step(ptr, col, val, src, dst, LAMBDA, implicit, ALPHA, prep["yty"], 0, n, stride)
         return time.perf_counter() - t0
 
-    # pilot with a large stride, then choose strides so each half takes ~target_s/2
+    prep["timed"] = timed
+    # pilot with a large stride: seconds per destination row of each side
     su, si = max(1, nu // 2000), max(1, ni // 500)
-    tu, ti = timed(uptr, ucol, uval, itf, uf.copy(), nu, su), timed(iptr, icol, ival, uf, itf.copy(), ni, si)
+    prep["pilot"] = (su, timed("user", su), si, timed("item", si))
+    return prep
+
+
+def cpu_baseline_run(prep, target_s=12.0):
+    """Time the oracle (CPU restatement of the MLlib algorithm) on a strided sample of destination rows of the SAME
+    workload, sized to about target_s seconds, and scale to one full iteration."""
+    o, timed = prep["o"], prep["timed"]
+    su, tu, si, ti = prep["pilot"]
     su2 = max(1, int(su * tu / (target_s / 2)))
     si2 = max(1, int(si * ti / (target_s / 2)))
-    tu = timed(uptr, ucol, uval, itf, uf.copy(), nu, su2)
-    ti = timed(iptr, icol, ival, uf, itf.copy(), ni, si2)
+    tu = timed("user", su2)
+    ti = timed("item", si2)
     t_gram = 0.0
-    if implicit:
+    if prep["implicit"]:
         t0 = time.perf_counter()
-        o.gram(uf)
-        o.gram(itf)
+        o.gram(prep["uf"])
+        o.gram(prep["itf"])
         t_gram = time.perf_counter() - t0
     iter_s = tu * su2 + ti * si2 + t_gram
-    return {"value": 1.0 / iter_s, "unit": "iterations/s", "cores": cores, "kind": "port",
+    return {"value": 1.0 / iter_s, "unit": "iterations/s", "cores": prep["cores"], "kind": "port",
             "sample": f"every {su2}th user row + every {si2}th item row of the full workload "
                       f"({tu + ti:.1f}s timed), scaled to one iteration; C/OpenMP restatement of MLlib ALS (not Spark)"}
+
+
+def cpu_baseline_sample(nu, ni, nnz, k, implicit, target_s=12.0, d_coo=None):
+    return cpu_baseline_run(cpu_baseline_prepare(nu, ni, nnz, k, implicit, d_coo=d_coo), target_s)
 
 
 def main():
@@ -185,10 +198,15 @@ def main():
         if rank != 0:
             return
         import pio_b200  # noqa: F401
+        # one step = one bounded sample of the workload (same ratings, strided destination rows); the ratings and
+        # both CSR orientations are built once; the per-step budget shrinks with the step count so that the whole
+        # run stays within a few minutes
+        prep = cpu_baseline_prepare(nu, ni, nnz, k, implicit)
+        per_step = min(16.0, max(2.0, 90.0 / (args.warmup + args.steps)))
         vals = []
         cb = None
         for s in range(args.warmup + args.steps):
-            cb = cpu_baseline_sample(nu, ni, nnz, k, implicit, target_s=16.0)
+            cb = cpu_baseline_run(prep, target_s=per_step)
             if s >= args.warmup:
                 vals.append(cb["value"])
         v = float(np.mean(vals))
