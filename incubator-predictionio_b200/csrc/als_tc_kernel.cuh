@@ -145,7 +145,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) mbar_timeout(bar, parity);   // ~2 s
+    if (clock64() - t0 > 16000000000ll) mbar_timeout(bar, parity);   // ~8 s (a half-step takes tens of ms; tools like compute-sanitizer slow the kernel ~100x)
   }
 }
 __device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity) {
