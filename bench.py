@@ -327,15 +327,18 @@ def main():
                   "item": 2 * nnz_eff * (k * (k + 1) + 2 * k) / 2 + nia * (k ** 3 / 3 + 2 * k * k)}
     side_bytes = {"user": 8 * nnz_eff + 4 * nua * k + 4 * nia * k, "item": 8 * nnz_eff + 4 * nia * k + 4 * nua * k}
     side_ms = {"user": ph["user_solve_ms"] / args.steps, "item": ph["item_solve_ms"] / args.steps}
-    side_tc = {"user": ph["user_side_tensor_core"], "item": ph["item_side_tensor_core"]}
+    side_kernel = {"user": ph["user_kernel"], "item": ph["item_kernel"]}
+    side_tc = {sd: side_kernel[sd] != "fp32" for sd in side_kernel}   # Gramian on tensor cores (tcgen05 or mma.sync)
+    kernel_names = {"fp32": "als_solve_kernel (gather + FP32 Gramian + warp Cholesky)",
+                    "tcgen05": "tc::als_solve_tc_kernel (tcgen05 split-TF32 Gramian + warp Cholesky)",
+                    "mma": "mm::als_solve_mma_kernel (one warp per row: mma.sync 3xTF32 Gramian + warp Cholesky)"}
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
     tf32_peak = bf16_peak / 2.0
 
     def side_obj(sd):
         tf = side_flops[sd] / (side_ms[sd] / 1e3) / 1e12 / max(world, 1)
         gb = side_bytes[sd] / (side_ms[sd] / 1e3) / 1e9 / max(world, 1)
-        o = {"kernel": ("tc::als_solve_tc_kernel (tcgen05 split-TF32 Gramian + warp Cholesky)" if side_tc[sd] else
-                        "als_solve_kernel (gather + FP32 Gramian + warp Cholesky)") + f", {sd} half-step",
+        o = {"kernel": kernel_names[side_kernel[sd]] + f", {sd} half-step",
              "ms_per_launch": side_ms[sd], "algorithmic_flops": side_flops[sd], "algorithmic_bytes": side_bytes[sd],
              "achieved_tflops": tf, "achieved_gbs": gb, "frac_of_fp32_fma_peak": tf / fp32_peak,
              "frac_of_hbm_peak": gb / hbm_peak}
@@ -352,7 +355,8 @@ def main():
         "achieved": d["achieved_tflops"], "peak": fp32_peak if not side_tc[dom] else tf32_peak, "unit": "TFLOP/s",
         "frac": d["achieved_tflops"] / (fp32_peak if not side_tc[dom] else tf32_peak),
         "peak_source": ("nominal 148 SM x 128 FFMA lanes x 2 x 1.965 GHz (CUDA-core FP32; MEASURED_PEAKS.json has no "
-                        "FP32 entry)") if not side_tc[dom] else f"{peak_src} dense bf16 / 2 (tf32)",
+                        "FP32 entry)") if not side_tc[dom] else
+                       f"{peak_src} dense bf16 / 2 (tf32 MMA rate; fp32-class products take three MMAs each)",
         "ms_per_launch": d["ms_per_launch"],
         "traffic": traffic_from_profiles(args.workload),
         "traffic_unit": "dram bytes of this launch, from the committed ncu --set full capture (profiles/traffic.json)",

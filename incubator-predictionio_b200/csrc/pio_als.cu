@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "als_kernels.cuh"
+#include "als_mma_kernel.cuh"
 // the tcgen05 half-step kernel; the header is parametrised by the role partition of its sixteen warps.  Measured at C2:
 // 2 gather + 5 converter warps + 2 solve teams (below) beats 1 + 2 + 3 teams on long rows AND on short rows (user side
 // 38 ms vs 86 ms: two converter warps cannot feed the MMAs), so only this partition is instantiated.
@@ -362,6 +363,7 @@ struct pio_als_handle {
   float* d_dbg = nullptr;     // PIO_ALS_TC_DEBUG=1: A/b dump of the last tensor-core half-step
   size_t dbg_rows = 0;
   bool use_tc = false;        // rank in 33..64 and PIO_ALS_TC != 0
+  bool use_mma = true;        // PIO_ALS_MMA=0: FP32 kernel instead of the mma.sync kernel for short rows of rank 33..64
   bool tc_split = false;      // PIO_ALS_TC_SPLIT=1: the tensor-core kernel only accumulates, a second kernel solves (measured: no gain)
   float* tc_out = nullptr;    // split mode: normal equations of one tile of rows ([rows][ASLOT + KP])
   size_t tc_out_rows = 0;
@@ -466,7 +468,9 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
   // kernel choice from global numbers only (ratings after dedup / rows of this side), so that every rank of a sharded
   // run and the single-GPU run take the same path for the same row
   row.use_tc = h->use_tc && h->KP == 64 && row.n > 0 && (double)nnz / (double)row.n >= h->tc_min_deg;
-  row.heavy_t = row.use_tc ? HEAVY_T_TC : HEAVY_T;
+  // one warp (mma kernel) or one accumulator slot (tcgen05 kernel) carries a whole row: rows up to 8192 ratings stay
+  // whole on those paths; the FP32 kernel (other ranks) shares a CTA between NG rows and cuts at 4096
+  row.heavy_t = (row.use_tc || (h->KP == 64 && h->use_mma)) ? HEAVY_T_TC : HEAVY_T;
   local_rows_kernel<<<nblk(row.R + 1, 256), 256, 0, st>>>(ptr_full, rk * row.R, row.R, be[0], row.inv, row.deg,
                                                            row.npos, h->cfg.implicit_prefs, row.ptr, row.nreg,
                                                            h->d_counts, row.heavy_t);
@@ -813,6 +817,20 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
     if (dst.use_tc && Cfg::KP == 64) {
       e = launch_tc<tc::Api>(h, dst, p, imp, nlight);
       if (e != cudaSuccess) return e;
+    } else if (Cfg::KP == 64 && h->use_mma) {
+      // short rows of rank 33..64: one warp per row, mma.sync Gramian (als_mma_kernel.cuh)
+      static bool mattr[64] = {};
+      auto mk = imp ? mm::als_solve_mma_kernel<true> : mm::als_solve_mma_kernel<false>;
+      if (h->cfg.device < 64 && !mattr[h->cfg.device]) {
+        if ((e = cudaFuncSetAttribute(mm::als_solve_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mm::SMEM_BYTES)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(mm::als_solve_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mm::SMEM_BYTES)) != cudaSuccess) return e;
+        mattr[h->cfg.device] = true;
+      }
+      const int grid = (nlight + mm::WARPS - 1) / mm::WARPS;
+      mk<<<grid, mm::NT, mm::SMEM_BYTES, h->stream>>>(p);
+      LAUNCHED(h);
+      ++h->st.solve_launches;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
     } else {
       const int grid = (nlight + Cfg::NG - 1) / Cfg::NG;
       e = imp ? launch_solve_one<Cfg, true>(h, p, grid, h->stream) : launch_solve_one<Cfg, false>(h, p, grid, h->stream);
@@ -937,12 +955,18 @@ static int create_common(pio_als_handle* h) {
   {
     // tensor-core Gramian (als_tc_kernel.cuh): parity-green but not yet faster than the FP32 kernel -> opt-in
     const char* env = getenv("PIO_ALS_TC");
-    // default: sides whose rows average >= 256 ratings (the item side of the headline workload) accumulate their
-    // Gramians on tcgen05; PIO_ALS_TC=0 disables it, PIO_ALS_TC=1 forces it for every side (PIO_ALS_TC_MIN_DEG overrides)
+    // rank 33..64 kernel selection for the rows below the heavy-row threshold.  Default: sides whose rows average >= 256
+    // ratings (the item side of the headline workload) accumulate their Gramians on tcgen05, every other side runs the
+    // one-warp-per-row mma.sync kernel.  Measured at C2: item side 15.0 ms (tcgen05) vs 13.7 ms (mma.sync), but the
+    // tcgen05 accumulator is the more accurate one on rows of thousands of ratings (mma.sync adds with truncation inside
+    // the tensor core: 1.1e-4 vs < 1e-4 against the oracle on the 10 000-ratings-per-row test), so accuracy decides.
+    // PIO_ALS_TC=0: no tcgen05 side; PIO_ALS_TC=1: every side; PIO_ALS_TC_MIN_DEG moves the threshold; PIO_ALS_MMA=0:
+    // FP32 CUDA-core kernel instead of mma.sync.
     h->use_tc = h->KP == 64 && !(env && env[0] == '0');
     h->tc_min_deg = (env && env[0] == '1') ? 0.0 : 256.0;
     if (const char* md = getenv("PIO_ALS_TC_MIN_DEG")) h->tc_min_deg = atof(md);
     if (const char* sp = getenv("PIO_ALS_TC_SPLIT")) h->tc_split = sp[0] == '1';
+    if (const char* mm_ = getenv("PIO_ALS_MMA")) h->use_mma = mm_[0] != '0';
   }
   h->gram_blocks = 2 * h->sm_count;
   if (cudaMallocAsync((void**)&h->yty, sizeof(float) * h->KP * h->KP, h->stream) != cudaSuccess ||
@@ -1148,8 +1172,10 @@ int pio_als_get_phase_ms(pio_als_handle* h, double out[8]) {
   if (!h || !out) return PIO_ALS_ERR_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   for (int i = 0; i < 8; ++i) out[i] = h->phase_ms[i];
-  out[4] = h->I.use_tc ? 1.0 : 0.0;
-  out[5] = h->U.use_tc ? 1.0 : 0.0;
+  // kernel of the rows below the heavy-row threshold: 0 = FP32 (als_solve_kernel), 1 = tcgen05, 2 = mma.sync
+  const bool mma = h->KP == 64 && h->use_mma;
+  out[4] = h->I.use_tc ? 1.0 : (mma ? 2.0 : 0.0);
+  out[5] = h->U.use_tc ? 1.0 : (mma ? 2.0 : 0.0);
   return PIO_ALS_OK;
 }
 

@@ -33,6 +33,9 @@ EXPORTED_SYMBOLS = [
 ]
 
 
+_KERNEL_NAMES = {0: "fp32", 1: "tcgen05", 2: "mma"}
+
+
 class NativeError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"pio_als error {code}: {msg}")
@@ -265,7 +268,8 @@ class NativeALS:
         out = (C.c_double * 8)()
         self._check(lib().pio_als_get_phase_ms(self._h, out))
         return {"item_solve_ms": out[0], "user_solve_ms": out[1], "gram_ms": out[2], "comm_ms": out[3],
-                "item_side_tensor_core": bool(out[4]), "user_side_tensor_core": bool(out[5]), "iterations": int(out[6])}
+                "item_kernel": _KERNEL_NAMES[int(out[4])], "user_kernel": _KERNEL_NAMES[int(out[5])],
+                "iterations": int(out[6])}
 
 
 def synth_ratings_device(device, n_users, n_items, nnz, seed, implicit, start, d_user, d_item, d_rating):

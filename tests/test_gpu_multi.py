@@ -29,8 +29,13 @@ WORKER = textwrap.dedent("""
             t = torch.tensor(list(native.nccl_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(t, 0)
         return bytes(t.cpu().tolist())
-    for (rk, implicit, nu, ni, nnz) in ((64, True, 6000, 900, 150000), (10, False, 3000, 500, 40000),
-                                        (64, True, 20000, 30, 300000)):
+    # (rank, implicit, users, items, ratings, PIO_ALS_TC): rank 64 runs the mma.sync kernel, plus the tcgen05 kernel on
+    # sides with long rows unless PIO_ALS_TC=0; the last two cases have heavy item rows (parts + finish kernel)
+    for (rk, implicit, nu, ni, nnz, tc) in ((64, True, 6000, 900, 150000, ""), (10, False, 3000, 500, 40000, ""),
+                                            (64, True, 20000, 30, 300000, "0"), (64, True, 20000, 30, 300000, "")):
+        os.environ.pop("PIO_ALS_TC", None)
+        if tc:
+            os.environ["PIO_ALS_TC"] = tc
         u, i, r = synth.synth_ratings(nu, ni, nnz, seed=3, implicit=implicit)
         u0 = synth.synth_init_factors(nu, rk, 5, 0)
         m = native.NativeALS(rk, nu, ni, lam=0.01, implicit=implicit, device=rank, world_size=world, world_rank=rank,

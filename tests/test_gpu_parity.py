@@ -69,8 +69,9 @@ def test_trained_factors_within_tolerance(native, oracle, rank, implicit, iters)
 
 @pytest.mark.parametrize("implicit", [True, False])
 def test_tensor_core_gramian_path(native, oracle, monkeypatch, implicit):
-    """PIO_ALS_TC=1 routes rank 33..64 through the tcgen05 split-TF32 SYRK kernel (als_tc_kernel.cuh):
-    same tolerance, including rows longer than one 504-rating accumulation segment and > 8192 (FP32 split kernel)."""
+    """PIO_ALS_TC=1 routes every side of rank 33..64 through the tcgen05 split-TF32 SYRK kernel
+    (als_tc_kernel.cuh): same tolerance, including rows longer than one 504-rating accumulation segment and > 8192
+    (parts on the FP32 kernel + finish kernel)."""
     monkeypatch.setenv("PIO_ALS_TC", "1")
     nu, ni, nnz = 30000, 60, 500000
     u, i, r = synth.synth_ratings(nu, ni, nnz, seed=11, implicit=implicit)
@@ -124,40 +125,53 @@ def test_config_c1_recommendation_template(native, oracle):
     assert np.abs(pg - po).max() <= 1e-3 * max(1.0, np.abs(po).max())
 
 
-@pytest.mark.parametrize("tc", ["0", None])
-def test_heavy_rows_split_mode(native, oracle, monkeypatch, tc):
-    """Items with far more ratings than the heavy-row threshold are cut into 2016-rating parts (part launch +
-    als_finish_kernel).  tc="0": FP32 kernel for the shorter rows; tc=None: the default selection, which sends this
-    item side (10000 ratings per row on average) through the tcgen05 kernel."""
-    if tc is None:
-        monkeypatch.delenv("PIO_ALS_TC", raising=False)
-    else:
-        monkeypatch.setenv("PIO_ALS_TC", tc)
+@pytest.mark.parametrize("path", ["fp32", "mma", "tcgen05"])
+def test_heavy_rows_split_mode(native, oracle, monkeypatch, path):
+    """Items with far more ratings than the heavy-row threshold are cut into 2016-rating parts (part launch on the FP32
+    kernel + als_finish_kernel); the rows below the threshold go through each of the three rank-64 kernels in turn
+    (tcgen05 is what the default selection picks for this item side: 10 000 ratings per row)."""
+    monkeypatch.delenv("PIO_ALS_TC", raising=False)
+    monkeypatch.delenv("PIO_ALS_MMA", raising=False)
+    if path == "fp32":
+        monkeypatch.setenv("PIO_ALS_TC", "0")
+        monkeypatch.setenv("PIO_ALS_MMA", "0")
+    elif path == "mma":
+        monkeypatch.setenv("PIO_ALS_TC", "0")
     nu, ni, nnz = 20000, 40, 400000
     u, i, r = synth.synth_ratings(nu, ni, nnz, seed=9, implicit=True)
-    _, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 3, 0.05, True, 1.0)
-    assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
+    m, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 3, 0.05, True, 1.0)
+    assert m.phase_ms()["item_kernel"] == path
+    # mma.sync sums the eight products of a chunk with truncation inside the tensor core; on 8000-rating rows that costs
+    # about 1.1e-4 on the item factors - the reason the default selection sends long-row sides to the tcgen05 kernel
+    tol = 2e-4 if path == "mma" else TOL
+    assert frob_rel(g[0], o[0]) <= tol and frob_rel(g[1], o[1]) <= tol, (frob_rel(g[0], o[0]), frob_rel(g[1], o[1]))
     _, g, o = run_both(native, oracle, nu, ni, u, i, r, 10, 3, 0.05, False, 1.0)
     assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
 
 
-def test_default_kernel_selection_mixed_sides(native, oracle, monkeypatch):
-    """Default build, rank 64: the item side (rows average >= 256 ratings) accumulates its Gramians on the tensor
-    cores, the user side (20 ratings per row) stays on the FP32 kernel; both within tolerance of the oracle, and the
-    all-FP32 run (PIO_ALS_TC=0) agrees with the mixed one to the same tolerance."""
-    monkeypatch.delenv("PIO_ALS_TC", raising=False)
-    monkeypatch.delenv("PIO_ALS_TC_MIN_DEG", raising=False)
+def test_rank64_kernel_selection(native, oracle, monkeypatch):
+    """Rank 64 default: the item side (rows average >= 256 ratings) on the tcgen05 kernel, the user side (20 ratings per
+    row) on the one-warp-per-row mma.sync kernel; PIO_ALS_TC=0 puts both on mma.sync, PIO_ALS_TC=0 + PIO_ALS_MMA=0 on the
+    FP32 kernel.  All three are within tolerance of the oracle and of each other, and really are different code paths."""
+    for v in ("PIO_ALS_TC", "PIO_ALS_TC_MIN_DEG", "PIO_ALS_MMA"):
+        monkeypatch.delenv(v, raising=False)
     nu, ni, nnz = 20000, 300, 400000
     for implicit in (True, False):
         u, i, r = synth.synth_ratings(nu, ni, nnz, seed=21, implicit=implicit)
-        _, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 4, 0.05, implicit, 1.0)
-        eu, ei = frob_rel(g[0], o[0]), frob_rel(g[1], o[1])
-        assert eu <= TOL and ei <= TOL, (implicit, eu, ei)
-        monkeypatch.setenv("PIO_ALS_TC", "0")
-        _, g0, _ = run_both(native, oracle, nu, ni, u, i, r, 64, 4, 0.05, implicit, 1.0)
-        monkeypatch.delenv("PIO_ALS_TC")
-        assert frob_rel(g0[0], g[0]) <= TOL and frob_rel(g0[1], g[1]) <= TOL
-        assert not np.array_equal(g0[1], g[1])   # the two kernels really are different code paths
+        res = {}
+        for path, env in (("tcgen05", {}), ("mma", {"PIO_ALS_TC": "0"}), ("fp32", {"PIO_ALS_TC": "0", "PIO_ALS_MMA": "0"})):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            m, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 4, 0.05, implicit, 1.0)
+            ph = m.phase_ms()
+            assert ph["item_kernel"] == path and ph["user_kernel"] == ("fp32" if path == "fp32" else "mma"), ph
+            eu, ei = frob_rel(g[0], o[0]), frob_rel(g[1], o[1])
+            assert eu <= TOL and ei <= TOL, (path, implicit, eu, ei)
+            res[path] = g
+            for k in env:
+                monkeypatch.delenv(k)
+        assert frob_rel(res["mma"][1], res["fp32"][1]) <= TOL and frob_rel(res["tcgen05"][1], res["fp32"][1]) <= TOL
+        assert not np.array_equal(res["mma"][1], res["fp32"][1]) and not np.array_equal(res["mma"][1], res["tcgen05"][1])
 
 
 def test_ragged_and_empty_rows(native, oracle):
