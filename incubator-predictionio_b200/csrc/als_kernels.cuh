@@ -16,10 +16,12 @@
 //  * gathered source rows are staged by cp.async (16 B per thread) into a 3-deep shared-memory
 //    ring; a short in-place pass scales them by sqrt(c1) (implicit) and accumulates b;
 //  * each warp then factorises one row's matrix with the rows held in registers
-//    (lane l owns rows l and N-1-l), pivots broadcast by shuffle, columns through shared memory;
+//    (lane l owns rows l and N/2+l), pivots broadcast by shuffle, columns through shared memory;
 //    forward substitution is fused into the factorisation, back substitution reads L from smem.
-// FP32 throughout the Gramian (the FMA pipe is the binding roofline at rank >= 32);
-// YtY is accumulated in fp64 by gram_partial_kernel.
+// FP32 FFMA throughout the Gramian: this kernel serves the ranks outside 33..64 and the parts of very long rows of
+// every rank; for rank 33..64 the tensor-core kernels (als_mma_kernel.cuh, als_tc_kernel.cuh) take the rows up to 8192
+// ratings because an 8x8 register block is shared-memory-bound by construction.  The warp Cholesky
+// below (chol_solve_warp) is shared by all three kernels.  YtY is accumulated in fp64 by gram_partial_kernel.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
