@@ -112,6 +112,25 @@ def test_low_rank_recovery_cases(native, oracle):
         assert abs(v - vo) <= 1e-3 * max(1.0, abs(vo)), (name, v, vo)
 
 
+def test_cuda_path_matches_stored_fixtures(native):
+    """tests/golden/als_small.npz (dense NumPy/SciPy restatement in fp64, see tests/golden/make_golden.py): the CUDA path
+    through the C ABI agrees with the stored factors within the stated 1e-4 - no oracle code runs in this test."""
+    from pathlib import Path
+    z = np.load(Path(__file__).parent / "golden" / "als_small.npz")
+    for n in sorted({k.split("/")[0] for k in z.files}):
+        nu, ni, rank, iters, lam, implicit, alpha = z[n + "/params"]
+        nu, ni, rank, iters, implicit = int(nu), int(ni), int(rank), int(iters), bool(implicit)
+        m = native.NativeALS(rank, nu, ni, lam=float(lam), implicit=implicit, alpha=float(alpha))
+        m.set_ratings(z[n + "/user"], z[n + "/item"], z[n + "/rating"], dedup=0)
+        m.set_init(z[n + "/user_init"], z[n + "/item_init"])
+        m.run(iters)
+        uf, itf, hu, hi = m.get_factors()
+        assert np.array_equal(hu, z[n + "/user_has"]) and np.array_equal(hi, z[n + "/item_has"])
+        eu, ei = frob_rel(uf, z[n + "/user_factors"]), frob_rel(itf, z[n + "/item_factors"])
+        assert eu <= TOL and ei <= TOL, (n, eu, ei)
+        m.close()
+
+
 def test_config_c1_recommendation_template(native, oracle):
     """BASELINE.json configs[0]: rank 10, 10k x 1k, 100k ratings, explicit, lambda 0.01, 20 iterations, seed 3."""
     nu, ni, nnz = 10000, 1000, 100000

@@ -143,3 +143,24 @@ def test_low_rank_recovery_cases(oracle):
         uf, itf, hu, hi = oracle.als_train(nu, ni, tr[0], tr[1], tr[2], rank, iters, reg, implicit, 1.0, u0, i0)
         v = L.score(metric, uf, itf, te, hu, hi)
         assert L.passes(metric, v, target), (name, metric, v, target)
+
+
+def _golden_cases():
+    from pathlib import Path
+    z = np.load(Path(__file__).parent / "golden" / "als_small.npz")
+    names = sorted({k.split("/")[0] for k in z.files})
+    for n in names:
+        nu, ni, rank, iters, lam, implicit, alpha = z[n + "/params"]
+        yield n, z, int(nu), int(ni), int(rank), int(iters), float(lam), bool(implicit), float(alpha)
+
+
+def test_c_oracle_matches_stored_fixtures(oracle):
+    """tests/golden/als_small.npz (dense NumPy/SciPy restatement, see make_golden.py): the C oracle reproduces the stored
+    factors to fp32 rounding of the stored factors between half-steps."""
+    for n, z, nu, ni, rank, iters, lam, implicit, alpha in _golden_cases():
+        uf, itf, hu, hi = oracle.als_train(nu, ni, z[n + "/user"], z[n + "/item"], z[n + "/rating"], rank, iters, lam,
+                                           implicit, alpha, z[n + "/user_init"], z[n + "/item_init"])
+        assert np.array_equal(hu, z[n + "/user_has"]) and np.array_equal(hi, z[n + "/item_has"])
+        for got, want in ((uf, z[n + "/user_factors"]), (itf, z[n + "/item_factors"])):
+            err = np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want)
+            assert err <= 2e-6, (n, err)
