@@ -412,6 +412,25 @@ static void dfree(pio_als_handle* h, T*& p) {
   p = nullptr;
 }
 
+// Device temporaries of one API call: released (stream-ordered) on every exit path, including the early error returns
+// of CK().
+struct Scratch {
+  pio_als_handle* h;
+  std::vector<void*> ptrs;
+  explicit Scratch(pio_als_handle* h_) : h(h_) {}
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  template <class T>
+  cudaError_t alloc(T** p, size_t n) {
+    const cudaError_t e = dalloc(h, p, n);
+    if (e == cudaSuccess) ptrs.push_back((void*)*p);
+    return e;
+  }
+  ~Scratch() {
+    for (void* q : ptrs) cudaFreeAsync(q, h->stream);
+  }
+};
+
 static void free_side(pio_als_handle* h, Side& s, bool keep_factors) {
   dfree(h, s.perm); dfree(h, s.inv); dfree(h, s.rpos); dfree(h, s.p2i); dfree(h, s.deg); dfree(h, s.npos); dfree(h, s.ptr);
   dfree(h, s.idx); dfree(h, s.val); dfree(h, s.nreg); dfree(h, s.cand_ext);
@@ -1234,6 +1253,7 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
   CK(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = h->stream;
   const int KP = h->KP;
+  Scratch tmp(h);
   int* d_users = nullptr;
   float* d_xq = nullptr;
   uint8_t *d_valid = nullptr, *d_mask = nullptr;
@@ -1255,16 +1275,16 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
       attr_smem[h->cfg.device] = sb_smem;
     }
   }
-  CK(h, dalloc(h, &d_users, (size_t)n));
-  CK(h, dalloc(h, &d_xq, (size_t)n * KP));
-  CK(h, dalloc(h, &d_valid, (size_t)n));
-  CK(h, dalloc(h, &d_cand, (size_t)n * gx * topk));
-  CK(h, dalloc(h, &d_oi, (size_t)n * topk));
-  CK(h, dalloc(h, &d_os, (size_t)n * topk));
-  CK(h, dalloc(h, &d_oc, (size_t)n));
+  CK(h, tmp.alloc(&d_users, (size_t)n));
+  CK(h, tmp.alloc(&d_xq, (size_t)n * KP));
+  CK(h, tmp.alloc(&d_valid, (size_t)n));
+  CK(h, tmp.alloc(&d_cand, (size_t)n * gx * topk));
+  CK(h, tmp.alloc(&d_oi, (size_t)n * topk));
+  CK(h, tmp.alloc(&d_os, (size_t)n * topk));
+  CK(h, tmp.alloc(&d_oc, (size_t)n));
   CK(h, cudaMemcpyAsync(d_users, users, sizeof(int) * n, cudaMemcpyHostToDevice, st));
   if (item_mask) {
-    CK(h, dalloc(h, &d_mask, (size_t)h->I.n));
+    CK(h, tmp.alloc(&d_mask, (size_t)h->I.n));
     CK(h, cudaMemcpyAsync(d_mask, item_mask, (size_t)h->I.n, cudaMemcpyHostToDevice, st));
   }
   gather_rows_kernel<<<n, 64, 0, st>>>(h->U.F, KP, d_users, n, h->U.perm, h->U.deg, h->U.n, d_xq, d_valid);
@@ -1284,8 +1304,6 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
   CK(h, cudaMemcpyAsync(out_items, d_oi, sizeof(int) * (size_t)n * topk, cudaMemcpyDeviceToHost, st));
   CK(h, cudaMemcpyAsync(out_scores, d_os, sizeof(float) * (size_t)n * topk, cudaMemcpyDeviceToHost, st));
   if (out_count) CK(h, cudaMemcpyAsync(out_count, d_oc, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
-  dfree(h, d_users); dfree(h, d_xq); dfree(h, d_valid); dfree(h, d_mask); dfree(h, d_cand);
-  dfree(h, d_oi); dfree(h, d_os); dfree(h, d_oc);
   CK(h, cudaStreamSynchronize(st));
   return PIO_ALS_OK;
 }
@@ -1303,12 +1321,13 @@ int pio_als_similar(pio_als_handle* h, const int32_t* query_items, int nq, int t
   CK(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = h->stream;
   const int KP = h->KP, k = h->cfg.rank;
+  Scratch tmp(h);
   int* d_q = nullptr;
   float* d_qf = nullptr;
   uint8_t *d_valid = nullptr, *d_mask = nullptr;
-  CK(h, dalloc(h, &d_q, (size_t)nq));
-  CK(h, dalloc(h, &d_qf, (size_t)nq * KP));
-  CK(h, dalloc(h, &d_valid, (size_t)nq));
+  CK(h, tmp.alloc(&d_q, (size_t)nq));
+  CK(h, tmp.alloc(&d_qf, (size_t)nq * KP));
+  CK(h, tmp.alloc(&d_valid, (size_t)nq));
   CK(h, cudaMemcpyAsync(d_q, query_items, sizeof(int) * nq, cudaMemcpyHostToDevice, st));
   gather_rows_kernel<<<nq, 64, 0, st>>>(h->I.F, KP, d_q, nq, h->I.perm, h->I.deg, h->I.n, d_qf, d_valid);
   LAUNCHED(h);
@@ -1322,11 +1341,11 @@ int pio_als_similar(pio_als_handle* h, const int32_t* query_items, int nq, int t
   int rc = PIO_ALS_OK;
   if (!keep.empty()) {
     float* d_qc = nullptr;
-    CK(h, dalloc(h, &d_qc, keep.size() * (size_t)KP));
+    CK(h, tmp.alloc(&d_qc, keep.size() * (size_t)KP));
     for (size_t j = 0; j < keep.size(); ++j)
       CK(h, cudaMemcpyAsync(d_qc + j * KP, d_qf + (size_t)keep[j] * KP, sizeof(float) * KP, cudaMemcpyDeviceToDevice, st));
     if (item_mask) {
-      CK(h, dalloc(h, &d_mask, (size_t)h->I.n));
+      CK(h, tmp.alloc(&d_mask, (size_t)h->I.n));
       CK(h, cudaMemcpyAsync(d_mask, item_mask, (size_t)h->I.n, cudaMemcpyHostToDevice, st));
     }
     // batched kernel (query vectors resident in shared memory) unless the query is too large for it
@@ -1350,10 +1369,10 @@ int pio_als_similar(pio_als_handle* h, const int32_t* query_items, int nq, int t
     int *d_oi = nullptr, *d_oc = nullptr;
     float* d_os = nullptr;
     const int npools = batched ? ntiles * SC_WARPS : ntiles;   // candidate lists of topk entries left for the merge
-    CK(h, dalloc(h, &d_cand, (size_t)npools * topk));
-    CK(h, dalloc(h, &d_oi, (size_t)topk));
-    CK(h, dalloc(h, &d_os, (size_t)topk));
-    CK(h, dalloc(h, &d_oc, 1));
+    CK(h, tmp.alloc(&d_cand, (size_t)npools * topk));
+    CK(h, tmp.alloc(&d_oi, (size_t)topk));
+    CK(h, tmp.alloc(&d_os, (size_t)topk));
+    CK(h, tmp.alloc(&d_oc, 1));
     if (batched)
       score_cos_topk_batched_kernel<<<ntiles, SB_THREADS, sc_smem, st>>>(h->I.F, h->I.n_internal, KP, k, d_qc, d_q, nq, nqv,
                                                                          h->I.cand_ext, d_mask, topk, d_cand);
@@ -1369,9 +1388,7 @@ int pio_als_similar(pio_als_handle* h, const int32_t* query_items, int nq, int t
     CK(h, cudaMemcpyAsync(&cnt, d_oc, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
     if (out_count) *out_count = cnt;
-    dfree(h, d_qc); dfree(h, d_cand); dfree(h, d_oi); dfree(h, d_os); dfree(h, d_oc); dfree(h, d_mask);
   }
-  dfree(h, d_q); dfree(h, d_qf); dfree(h, d_valid);
   CK(h, cudaStreamSynchronize(st));
   return rc;
 }
