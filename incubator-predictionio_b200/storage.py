@@ -25,6 +25,44 @@ from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Tupl
 import numpy as np
 
 
+def _coerce(v, typ):
+    """json4s-style extraction of a JSON value into a Python type: primitives, List[T], Set[T], Optional[T],
+    dataclasses (case classes; absent Optional fields become None)."""
+    import dataclasses
+    import typing
+    origin = typing.get_origin(typ)
+    args = typing.get_args(typ)
+    if typ is None or typ is typing.Any:
+        return v
+    if origin is typing.Union:                       # Optional[T]
+        inner = [a for a in args if a is not type(None)]
+        return None if v is None else _coerce(v, inner[0])
+    if origin in (list, typing.List):
+        return [_coerce(x, args[0]) if args else x for x in v]
+    if origin in (set, typing.Set, frozenset):
+        return {(_coerce(x, args[0]) if args else x) for x in v}
+    if typ in (list, set):
+        return typ(v)
+    if dataclasses.is_dataclass(typ):
+        hints = typing.get_type_hints(typ)
+        kw = {}
+        for f in dataclasses.fields(typ):
+            if f.name in v and v[f.name] is not None:
+                kw[f.name] = _coerce(v[f.name], hints[f.name])
+            elif typing.get_origin(hints[f.name]) is typing.Union and type(None) in typing.get_args(hints[f.name]):
+                kw[f.name] = None
+            elif f.default is not dataclasses.MISSING or f.default_factory is not dataclasses.MISSING:  # type: ignore
+                continue
+            else:
+                raise DataMapException(f"The field {f.name} is required.")
+        return typ(**kw)
+    if typ is bool:
+        if not isinstance(v, bool):
+            raise DataMapException(f"{v!r} is not a Boolean")
+        return v
+    return typ(v)
+
+
 class DataMapException(KeyError):
     pass
 
@@ -49,17 +87,27 @@ class DataMap:
         v = self.fields[name]
         if v is None:
             raise DataMapException(f"The required field {name} cannot be null.")
-        return typ(v) if typ is not None else v
+        return _coerce(v, typ) if typ is not None else v
 
     def getOpt(self, name: str, typ=None):
         v = self.fields.get(name)
         if v is None:
             return None
-        return typ(v) if typ is not None else v
+        return _coerce(v, typ) if typ is not None else v
 
     def getOrElse(self, name: str, default, typ=None):
         v = self.getOpt(name, typ)
         return default if v is None else v
+
+    def extract(self, cls):
+        """DataMap.extract[T] (DataMap.scala): the whole property bag as a case class - here a dataclass whose
+        Optional[...] fields may be absent."""
+        return _coerce(self.fields, cls)
+
+    @staticmethod
+    def fromJson(text: str) -> "DataMap":
+        """DataMap(jsonString) of the reference (DataMap.scala companion)."""
+        return DataMap(json.loads(text))
 
     def __add__(self, other: "DataMap") -> "DataMap":  # ++
         d = dict(self.fields)
@@ -95,6 +143,16 @@ class PropertyMap(DataMap):
         super().__init__(fields)
         self.firstUpdated = firstUpdated
         self.lastUpdated = lastUpdated
+
+    def __eq__(self, o):   # PropertyMap.scala: equal fields AND equal first/last update times
+        if isinstance(o, PropertyMap):
+            return self.fields == o.fields and self.firstUpdated == o.firstUpdated and self.lastUpdated == o.lastUpdated
+        return False
+
+    __hash__ = None
+
+    def __repr__(self):
+        return f"PropertyMap({self.fields}, {self.firstUpdated}, {self.lastUpdated})"
 
 
 def _parse_time(s) -> _dt.datetime:
@@ -264,6 +322,50 @@ def _iter_events(appName: str, channelName: Optional[str]) -> Iterator[Event]:
 _UNSET = object()
 
 
+class LEventAggregator:
+    """Fold of $set / $unset / $delete events into per-entity properties, restated from
+    data/src/main/scala/org/apache/predictionio/data/storage/LEventAggregator.scala:42-146: events are sorted by event
+    time per entity; $set merges (or creates), $unset removes keys (no-op without state), $delete drops the state;
+    firstUpdated / lastUpdated are the earliest / latest time over ALL three event kinds (a $delete does not reset them)."""
+
+    eventNames = ["$set", "$unset", "$delete"]
+
+    @staticmethod
+    def _fold(events: Iterable[Event]):
+        dm: Optional[Dict[str, Any]] = None
+        first = last = None
+        for e in sorted(events, key=lambda x: x.eventTime):
+            if e.event not in LEventAggregator.eventNames:
+                continue
+            if e.event == "$set":
+                dm = dict(e.properties.fields) if dm is None else {**dm, **e.properties.fields}
+            elif e.event == "$unset":
+                if dm is not None:
+                    dm = {k: v for k, v in dm.items() if k not in e.properties.fields}
+            else:
+                dm = None
+            first = e.eventTime if first is None or e.eventTime < first else first
+            last = e.eventTime if last is None or e.eventTime > last else last
+        return dm, first, last
+
+    @staticmethod
+    def aggregateProperties(events: Iterable[Event]) -> Dict[str, PropertyMap]:
+        groups: Dict[str, List[Event]] = {}
+        for e in events:
+            groups.setdefault(e.entityId, []).append(e)
+        out = {}
+        for k, evs in groups.items():
+            dm, first, last = LEventAggregator._fold(evs)
+            if dm is not None:
+                out[k] = PropertyMap(dm, first, last)
+        return out
+
+    @staticmethod
+    def aggregatePropertiesSingle(events: Iterable[Event]) -> Optional[PropertyMap]:
+        dm, first, last = LEventAggregator._fold(events)
+        return None if dm is None else PropertyMap(dm, first, last)
+
+
 class PEventStore:
     """PEventStore.find / aggregateProperties over the file store (the `sc` argument is accepted and ignored)."""
 
@@ -300,30 +402,11 @@ class PEventStore:
                             ) -> List[Tuple[str, PropertyMap]]:
         evs = PEventStore.find(appName, channelName, startTime, untilTime, entityType=entityType,
                                eventNames=["$set", "$unset", "$delete"])
-        evs.sort(key=lambda e: e.eventTime)
-        state: Dict[str, Optional[Tuple[Dict[str, Any], _dt.datetime, _dt.datetime]]] = {}
-        for e in evs:
-            cur = state.get(e.entityId)
-            if e.event == "$set":
-                if cur is None:
-                    state[e.entityId] = (dict(e.properties.fields), e.eventTime, e.eventTime)
-                else:
-                    cur[0].update(e.properties.fields)
-                    state[e.entityId] = (cur[0], cur[1], e.eventTime)
-            elif e.event == "$unset":
-                if cur is not None:
-                    for k in e.properties.fields:
-                        cur[0].pop(k, None)
-                    state[e.entityId] = (cur[0], cur[1], e.eventTime)
-            elif e.event == "$delete":
-                state[e.entityId] = None
         out = []
-        for k, v in state.items():
-            if v is None:
+        for k, pm in LEventAggregator.aggregateProperties(evs).items():
+            if required is not None and not all(r in pm.fields for r in required):
                 continue
-            if required is not None and not all(r in v[0] for r in required):
-                continue
-            out.append((k, PropertyMap(v[0], v[1], v[2])))
+            out.append((k, pm))
         return out
 
 
