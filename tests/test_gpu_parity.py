@@ -193,7 +193,8 @@ def test_rank64_kernel_selection(native, oracle, monkeypatch):
         assert not np.array_equal(res["mma"][1], res["fp32"][1]) and not np.array_equal(res["mma"][1], res["tcgen05"][1])
 
 
-def test_ragged_and_empty_rows(native, oracle):
+@pytest.mark.parametrize("rank", [8, 64])    # 8: FP32 kernel, 64: mma.sync kernel
+def test_ragged_and_empty_rows(native, oracle, rank):
     """Users/items that never occur own no factor (has=0, zero row); duplicates count separately."""
     nu, ni = 50, 30
     rng = np.random.default_rng(1)
@@ -202,17 +203,18 @@ def test_ragged_and_empty_rows(native, oracle):
     r = rng.integers(1, 6, 400).astype(np.float32)
     u[:20] = u[0]
     i[:20] = i[0]                                             # 20 duplicates of one pair
-    _, g, o = run_both(native, oracle, nu, ni, u, i, r, 8, 4, 0.1, False, 1.0)
+    _, g, o = run_both(native, oracle, nu, ni, u, i, r, rank, 4, 0.1, False, 1.0)
     assert (g[2] == o[2]).all() and (g[3] == o[3]).all()
     assert (g[0][g[2] == 0] == 0).all() and (g[1][g[3] == 0] == 0).all()
     assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
 
 
-def test_single_rating(native, oracle):
+@pytest.mark.parametrize("rank", [5, 64])
+def test_single_rating(native, oracle, rank):
     u = np.array([2], np.int32)
     i = np.array([1], np.int32)
     r = np.array([3.0], np.float32)
-    _, g, o = run_both(native, oracle, 4, 3, u, i, r, 5, 2, 0.1, False, 1.0)
+    _, g, o = run_both(native, oracle, 4, 3, u, i, r, rank, 2, 0.1, False, 1.0)
     assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
 
 
@@ -236,13 +238,14 @@ def test_dedup_modes_match_host_preparation(native, oracle, mode):
     assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
 
 
-def test_implicit_negative_and_zero_preferences(native, oracle):
+@pytest.mark.parametrize("rank", [12, 64])   # 12: FP32 kernel, 64: mma.sync kernel
+def test_implicit_negative_and_zero_preferences(native, oracle, rank):
     nu, ni, nnz = 500, 80, 8000
     u, i, r = synth.synth_ratings(nu, ni, nnz, seed=4, implicit=True)
     r = r.copy()
     r[::5] = -r[::5]
     r[::7] = 0.0
-    _, g, o = run_both(native, oracle, nu, ni, u, i, r, 12, 4, 0.02, True, 0.7)
+    _, g, o = run_both(native, oracle, nu, ni, u, i, r, rank, 4, 0.02, True, 0.7)
     assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
 
 
