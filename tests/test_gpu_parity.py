@@ -238,8 +238,11 @@ def test_dedup_modes_match_host_preparation(native, oracle, mode):
     assert frob_rel(g[0], o[0]) <= TOL and frob_rel(g[1], o[1]) <= TOL
 
 
-@pytest.mark.parametrize("rank", [12, 64])   # 12: FP32 kernel, 64: mma.sync kernel
-def test_implicit_negative_and_zero_preferences(native, oracle, rank):
+@pytest.mark.parametrize("rank,tc", [(12, None), (64, None), (64, "1")])   # FP32 kernel, mma.sync kernel, tcgen05 kernel
+def test_implicit_negative_and_zero_preferences(native, oracle, monkeypatch, rank, tc):
+    monkeypatch.delenv("PIO_ALS_TC", raising=False)
+    if tc:
+        monkeypatch.setenv("PIO_ALS_TC", tc)
     nu, ni, nnz = 500, 80, 8000
     u, i, r = synth.synth_ratings(nu, ni, nnz, seed=4, implicit=True)
     r = r.copy()
