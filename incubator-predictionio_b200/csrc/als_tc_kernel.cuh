@@ -1,31 +1,38 @@
-// als_tc_kernel.cuh -- rank-64 ALS half-step with the Gramian on the 5th-gen tensor cores.
+// als_tc_kernel.cuh -- rank 33..64 ALS half-step with the Gramian on the 5th-gen tensor cores (tcgen05 + TMEM).
 //
 // Same mathematics as als_solve_kernel (als_kernels.cuh) for KP = 64, but  A = sum (s y)(s y)^T  is a
 // split-precision SYRK on tcgen05:
 //   every gathered, sqrt(c1)-scaled source row x (64 floats) is staged as  [hi | lo]  (128 floats),
-//   hi = tf32_round(x), lo = x - hi;  8 ratings form one K-block in the MN-major
+//   hi = the top 10 mantissa bits of x, lo = x - hi (exact);  8 ratings form one K-block in the MN-major
 //   SWIZZLE_128B_BASE32B UMMA shared-memory layout (per 32 columns a 1 KB atom: one 128-byte row per
 //   rating, its four 32-byte chunks XOR-swizzled by rating%4) -- the only MN-major layout kind::tf32
 //   accepts (verified with tools/umma_probe.cu; the un-swizzled MN-major forms silently produce 0);
-//   per K-block three  tcgen05.mma.cta_group::1.kind::tf32  (M = N = 64, K = 8) accumulate
-//   D += hi^T hi + lo^T hi + hi^T lo  into ONE 64-column TMEM accumulator (the dropped lo^T lo term is
-//   ~2^-22 relative) -- fp32-class products at tensor-core rate, and the accumulator is the matrix
-//   itself (row r in TMEM lane 32*(r/16) + r%16, tools/umma_probe64.cu), so draining needs no
-//   cross-warp quadrant sum and TMEM (512 columns) holds two batches of four rows: the MMAs of batch
-//   b+1 overlap the drain of batch b.
+//   per K-block ONE  tcgen05.mma.cta_group::1.kind::tf32  with A = all 128 staged columns (M = 128) and
+//   B = the 64 hi columns (N = 64, K = 8) accumulates  D = [hi^T hi ; lo^T hi]  into a 128-lane x 64-column
+//   TMEM accumulator (row r in lane r); the drain forms  A = HH + LH + LH^T  (the dropped lo^T lo term is
+//   ~2^-20 relative).  TMEM (512 columns) holds two batches of four rows: the MMAs of batch b+1 overlap the
+//   drain of batch b.
 //
-// Warp roles (512 threads, 1 CTA per SM, persistent; rows are claimed from a global counter in
-// degree-descending order):
-//   warp 0      scheduler + MMA issuer (one elected lane): builds batch descriptors, issues the MMAs,
-//               commits to mbarriers
-//   warps 1-3   producers: gather source rows (LDG.128), scale, split hi/lo, STS into the stage ring,
-//               accumulate the right-hand side b
-//   warps 4-15  three teams of four warps (one warp per TMEM lane quarter): drain the four
-//               accumulators of their batch (tcgen05.ld -> packed A slot in smem), then each warp
-//               Cholesky-solves one of the four rows (chol_solve_warp<PACKED_IN>).
-// A batch = up to four (row, rating-segment) pairs, one per TMEM accumulator (64 columns each);
-// rows longer than SEG ratings are accumulated segment by segment with fp32 adds in shared memory
-// between segments (bounds the length of any single tensor-core accumulation chain).
+// Warp roles (512 threads, 1 CTA per SM, persistent; degree-sorted rows are dealt statically: groups of
+// NTEAM*NSLOT consecutive rows go to the CTAs in snake order):
+//   warp 0              scheduler + MMA issuer, warp-parallel: lane t*4+s keeps row lane (team t, slot s) in
+//                       registers, builds the flat stage list of a batch with shuffles, publishes it, issues the
+//                       batch's MMAs from one lane and commits to mbarriers
+//   warps 1..NGATHER    gather warps: gw owns every NGATHER-th stage; source indices two stages ahead in
+//                       registers, 12 LDGSTS per 24-rating stage into the raw ring (rows padded to 288 bytes),
+//                       completion by cp.async.mbarrier.arrive.noinc
+//   next NCONV warps    converters: cw owns the stages whose number inside their segment is cw mod NCONV: LDS.128
+//                       of the raw rows, scale, hi/lo split, 24 conflict-free STS.128 into the UMMA stage ring,
+//                       fence.proxy.async, arrive on full[stage]; right-hand side b reduced at segment ends
+//   last 4*NTEAM warps  teams of four warps (one per TMEM lane quarter): drain the four accumulators of their
+//                       batch (tcgen05.ld: two warps store HH, two add LH and then its transpose), then each
+//                       warp Cholesky-solves one of the four rows (chol_solve_warp<PACKED_IN>), or - split mode -
+//                       stores the normal equations for als_solve_packed_kernel.
+// A batch = up to four (row, rating-segment) pairs, one per TMEM accumulator (64 columns each); rows longer
+// than SEG ratings are accumulated segment by segment with fp32 adds in shared memory between segments (bounds
+// the length of any single tensor-core accumulation chain).  Every sum has a fixed order that depends on the
+// row alone, so results do not depend on the grid or on how rows are sharded over GPUs.
+// Every blocking mbarrier wait has a watchdog (mbar_wait): a protocol error traps with a diagnostic.
 // This header is included once per role partition (pio_als.cu): TC_NS names the namespace, TC_NTEAM / TC_NCONV /
 // TC_NGATHER / TC_NSTAGE / TC_NRAW fix how the sixteen warps and the shared memory of the CTA are divided.
 #ifndef TC_NS
