@@ -279,7 +279,6 @@ static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget (227 KB) exce
 
 struct TcParams {
   SolveParams sp;
-  int* counter;  // next row to claim (starts at sp.row_begin)
   long long* timing;  // debug only (PIO_ALS_TC_TIMING=1): [grid][16 warps][8] cycle counters, else null
   float* dbg;    // debug only (PIO_ALS_TC_DEBUG=1): per local row ASLOT + KP floats (A as drained, b), else null
   float* out;    // split mode: per local row ASLOT + KP floats (packed lower triangle of the Gramian, then b); the rows

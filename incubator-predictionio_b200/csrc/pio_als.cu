@@ -167,7 +167,6 @@ __global__ void assign_internal_kernel(const uint32_t* order, int n, int W, int 
   rpos[row] = p;       // degree-rank position: independent of the number of GPUs
   p2i[p] = internal;
 }
-__global__ void set_int_kernel(int* a, int v) { *a = v; }
 __global__ void fill_int_kernel(int* a, long long n, int v) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) a[e] = v;
@@ -358,7 +357,6 @@ struct pio_als_handle {
   int gram_blocks = 0;
   int* d_fail = nullptr;
   int* d_counts = nullptr;
-  int* d_counter = nullptr;   // row-claim counter of the tensor-core solve kernel
   long long* d_timing = nullptr;  // PIO_ALS_TC_TIMING=1: per-warp cycle counters of the last tensor-core launch
   float* d_dbg = nullptr;     // PIO_ALS_TC_DEBUG=1: A/b dump of the last tensor-core half-step
   size_t dbg_rows = 0;
@@ -719,7 +717,6 @@ static cudaError_t launch_tc(pio_als_handle* h, Side& dst, const SolveParams& p,
     attr_set[h->cfg.device] = true;
   }
   typename A::Params tp;
-  tp.counter = h->d_counter;
   tp.dbg = nullptr;
   tp.timing = nullptr;
   tp.out = nullptr;
@@ -991,8 +988,7 @@ static int create_common(pio_als_handle* h) {
   if (cudaMallocAsync((void**)&h->yty, sizeof(float) * h->KP * h->KP, h->stream) != cudaSuccess ||
       cudaMallocAsync((void**)&h->gram_partial, sizeof(double) * (size_t)h->gram_blocks * h->KP * h->KP, h->stream) != cudaSuccess ||
       cudaMallocAsync((void**)&h->d_fail, sizeof(int), h->stream) != cudaSuccess ||
-      cudaMallocAsync((void**)&h->d_counts, 4 * sizeof(int), h->stream) != cudaSuccess ||
-      cudaMallocAsync((void**)&h->d_counter, sizeof(int), h->stream) != cudaSuccess)
+      cudaMallocAsync((void**)&h->d_counts, 4 * sizeof(int), h->stream) != cudaSuccess)
     return fail(nullptr, PIO_ALS_ERR_CUDA, "device allocation failed");
   cudaMemsetAsync(h->yty, 0, sizeof(float) * h->KP * h->KP, h->stream);
   cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream);
@@ -1039,7 +1035,6 @@ void pio_als_destroy(pio_als_handle* h) {
     dfree(h, h->gram_partial);
     dfree(h, h->d_fail);
     dfree(h, h->d_counts);
-    dfree(h, h->d_counter);
     cudaStreamSynchronize(h->stream);
     if (h->tc_out) cudaFree(h->tc_out);
     if (h->d_dbg) cudaFree(h->d_dbg);
