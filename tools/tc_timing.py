@@ -1,3 +1,7 @@
+"""Per-role cycle counters of the tcgen05 kernel.  Needs a library built with the instrumentation compiled in:
+    nvcc ... -DPIO_TC_TIMING=1 ... pio_als.cu   (the default build carries none)
+then  PIO_ALS_TC=1 [PIO_ALS_TC_MIN_DEG=...] python tools/tc_timing.py   (TC_NU / TC_NI / TC_NNZ choose the problem size).
+The warp -> role map below matches the partition instantiated in pio_als.cu (2 gather, 5 converter warps, 2 teams)."""
 import os, sys, ctypes as C
 os.environ["PIO_ALS_TC_TIMING"] = "1"
 sys.path.insert(0, "/root/repo")
