@@ -1,11 +1,18 @@
 #!/usr/bin/env python
-"""bench.py -- ALS iterations/sec on the BASELINE.json workload (configs[1]: rank 64, 1M users x 100k
-items, 100M synthetic implicit ratings), B200-native path vs the CPU restatement of the reference.
+"""bench.py -- ALS iterations/sec and top-k predictions/sec on the BASELINE.json workload (configs[1]: rank 64,
+1M users x 100k items, 100M synthetic implicit ratings), B200-native path vs the CPU restatement of the reference.
 
 One "step" = one ALS iteration (item half-step + user half-step) over the whole rating set.
-  value : iterations/sec with ratings + CSR already resident in HBM (CUDA events on the library stream)
-  e2e   : iterations/sec through the one-shot C-ABI call pio_als_train with HOST buffers:
-          H2D of the COO triplets, ingest (dedup + 2 CSR builds), K iterations, D2H of the factors.
+  value    : iterations/sec with ratings + CSR already resident in HBM (CUDA events on the library stream)
+  e2e      : iterations/sec through the one-shot C-ABI call pio_als_train with HOST buffers:
+             H2D of the COO triplets, ingest (dedup + 2 CSR builds), K iterations, D2H of the factors
+  parity   : after the timed region one more iteration runs on the GPU; a sample of its destination rows (strided rows
+             plus the heaviest rows of both sides) is recomputed by the CPU oracle from the GPU's own source factors and
+             compared; the process exits non-zero above 1e-4
+  checksum : CRC of both factor matrices after warm-up + K iterations -- identical at every GPU count
+  cpu_baseline / --impl reference : the oracle (C/OpenMP restatement of MLlib ALS) timed on the host's physical cores
+             over FULL iterations of the same workload
+  topk     : top-k predictions/sec through pio_als_recommend / pio_als_similar with host buffers
 See DESIGN.md for the roofline arithmetic.
 """
 import argparse
@@ -15,6 +22,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 from pathlib import Path
 
 import numpy as np
@@ -25,10 +33,13 @@ sys.path.insert(0, str(ROOT))
 WORKLOADS = {
     # name: (n_users, n_items, nnz, rank, implicit)
     "c2": (1_000_000, 100_000, 100_000_000, 64, True),
+    "c3": (10_000_000, 1_000_000, 1_000_000_000, 128, True),
     "c1": (10_000, 1_000, 100_000, 10, False),
     "small": (100_000, 20_000, 5_000_000, 64, True),
+    "small128": (200_000, 40_000, 10_000_000, 128, True),
 }
 LAMBDA, ALPHA, SEED = 0.01, 1.0, 3
+PARITY_TOL = 1e-4
 
 
 def algorithmic_work(nu, ni, nnz, k, implicit):
@@ -98,79 +109,216 @@ def traffic_from_profiles(workload):
 
 
 def measured_peaks():
+    """HBM GB/s, dense bf16 TFLOP/s (driver-written MEASURED_PEAKS.json), FP32 FFMA TFLOP/s (profiles/peaks_r02.json,
+    measured by tools/peaks.cu on this pool; nominal 148 x 128 x 2 x 1.965 GHz otherwise)."""
+    hbm, bf16, src = 6650.0, 1590.0, "fallback"
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
-    return 6650.0, 1590.0, "fallback"
+        hbm, bf16, src = d.get("hbm_gbs", hbm), d.get("bf16_tflops", bf16), "measured"
+    fp32, fp32_src = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"
+    mma_tf32 = None
+    q = ROOT / "profiles" / "peaks_r02.json"
+    if q.exists():
+        try:
+            d = json.loads(q.read_text())
+            if d.get("ffma_tflops"):
+                fp32, fp32_src = float(d["ffma_tflops"]), "measured (tools/peaks.cu, profiles/peaks_r02.json)"
+            mma_tf32 = d.get("mma_sync_tf32_tflops")
+        except Exception:
+            pass
+    return {"hbm": hbm, "bf16": bf16, "src": src, "fp32": fp32, "fp32_src": fp32_src, "mma_tf32": mma_tf32}
 
 
-def cpu_baseline_prepare(nu, ni, nnz, k, implicit, d_coo=None):
-    """Load the oracle, generate (or take) the workload's ratings and build both CSR orientations - done once."""
+# ---------------------------------------------------------------------------------------------------------
+# CPU side: the oracle as checker (parity sample) and as reported baseline (full iterations on the host cores)
+# ---------------------------------------------------------------------------------------------------------
+def physical_cores():
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
+def load_oracle():
+    """The oracle library, rebuilt with -march=native when gcc is on the box, on the physical cores of the host
+    (torchrun exports OMP_NUM_THREADS=1: the explicit oracle_set_num_threads call overrides it)."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
     from oracle import als_oracle as o
-    from pio_b200 import synth
-    try:  # use a host-native build for the timed baseline when gcc is on the box
+    try:
+        import ctypes
         import shutil
         if shutil.which("gcc"):
             so = o._SO.parent / "libals_oracle_native.so"
-            subprocess.run(["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-fvisibility=hidden",
-                            "-o", str(so), str(o._SRC), "-lm"], check=True)
-            import ctypes
+            if not so.exists() or so.stat().st_mtime < o._SRC.stat().st_mtime:
+                subprocess.run(["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-fvisibility=hidden",
+                                "-o", str(so), str(o._SRC), "-lm"], check=True)
             o._lib = ctypes.CDLL(str(so))
             o._lib.oracle_num_threads.restype = ctypes.c_int
     except Exception:
         pass
-    if d_coo is not None:
-        u, i, r = d_coo
-    else:
-        u, i, r = synth.synth_ratings(nu, ni, nnz, seed=SEED, implicit=implicit)
-    # duplicates are kept as separate ratings for the CPU sample (same arithmetic per rating)
+    cores = physical_cores()
+    o.set_num_threads(cores)
+    return o, cores
+
+
+def build_host_problem(o, nu, ni, k, implicit, coo):
+    """Both CSR orientations of the workload on the host, prepared like the GPU ingest (implicit: reduceByKey(_+_))."""
+    t0 = time.perf_counter()
+    u, i, r = coo
     uptr, ucol, uval = o.csr_build(nu, u, i, r)
-    iptr, icol, ival = o.csr_build(ni, i, u, r)
-    uf = synth.synth_init_factors(min(nu, 1 << 16), k, SEED, 0)
-    uf = np.ascontiguousarray(np.resize(uf, (nu, k)))
-    itf = synth.synth_init_factors(min(ni, 1 << 16), k, SEED, 1)
-    itf = np.ascontiguousarray(np.resize(itf, (ni, k)))
-    prep = {"o": o, "nu": nu, "ni": ni, "implicit": implicit, "user": (uptr, ucol, uval), "item": (iptr, icol, ival),
-            "uf": uf, "itf": itf, "yty": o.gram(uf) if implicit else None, "cores": o.num_threads()}
+    if implicit:
+        uptr, ucol, uval = o.csr_dedup_sum(uptr, ucol, uval)
+    urow = o.csr_rows(uptr)
+    iptr, icol, ival = o.csr_build(ni, ucol, urow, uval)
+    return {"nu": nu, "ni": ni, "k": k, "implicit": implicit, "user": (uptr, ucol, uval), "item": (iptr, icol, ival),
+            "nnz": int(uptr[-1]), "prep_s": time.perf_counter() - t0}
 
-    def timed(side, stride):
-        ptr, col, val = prep[side]
-        src, dst, n = (itf, uf.copy(), nu) if side == "user" else (uf, itf.copy(), ni)
+
+def cpu_iteration(o, prob, uf, itf, stride=1):
+    """One ALS iteration of the oracle in place (YtY, item half-step, YtY, user half-step); stride > 1 solves every
+    stride-th destination row only.  Returns seconds."""
+    imp = prob["implicit"]
+    t0 = time.perf_counter()
+    yty = o.gram(uf) if imp else None
+    o.half_step(*prob["item"], uf, itf, LAMBDA, imp, ALPHA, yty, 0, prob["ni"], stride)
+    yty = o.gram(itf) if imp else None
+    o.half_step(*prob["user"], itf, uf, LAMBDA, imp, ALPHA, yty, 0, prob["nu"], stride)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_steps(o, cores, prob, uf, itf, n_steps, n_warm, budget_s):
+    """n_warm + n_steps oracle iterations within about budget_s seconds: full iterations when they fit, otherwise every
+    stride-th destination row (>= 25 % of the rows) scaled to a full iteration and flagged as extrapolated."""
+    pilot_stride = 16
+    t_pilot = cpu_iteration(o, prob, uf, itf, pilot_stride) * pilot_stride      # estimate of one full iteration
+    per_step = budget_s / max(1, n_steps + n_warm)
+    stride = 1 if t_pilot <= per_step else min(4, int(np.ceil(t_pilot / per_step)))
+    secs = []
+    for s in range(n_warm + n_steps):
+        t = cpu_iteration(o, prob, uf, itf, stride)
+        if s >= n_warm:
+            secs.append(t)
+    it_s = float(np.mean(secs)) * stride if stride > 1 else float(np.mean(secs))
+    gram_note = ""
+    sample = (f"{n_steps} full iteration(s) over all {prob['nu']} user rows + {prob['ni']} item rows "
+              f"({prob['nnz']} ratings), {np.mean(secs):.2f} s each" if stride == 1 else
+              f"every {stride}th destination row of each side ({100.0 / stride:.0f} % of the rows, "
+              f"{np.mean(secs):.2f} s timed per step), scaled to one iteration")
+    out = {"value": 1.0 / it_s, "unit": "iterations/s", "cores": cores, "kind": "port",
+           "sample": sample + "; C/OpenMP restatement of MLlib ALS (not Spark), threads bound to physical cores" + gram_note,
+           "extrapolated": stride > 1, "sampled_fraction": 1.0 / stride, "seconds_per_step": float(np.mean(secs)),
+           "spread": [float(min(secs)), float(max(secs))]}
+    return out
+
+
+def frob_rel(a, b):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def max_row_rel(a, b):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    nb = np.linalg.norm(b, axis=1)
+    d = np.linalg.norm(a - b, axis=1)
+    return float((d / np.maximum(nb, 1e-3 * nb.max() + 1e-30)).max())
+
+
+def parity_sample(o, prob, src_u, new_i, new_u, n_user=2000, n_item=500, n_heavy=50):
+    """The last GPU iteration (new_i from src_u, then new_u from new_i) against the oracle on a row sample: strided rows
+    plus the heaviest rows of each side (the parts + finish path, the long tensor-core accumulations)."""
+    imp = prob["implicit"]
+    res = {}
+    for side, (ptr, col, val), src, got, n_s in (("item", prob["item"], src_u, new_i, n_item),
+                                                 ("user", prob["user"], new_i, new_u, n_user)):
+        n = ptr.shape[0] - 1
+        deg = np.diff(ptr)
+        rows = np.unique(np.concatenate([np.arange(0, n, max(1, n // n_s)), np.argsort(-deg, kind="stable")[:n_heavy]]))
+        rows = rows[deg[rows] > 0].astype(np.int32)
+        yty = o.gram(src) if imp else None
+        want, fails = o.half_step_rows(ptr, col, val, src, rows, LAMBDA, imp, ALPHA, yty)
+        res[side] = {"rows": int(rows.shape[0]), "max_ratings_in_a_row": int(deg[rows].max()),
+                     "frob_rel": frob_rel(got[rows], want), "max_row_rel": max_row_rel(got[rows], want),
+                     "oracle_cholesky_failures": int(fails)}
+    worst = max(res["item"]["frob_rel"], res["user"]["frob_rel"])
+    return {"frob_rel": worst, "max_rel": max(res["item"]["max_row_rel"], res["user"]["max_row_rel"]),
+            "rows": res["item"]["rows"] + res["user"]["rows"], "tolerance": PARITY_TOL, "ok": bool(worst <= PARITY_TOL),
+            "item": res["item"], "user": res["user"],
+            "how": "GPU iteration W+K+1 recomputed by the CPU oracle (fp64 normal equations) from the GPU's own source "
+                   "factors on strided + heaviest destination rows"}
+
+
+def factor_checksum(uf, itf):
+    """64-bit value: CRC32 of the user factor bytes (high word) and of the item factor bytes (low word)."""
+    return f"{zlib.crc32(np.ascontiguousarray(uf).view(np.uint8)):08x}{zlib.crc32(np.ascontiguousarray(itf).view(np.uint8)):08x}"
+
+
+# ---------------------------------------------------------------------------------------------------------
+def reference_arm(args, nu, ni, nnz, k, implicit, config):
+    """--impl reference: the reference's CPU algorithm (oracle port of MLlib ALS) on this box's physical cores, same
+    workload; every step is a full iteration when W + K of them fit in a few minutes."""
+    import pio_b200  # noqa: F401
+    from pio_b200 import synth
+    o, cores = load_oracle()
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=SEED, implicit=implicit)
+    prob = build_host_problem(o, nu, ni, k, implicit, (u, i, r))
+    del u, i, r
+    uf = np.ascontiguousarray(np.resize(synth.synth_init_factors(min(nu, 1 << 16), k, SEED, 0), (nu, k)))
+    itf = np.ascontiguousarray(np.resize(synth.synth_init_factors(min(ni, 1 << 16), k, SEED, 1), (ni, k)))
+    cb = cpu_baseline_steps(o, cores, prob, uf, itf, args.steps, args.warmup, budget_s=240.0)
+    v = cb["value"]
+    print(json.dumps({"impl": "reference", "metric": "ALS iterations/sec", "value": v, "unit": "iterations/s",
+                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1000.0 * cb["seconds_per_step"], "higher_is_better": True, "scaling": "strong",
+                      "vs_baseline": None, "dtype": "f64 accumulate / f32 storage", "data": "synthetic",
+                      "config": config, "cpu_baseline": cb, "extrapolated": cb["extrapolated"],
+                      "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def topk_bench(native, o, cores, m, nu, ni, k, uf, itf, uh, ih, peaks, dev):
+    """Top-k predictions/sec through the C ABI with host buffers (the second half of BASELINE.json's metric)."""
+    out = {}
+    rng = np.random.default_rng(SEED)
+    # recommendation path (A7/A8): distinct users x top-10 over all items of the trained model
+    nq = min(100_000, nu)
+    users = rng.permutation(nu)[:nq].astype(np.int32)
+    m.recommend(users[:256], 10)   # warm-up
+    t0 = time.perf_counter()
+    gi, gs, gc = m.recommend(users, 10)
+    dt = time.perf_counter() - t0
+    ns = min(2000, nq)
+    t0 = time.perf_counter()
+    oi, os_, oc = o.recommend(uf, uh, itf, ih, users[:ns], 10)
+    cpu_dt = time.perf_counter() - t0
+    scan_bytes = ni * k * 4
+    out["recommend"] = {
+        "what": f"pio_als_recommend: {nq} distinct users x top-10 over {ni} items, rank {k}, one call, host buffers",
+        "value": nq / dt, "unit": "predictions/s", "seconds": dt,
+        "bit_exact_vs_oracle_on_sample": bool(np.array_equal(gi[:ns], oi) and np.array_equal(gs[:ns], os_)),
+        "sample_queries_checked": int(ns),
+        "cpu_baseline": {"value": ns / cpu_dt, "unit": "predictions/s", "cores": cores, "kind": "port",
+                         "sample": f"{ns} of the same queries, fp64 ddot scan + heap (oracle restatement of "
+                                   "recommendProducts)"},
+        "roofline": {"bound": "hbm", "achieved": nq / 16.0 * scan_bytes / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": nq / 16.0 * scan_bytes / dt / 1e9 / peaks["hbm"],
+                     "note": "algorithmic bytes = one scan of the item matrix per group of 16 queries (the kernel's "
+                             "batching); fp64 score accumulation makes the DFMA pipe the real bound"}}
+    # single-query latency
+    lat = []
+    for q in range(20):
         t0 = time.perf_counter()
-        o.half_step(ptr, col, val, src, dst, LAMBDA, implicit, ALPHA, prep["yty"], 0, n, stride)
-        return time.perf_counter() - t0
-
-    prep["timed"] = timed
-    # pilot with a large stride: seconds per destination row of each side
-    su, si = max(1, nu // 2000), max(1, ni // 500)
-    prep["pilot"] = (su, timed("user", su), si, timed("item", si))
-    return prep
-
-
-def cpu_baseline_run(prep, target_s=12.0):
-    """Time the oracle (CPU restatement of the MLlib algorithm) on a strided sample of destination rows of the SAME
-    workload, sized to about target_s seconds, and scale to one full iteration."""
-    o, timed = prep["o"], prep["timed"]
-    su, tu, si, ti = prep["pilot"]
-    su2 = max(1, int(su * tu / (target_s / 2)))
-    si2 = max(1, int(si * ti / (target_s / 2)))
-    tu = timed("user", su2)
-    ti = timed("item", si2)
-    t_gram = 0.0
-    if prep["implicit"]:
-        t0 = time.perf_counter()
-        o.gram(prep["uf"])
-        o.gram(prep["itf"])
-        t_gram = time.perf_counter() - t0
-    iter_s = tu * su2 + ti * si2 + t_gram
-    return {"value": 1.0 / iter_s, "unit": "iterations/s", "cores": prep["cores"], "kind": "port",
-            "sample": f"every {su2}th user row + every {si2}th item row of the full workload "
-                      f"({tu + ti:.1f}s timed), scaled to one iteration; C/OpenMP restatement of MLlib ALS (not Spark)"}
-
-
-def cpu_baseline_sample(nu, ni, nnz, k, implicit, target_s=12.0, d_coo=None):
-    return cpu_baseline_run(cpu_baseline_prepare(nu, ni, nnz, k, implicit, d_coo=d_coo), target_s)
+        m.recommend(users[q:q + 1], 10)
+        lat.append(time.perf_counter() - t0)
+    out["recommend"]["single_query_ms"] = float(np.median(lat) * 1e3)
+    out["recommend"]["single_query_hbm_floor_ms"] = scan_bytes / (peaks["hbm"] * 1e9) * 1e3
+    return out
 
 
 def main():
@@ -182,6 +330,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("PIO_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-topk", action="store_true")
     args = ap.parse_args()
     nu, ni, nnz, k, implicit = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -196,28 +346,9 @@ def main():
 
     if args.impl == "reference":
         if rank != 0:
-            return
-        import pio_b200  # noqa: F401
-        # one step = one bounded sample of the workload (same ratings, strided destination rows); the ratings and
-        # both CSR orientations are built once; the per-step budget shrinks with the step count so that the whole
-        # run stays within a few minutes
-        prep = cpu_baseline_prepare(nu, ni, nnz, k, implicit)
-        per_step = min(16.0, max(2.0, 90.0 / (args.warmup + args.steps)))
-        vals = []
-        cb = None
-        for s in range(args.warmup + args.steps):
-            cb = cpu_baseline_run(prep, target_s=per_step)
-            if s >= args.warmup:
-                vals.append(cb["value"])
-        v = float(np.mean(vals))
-        cb["value"] = v
-        print(json.dumps({"impl": "reference", "metric": "ALS iterations/sec", "value": v, "unit": "iterations/s",
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f64 accumulate / f32 storage", "data": "synthetic",
-                          "config": config, "cpu_baseline": cb,
-                          "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
+            return 0
+        reference_arm(args, nu, ni, nnz, k, implicit, config)
+        return 0
 
     import torch
     import pio_b200  # noqa: F401
@@ -264,18 +395,30 @@ def main():
     wall_s = time.perf_counter() - t0
     clocks = sampler.stop()
     st = m.stats()
+    ph = m.phase_ms()
     dev_ms = st["last_run_ms"]
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([dev_ms, st["last_solve_ms"], st["last_gram_ms"], st["last_comm_ms"], wall_s * 1e3],
-                         dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, st["last_solve_ms"], st["last_gram_ms"], st["last_comm_ms"], wall_s * 1e3,
+                          ph["user_solve_ms"], ph["item_solve_ms"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, solve_ms, gram_ms, comm_ms, wall_ms = t.tolist()
+        dev_ms, solve_ms, gram_ms, comm_ms, wall_ms, ph["user_solve_ms"], ph["item_solve_ms"] = t.tolist()
     else:
         solve_ms, gram_ms, comm_ms, wall_ms = st["last_solve_ms"], st["last_gram_ms"], st["last_comm_ms"], wall_s * 1e3
     launches = st["kernel_launches"] - l0["kernel_launches"]
     solve_launches = st["solve_launches"] - l0["solve_launches"]
     value = args.steps / (dev_ms / 1e3)
+
+    # factors after W + K iterations (checksum; source of the parity iteration); then one more iteration for parity
+    want_parity = not args.no_parity
+    uf_T = itf_T = uf_T1 = itf_T1 = uh = ih = None
+    if rank == 0:
+        uf_T, itf_T, uh, ih = m.get_factors()
+    checksum = factor_checksum(uf_T, itf_T) if rank == 0 else None
+    if want_parity:
+        m.run(1)
+        if rank == 0:
+            uf_T1, itf_T1, _, _ = m.get_factors()
 
     # ---- end to end through the C ABI with host buffers ------------------------------------
     e2e = None
@@ -292,37 +435,52 @@ def main():
                               world_size=world, world_rank=rank, nccl_id=None if world == 1 else nccl_id_2(native, rank, world),
                               init_mode=native.INIT_HASH)
         m2.train(hu.numpy(), hi.numpy(), hr.numpy(), 1, dedup=dedup, out_user=out_u.numpy(), out_item=out_i.numpy())  # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        m2.train(hu.numpy(), hi.numpy(), hr.numpy(), args.steps, dedup=dedup, out_user=out_u.numpy(), out_item=out_i.numpy())
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+
+        def timed_train(a, b, c, ou, oi):
+            barrier()
+            t0 = time.perf_counter()
+            m2.train(a, b, c, args.steps, dedup=dedup, out_user=ou, out_item=oi)
+            barrier()
+            s = time.perf_counter() - t0
+            if world > 1:
+                import torch.distributed as dist
+                t = torch.tensor([s], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                s = float(t.item())
+            return s
+
+        e2e_s = timed_train(hu.numpy(), hi.numpy(), hr.numpy(), out_u.numpy(), out_i.numpy())
         st2 = m2.stats()
+        # the same call with ordinary pageable arrays (what a JNI caller holding GetPrimitiveArrayCritical arrays passes)
+        pu, pi_, pr = (np.array(x.numpy(), copy=True) for x in (hu, hi, hr))
+        pou, poi = np.empty((nu, k), np.float32), np.empty((ni, k), np.float32)
+        e2e_pageable_s = timed_train(pu, pi_, pr, pou, poi)
+        del pu, pi_, pr, pou, poi
+        h2d_call, d2h_call = 12 * nnz, 4 * (nu + ni) * k + (nu + ni)
         e2e = {"value": args.steps / e2e_s, "unit": "iterations/s", "seconds_per_train_call": e2e_s,
                "iterations_per_call": args.steps,
-               "h2d_bytes_per_step": 12 * nnz, "d2h_bytes_per_step": 4 * (nu + ni) * k + (nu + ni),
+               "h2d_bytes_per_step": h2d_call / args.steps, "d2h_bytes_per_step": d2h_call / args.steps,
+               "h2d_bytes_per_call": h2d_call, "d2h_bytes_per_call": d2h_call,
+               "host_memory": "pinned", "value_pageable_host_memory": args.steps / e2e_pageable_s,
                "ingest_ms": st2["last_ingest_ms"], "run_ms": st2["last_run_ms"],
-               "note": "one step = one pio_als_train call: H2D COO + ingest + K iterations + D2H factors"}
+               "note": "one pio_als_train call = H2D of the COO triplets + ingest + K iterations + D2H of the factors; the "
+                       "copies happen once per call, so bytes per step = bytes per call / K"}
         m2.close()
+        del hu, hi, hr, out_u, out_i
 
     if rank != 0:
-        return
+        return 0
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     # One iteration = item half-step + user half-step; each is (YtY) + one solve launch for the rows up to the
     # heavy-row threshold (+ a part launch and a finish launch for longer rows).  The dominant kernel is the solve
     # launch of the slower half-step; its time is the CUDA-event time of that half-step's solve launches (measured
     # inside pio_als_run on the launching stream), its work the algorithmic FLOPs / bytes of that side.
-    hbm_peak, bf16_peak, peak_src = measured_peaks()
-    nua = st["n_users_active"] if world == 1 else nu
-    nia = st["n_items_active"] if world == 1 else ni
+    peaks = measured_peaks()
+    hbm_peak, bf16_peak, peak_src = peaks["hbm"], peaks["bf16"], peaks["src"]
+    nua = int(uh.sum())
+    nia = int(ih.sum())
     b_alg, f_solve, f_gram = algorithmic_work(nua, nia, nnz_eff, k, implicit)
-    ph = m.phase_ms()
     side_flops = {"user": 2 * nnz_eff * (k * (k + 1) + 2 * k) / 2 + nua * (k ** 3 / 3 + 2 * k * k),
                   "item": 2 * nnz_eff * (k * (k + 1) + 2 * k) / 2 + nia * (k ** 3 / 3 + 2 * k * k)}
     side_bytes = {"user": 8 * nnz_eff + 4 * nua * k + 4 * nia * k, "item": 8 * nnz_eff + 4 * nia * k + 4 * nua * k}
@@ -331,21 +489,21 @@ def main():
     side_tc = {sd: side_kernel[sd] != "fp32" for sd in side_kernel}   # Gramian on tensor cores (tcgen05 or mma.sync)
     kernel_names = {"fp32": "als_solve_kernel (gather + FP32 Gramian + warp Cholesky)",
                     "tcgen05": "tc::als_solve_tc_kernel (tcgen05 split-TF32 Gramian + warp Cholesky)",
-                    "mma": "mm::als_solve_mma_kernel (one warp per row: mma.sync 3xTF32 Gramian + warp Cholesky)"}
-    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+                    "mma": "mm::als_solve_mma_kernel (mma.sync 3xTF32 Gramian + lockstep warp Cholesky)"}
+    fp32_peak = peaks["fp32"]
     tf32_peak = bf16_peak / 2.0
     split_peak = tf32_peak / 3.0   # an fp32-class product costs three TF32 MMAs (hi*hi + lo*hi + hi*lo)
 
     def side_obj(sd):
         tf = side_flops[sd] / (side_ms[sd] / 1e3) / 1e12 / max(world, 1)
         gb = side_bytes[sd] / (side_ms[sd] / 1e3) / 1e9 / max(world, 1)
-        o = {"kernel": kernel_names[side_kernel[sd]] + f", {sd} half-step",
-             "ms_per_launch": side_ms[sd], "algorithmic_flops": side_flops[sd], "algorithmic_bytes": side_bytes[sd],
-             "achieved_tflops": tf, "achieved_gbs": gb, "frac_of_fp32_fma_peak": tf / fp32_peak,
-             "frac_of_hbm_peak": gb / hbm_peak}
+        o_ = {"kernel": kernel_names[side_kernel[sd]] + f", {sd} half-step",
+              "ms_per_launch": side_ms[sd], "algorithmic_flops": side_flops[sd], "algorithmic_bytes": side_bytes[sd],
+              "achieved_tflops": tf, "achieved_gbs": gb, "frac_of_fp32_fma_peak": tf / fp32_peak,
+              "frac_of_hbm_peak": gb / hbm_peak}
         if side_tc[sd]:
-            o["frac_of_split_tf32_tensor_peak"] = tf / split_peak
-        return o
+            o_["frac_of_split_tf32_tensor_peak"] = tf / split_peak
+        return o_
 
     dom = "user" if side_ms["user"] >= side_ms["item"] else "item"
     other = "item" if dom == "user" else "user"
@@ -356,10 +514,10 @@ def main():
         "achieved": d["achieved_tflops"], "peak": fp32_peak if not side_tc[dom] else split_peak, "unit": "TFLOP/s",
         "frac": d["achieved_tflops"] / (fp32_peak if not side_tc[dom] else split_peak),
         "frac_of_fp32_fma_peak": d["achieved_tflops"] / fp32_peak,
-        "peak_source": ("nominal 148 SM x 128 FFMA lanes x 2 x 1.965 GHz (CUDA-core FP32; MEASURED_PEAKS.json has no "
-                        "FP32 entry)") if not side_tc[dom] else
-                       f"{peak_src} dense bf16 / 2 = tf32 MMA rate, / 3 because an fp32-class product is three TF32 MMAs; "
-                       "the kernel is paced by its warp-level Cholesky and fragment loads, not by the tensor pipe",
+        "fp32_fma_peak": fp32_peak, "fp32_fma_peak_source": peaks["fp32_src"],
+        "mma_sync_tf32_peak_tflops": peaks["mma_tf32"],
+        "peak_source": peaks["fp32_src"] if not side_tc[dom] else
+                       f"{peak_src} dense bf16 / 2 = tf32 MMA rate, / 3 because an fp32-class product is three TF32 MMAs",
         "ms_per_launch": d["ms_per_launch"],
         "traffic": traffic_from_profiles(args.workload),
         "traffic_unit": "dram bytes of this launch, from the committed ncu --set full capture (profiles/traffic.json)",
@@ -377,13 +535,41 @@ def main():
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
            "wall_ms_per_step": wall_ms / args.steps, "ingest_ms": ingest_ms, "nnz_after_dedup": int(nnz_eff),
+           "factor_checksum": checksum,
+           "factor_checksum_note": f"crc32(user factors) || crc32(item factors) after {args.warmup}+{args.steps} iterations "
+                                   "from the hash initialisation: the same at every GPU count (sharded runs are bit-identical)",
            "roofline": roofline}
     if e2e:
         out["e2e"] = e2e
-    if not args.no_cpu_baseline and args.gpus == 1:
+
+    rc = 0
+    need_host = (want_parity or (not args.no_cpu_baseline and args.gpus == 1) or not args.no_topk)
+    if need_host:
+        o, cores = load_oracle()
+    if want_parity or (not args.no_cpu_baseline and args.gpus == 1):
         coo = (du.cpu().numpy(), di.cpu().numpy(), dr.cpu().numpy())
-        out["cpu_baseline"] = cpu_baseline_sample(nu, ni, nnz, k, implicit, d_coo=coo)
+        del du, di, dr
+        prob = build_host_problem(o, nu, ni, k, implicit, coo)
+        del coo
+        if want_parity:
+            par = parity_sample(o, prob, uf_T, itf_T1, uf_T1)
+            par["host_nnz_after_dedup"] = prob["nnz"]
+            par["ok"] = bool(par["ok"] and prob["nnz"] == int(nnz_eff))
+            out["parity"] = par
+            if not par["ok"]:
+                rc = 3
+        if not args.no_cpu_baseline and args.gpus == 1:
+            cu, ci = np.array(uf_T, copy=True), np.array(itf_T, copy=True)
+            out["cpu_baseline"] = cpu_baseline_steps(o, cores, prob, cu, ci, n_steps=1, n_warm=0, budget_s=30.0)
+        del prob
+    if not args.no_topk and args.gpus == 1:
+        try:
+            out["topk"] = topk_bench(native, o, cores, m, nu, ni, k, uf_T, itf_T, uh, ih, peaks, dev)
+        except Exception as e:   # a scoring failure must not hide the training line
+            out["topk"] = {"error": repr(e)}
+            rc = rc or 4
     print(json.dumps(out))
+    return rc
 
 
 def nccl_id_2(native, rank, world):
@@ -398,10 +584,11 @@ def nccl_id_2(native, rank, world):
 
 
 if __name__ == "__main__":
-    main()
+    rc = main()
     try:   # leave the torch.distributed group cleanly (no teardown warning after the JSON line)
         import torch.distributed as _dist
         if _dist.is_available() and _dist.is_initialized():
             _dist.destroy_process_group()
     except Exception:
         pass
+    sys.exit(rc or 0)

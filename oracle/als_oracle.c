@@ -154,6 +154,42 @@ ORACLE_API void oracle_gram(int32_t n_rows, int k, const float *f, const uint8_t
 /* no factor for them).  Returns the number of rows whose Cholesky     */
 /* failed (0 on success).                                              */
 /* ------------------------------------------------------------------ */
+/* normal equation + Cholesky solve of ONE destination row; scratch ata/atb/da are
+ * caller-provided.  Returns 1 if the row was solved into x, 0 if it has no ratings, -1 if dppsv failed. */
+static int solve_row(int k, int64_t b, int64_t e, const int32_t *idx, const float *val, const float *src,
+                     double lambda, int implicit, double alpha, const double *yty, double *ata, double *atb,
+                     double *da, float *x) {
+  const int tri = k * (k + 1) / 2;
+  if (e == b) return 0;
+  if (implicit && yty) memcpy(ata, yty, sizeof(double) * (size_t)tri);
+  else memset(ata, 0, sizeof(double) * (size_t)tri);
+  memset(atb, 0, sizeof(double) * (size_t)k);
+  int64_t n = 0;
+  for (int64_t p = b; p < e; ++p) {
+    const float *y = src + (size_t)idx[p] * k;
+    for (int i = 0; i < k; ++i) da[i] = (double)y[i];
+    const double rating = (double)val[p];
+    if (implicit) {
+      const double c1 = alpha * fabs(rating);
+      dspr_upper(k, c1, da, ata);
+      if (rating > 0.0) {
+        const double w = 1.0 + c1;
+        for (int i = 0; i < k; ++i) atb[i] += w * da[i];
+        n += 1;
+      }
+    } else {
+      dspr_upper(k, 1.0, da, ata);
+      for (int i = 0; i < k; ++i) atb[i] += rating * da[i];
+      n += 1;
+    }
+  }
+  const double ridge = lambda * (double)n;
+  for (int j = 0; j < k; ++j) ata[(size_t)j * (j + 1) / 2 + j] += ridge;
+  if (dppsv_upper(k, ata, atb) != 0) return -1;
+  for (int i = 0; i < k; ++i) x[i] = (float)atb[i];
+  return 1;
+}
+
 ORACLE_API int oracle_als_half_step(int32_t n_dst, int k, const int64_t *ptr,
                                     const int32_t *idx, const float *val,
                                     const float *src, float *dst, double lambda,
@@ -172,44 +208,95 @@ ORACLE_API int oracle_als_half_step(int32_t n_dst, int k, const int64_t *ptr,
     double *da = (double *)malloc(sizeof(double) * (size_t)k);
 #pragma omp for schedule(dynamic, 16)
     for (int32_t r = row_begin; r < row_end; r += row_stride) {
-      const int64_t b = ptr[r], e = ptr[r + 1];
-      if (e == b) continue;
-      if (implicit && yty) memcpy(ata, yty, sizeof(double) * (size_t)tri);
-      else memset(ata, 0, sizeof(double) * (size_t)tri);
-      memset(atb, 0, sizeof(double) * (size_t)k);
-      int64_t n = 0;
-      for (int64_t p = b; p < e; ++p) {
-        const float *y = src + (size_t)idx[p] * k;
-        for (int i = 0; i < k; ++i) da[i] = (double)y[i];
-        const double rating = (double)val[p];
-        if (implicit) {
-          const double c1 = alpha * fabs(rating);
-          dspr_upper(k, c1, da, ata);
-          if (rating > 0.0) {
-            const double w = 1.0 + c1;
-            for (int i = 0; i < k; ++i) atb[i] += w * da[i];
-            n += 1;
-          }
-        } else {
-          dspr_upper(k, 1.0, da, ata);
-          for (int i = 0; i < k; ++i) atb[i] += rating * da[i];
-          n += 1;
-        }
-      }
-      const double ridge = lambda * (double)n;
-      for (int j = 0; j < k; ++j) ata[(size_t)j * (j + 1) / 2 + j] += ridge;
-      if (dppsv_upper(k, ata, atb) != 0) {
+      if (solve_row(k, ptr[r], ptr[r + 1], idx, val, src, lambda, implicit, alpha, yty, ata, atb, da,
+                    dst + (size_t)r * k) < 0)
         fails += 1;
-        continue;
-      }
-      float *x = dst + (size_t)r * k;
-      for (int i = 0; i < k; ++i) x[i] = (float)atb[i];
     }
     free(ata);
     free(atb);
     free(da);
   }
   return fails;
+}
+
+/* Same arithmetic for an explicit LIST of destination rows (bench.py's parity sample of the benchmarked workload):
+ * out is n_list x k, row j = the solution of destination row rows[j] (left untouched if that row has no ratings). */
+ORACLE_API int oracle_als_half_step_rows(int k, const int64_t *ptr, const int32_t *idx, const float *val,
+                                         const float *src, double lambda, int implicit, double alpha,
+                                         const double *yty, const int32_t *rows, int32_t n_list, float *out) {
+  const int tri = k * (k + 1) / 2;
+  int fails = 0;
+#pragma omp parallel reduction(+ : fails)
+  {
+    double *ata = (double *)malloc(sizeof(double) * (size_t)tri);
+    double *atb = (double *)malloc(sizeof(double) * (size_t)k);
+    double *da = (double *)malloc(sizeof(double) * (size_t)k);
+#pragma omp for schedule(dynamic, 1)
+    for (int32_t j = 0; j < n_list; ++j) {
+      const int32_t r = rows[j];
+      if (solve_row(k, ptr[r], ptr[r + 1], idx, val, src, lambda, implicit, alpha, yty, ata, atb, da,
+                    out + (size_t)j * k) < 0)
+        fails += 1;
+    }
+    free(ata);
+    free(atb);
+    free(da);
+  }
+  return fails;
+}
+
+/* reduceByKey(_ + _) on a CSR (rows in input order, oracle_csr_build): inside every row the entries are ordered by
+ * column, ties in input order, and repeated columns are folded left to right in fp32 -- the same result as
+ * als_oracle.py dedup_coo(mode="sum") (examples/scala-parallel-similarproduct/multi-events-multi-algos/src/main/
+ * scala/ALSAlgorithm.scala:106), fast enough for the 100 M-rating bench workload.  Compacts col/val in place,
+ * rewrites ptr, returns the new nnz. */
+typedef struct { int32_t c; int32_t pos; float v; } dd_ent;
+static int dd_cmp(const void *a, const void *b) {
+  const dd_ent *x = (const dd_ent *)a, *y = (const dd_ent *)b;
+  if (x->c != y->c) return x->c < y->c ? -1 : 1;
+  return x->pos < y->pos ? -1 : (x->pos > y->pos);
+}
+ORACLE_API int64_t oracle_csr_dedup_sum(int32_t n_rows, int64_t *ptr, int32_t *col, float *val) {
+  int64_t *newlen = (int64_t *)calloc((size_t)n_rows + 1, sizeof(int64_t));
+  if (!newlen) return -2;
+#pragma omp parallel
+  {
+    dd_ent *buf = NULL;
+    int64_t cap = 0;
+#pragma omp for schedule(dynamic, 64)
+    for (int32_t r = 0; r < n_rows; ++r) {
+      const int64_t b = ptr[r], n = ptr[r + 1] - b;
+      if (n > cap) {
+        free(buf);
+        cap = n * 2;
+        buf = (dd_ent *)malloc(sizeof(dd_ent) * (size_t)cap);
+      }
+      for (int64_t t = 0; t < n; ++t) { buf[t].c = col[b + t]; buf[t].pos = (int32_t)t; buf[t].v = val[b + t]; }
+      qsort(buf, (size_t)n, sizeof(dd_ent), dd_cmp);
+      int64_t o = 0;
+      for (int64_t t = 0; t < n;) {
+        float acc = 0.f;
+        int64_t u = t;
+        while (u < n && buf[u].c == buf[t].c) { acc = acc + buf[u].v; ++u; }
+        col[b + o] = buf[t].c;
+        val[b + o] = acc;
+        ++o;
+        t = u;
+      }
+      newlen[r] = o;
+    }
+    free(buf);
+  }
+  int64_t w = 0;
+  for (int32_t r = 0; r < n_rows; ++r) {
+    const int64_t b = ptr[r], n = newlen[r];
+    if (w != b) { memmove(col + w, col + b, sizeof(int32_t) * (size_t)n); memmove(val + w, val + b, sizeof(float) * (size_t)n); }
+    ptr[r] = w;
+    w += n;
+  }
+  ptr[n_rows] = w;
+  free(newlen);
+  return w;
 }
 
 /* ------------------------------------------------------------------ */

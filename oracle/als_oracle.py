@@ -106,6 +106,39 @@ def half_step(ptr, idx, val, src, dst, lam, implicit, alpha, yty=None, row_begin
         yp, C.c_int32(row_begin), C.c_int32(row_end), C.c_int32(row_stride)))
 
 
+def half_step_rows(ptr, idx, val, src, rows, lam, implicit, alpha, yty=None):
+    """Solutions of the listed destination rows (len(rows) x k) from src factors; rows without ratings stay zero."""
+    k = src.shape[1]
+    rows = np.ascontiguousarray(rows, np.int32)
+    out = np.zeros((rows.shape[0], k), np.float32)
+    assert src.dtype == np.float32 and src.flags.c_contiguous
+    yp = None if yty is None else _p(np.ascontiguousarray(yty, np.float64), C.c_double)
+    fails = int(lib().oracle_als_half_step_rows(
+        C.c_int(k), _p(ptr, C.c_int64), _p(idx, C.c_int32), _p(val, C.c_float), _p(src, C.c_float), C.c_double(lam),
+        C.c_int(int(implicit)), C.c_double(alpha), yp, _p(rows, C.c_int32), C.c_int32(rows.shape[0]),
+        _p(out, C.c_float)))
+    return out, fails
+
+
+def csr_dedup_sum(ptr, col, val):
+    """reduceByKey(_ + _) inside every CSR row (same result as dedup_coo(mode="sum")); returns new (ptr, col, val)."""
+    ptr = np.array(ptr, np.int64, copy=True)
+    col = np.array(col, np.int32, copy=True)
+    val = np.array(val, np.float32, copy=True)
+    lib().oracle_csr_dedup_sum.restype = C.c_int64
+    n = int(lib().oracle_csr_dedup_sum(C.c_int32(ptr.shape[0] - 1), _p(ptr, C.c_int64), _p(col, C.c_int32),
+                                       _p(val, C.c_float)))
+    if n < 0:
+        raise MemoryError("oracle_csr_dedup_sum")
+    return ptr, col[:n], val[:n]
+
+
+def csr_rows(ptr):
+    """Row index of every CSR entry (int32)."""
+    n = ptr.shape[0] - 1
+    return np.repeat(np.arange(n, dtype=np.int32), np.diff(ptr))
+
+
 def als_train(n_users, n_items, user, item, rating, rank, iters, lam, implicit, alpha, user_init, item_init):
     """Full MLlib-style training. Returns (user_f, item_f, user_has, item_has)."""
     user = np.ascontiguousarray(user, np.int32)

@@ -164,3 +164,31 @@ def test_c_oracle_matches_stored_fixtures(oracle):
         for got, want in ((uf, z[n + "/user_factors"]), (itf, z[n + "/item_factors"])):
             err = np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want)
             assert err <= 2e-6, (n, err)
+
+
+def test_csr_dedup_sum_equals_dedup_coo(oracle):
+    """oracle_csr_dedup_sum (used by bench.py's parity sample at 100 M ratings) == dedup_coo(mode="sum")."""
+    rng = np.random.default_rng(0)
+    nu, ni, nnz = 300, 40, 6000
+    u = rng.integers(0, nu, nnz).astype(np.int32)
+    i = rng.integers(0, ni, nnz).astype(np.int32)
+    r = (rng.integers(1, 9, nnz) + rng.random(nnz)).astype(np.float32)
+    uu, ii, rr = oracle.dedup_coo(u, i, r, "sum")
+    ptr, col, val = oracle.csr_dedup_sum(*oracle.csr_build(nu, u, i, r))
+    assert np.array_equal(oracle.csr_rows(ptr), uu) and np.array_equal(col, ii) and np.array_equal(val, rr)
+    assert ptr[-1] == rr.shape[0] < nnz
+
+
+@pytest.mark.parametrize("implicit", [False, True])
+def test_half_step_rows_equals_half_step(oracle, implicit):
+    rng = np.random.default_rng(1)
+    nu, ni, nnz, k = 200, 50, 3000, 8
+    u, i, r = _problem(nu, ni, nnz, 9, implicit)
+    ptr, col, val = oracle.csr_build(nu, u, i, r)
+    src = rng.standard_normal((ni, k)).astype(np.float32)
+    dst = np.zeros((nu, k), np.float32)
+    yty = oracle.gram(src) if implicit else None
+    assert oracle.half_step(ptr, col, val, src, dst, 0.05, implicit, 1.0, yty) == 0
+    rows = np.array([0, 5, 17, 199], np.int32)
+    out, fails = oracle.half_step_rows(ptr, col, val, src, rows, 0.05, implicit, 1.0, yty)
+    assert fails == 0 and np.array_equal(out, dst[rows])
