@@ -154,7 +154,14 @@ def load_oracle():
         import ctypes
         import shutil
         if shutil.which("gcc"):
-            so = o._SO.parent / "libals_oracle_native.so"
+            # -march=native code must not travel between machines: key the file by this host's CPU flags
+            import hashlib
+            flags = ""
+            try:
+                flags = next(ln for ln in open("/proc/cpuinfo") if ln.startswith("flags"))
+            except Exception:
+                pass
+            so = o._SO.parent / f"libals_oracle_native_{hashlib.sha1(flags.encode()).hexdigest()[:10]}.so"
             if not so.exists() or so.stat().st_mtime < o._SRC.stat().st_mtime:
                 subprocess.run(["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-fvisibility=hidden",
                                 "-o", str(so), str(o._SRC), "-lm"], check=True)
@@ -489,7 +496,8 @@ def main():
     side_tc = {sd: side_kernel[sd] != "fp32" for sd in side_kernel}   # Gramian on tensor cores (tcgen05 or mma.sync)
     kernel_names = {"fp32": "als_solve_kernel (gather + FP32 Gramian + warp Cholesky)",
                     "tcgen05": "tc::als_solve_tc_kernel (tcgen05 split-TF32 Gramian + warp Cholesky)",
-                    "mma": "mm::als_solve_mma_kernel (mma.sync 3xTF32 Gramian + lockstep warp Cholesky)"}
+                    "mma": "mm::als_solve_mma_kernel (one warp per row: mma.sync 3xTF32 Gramian + warp Cholesky)",
+                    "pair": "pr::als_solve_pair_kernel (two rows per warp: mma.sync 3xTF32 Gramian + lockstep Cholesky)"}
     fp32_peak = peaks["fp32"]
     tf32_peak = bf16_peak / 2.0
     split_peak = tf32_peak / 3.0   # an fp32-class product costs three TF32 MMAs (hi*hi + lo*hi + hi*lo)

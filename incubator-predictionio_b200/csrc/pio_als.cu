@@ -20,6 +20,7 @@
 
 #include "als_kernels.cuh"
 #include "als_mma_kernel.cuh"
+#include "als_pair_kernel.cuh"
 // the tcgen05 half-step kernel; the header is parametrised by the role partition of its sixteen warps.  Measured at C2:
 // 2 gather + 5 converter warps + 2 solve teams (below) beats 1 + 2 + 3 teams on long rows AND on short rows (user side
 // 38 ms vs 86 ms: two converter warps cannot feed the MMAs), so only this partition is instantiated.
@@ -45,6 +46,8 @@ constexpr int HEAVY_T = 4096;     // rows with more ratings than this are cut in
 constexpr int HEAVY_T_TC = 8192;  // same threshold when the tensor-core path handles the shorter rows
 constexpr int TC_TILE_ROWS = 1 << 20;  // split mode: rows whose normal equations are buffered at once (9.1 KB per row)
 constexpr int PART = 2016;        // ratings per part (multiple of every CH and of the tensor-core stage size 24)
+constexpr int PAIR_SEG_T = 1024;  // pair kernel (als_pair_kernel.cuh): rows with more ratings than this are cut into parts ...
+constexpr int PAIR_PART = 512;    // ... of this many ratings: two-level summation keeps long rows inside the parity bound
 
 static thread_local std::string g_create_error;
 
@@ -329,6 +332,8 @@ struct Side {
   int n_active = 0, n_heavy = 0;
   bool use_tc = false;       // this side's short rows go through the tensor-core kernel (decided from GLOBAL counts: every rank agrees)
   int heavy_t = 0;           // rows with more ratings than this are cut into parts
+  int part_len = 0;          // ratings per part
+  bool use_pair = false;     // rows and parts of this side run on the pair kernel (rank 33..64, mma.sync + lockstep solve)
   // parts of the n_heavy longest local rows
   long long* part_beg = nullptr;
   long long* part_end = nullptr;
@@ -361,7 +366,9 @@ struct pio_als_handle {
   float* d_dbg = nullptr;     // PIO_ALS_TC_DEBUG=1: A/b dump of the last tensor-core half-step
   size_t dbg_rows = 0;
   bool use_tc = false;        // rank in 33..64 and PIO_ALS_TC != 0
-  bool use_mma = true;        // PIO_ALS_MMA=0: FP32 kernel instead of the mma.sync kernel for short rows of rank 33..64
+  bool use_mma = true;        // PIO_ALS_MMA=0: FP32 kernel instead of the mma.sync kernels for rank 33..64
+  bool use_pair = true;       // PIO_ALS_MMA=1: round-1 one-warp-per-row mma.sync kernel instead of the pair kernel
+  int pair_seg_t = PAIR_SEG_T, pair_part = PAIR_PART;   // PIO_ALS_SEG_T / PIO_ALS_PART
   bool tc_split = false;      // PIO_ALS_TC_SPLIT=1: the tensor-core kernel only accumulates, a second kernel solves (measured: no gain)
   float* tc_out = nullptr;    // split mode: normal equations of one tile of rows ([rows][ASLOT + KP])
   size_t tc_out_rows = 0;
@@ -485,9 +492,13 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
   // kernel choice from global numbers only (ratings after dedup / rows of this side), so that every rank of a sharded
   // run and the single-GPU run take the same path for the same row
   row.use_tc = h->use_tc && h->KP == 64 && row.n > 0 && (double)nnz / (double)row.n >= h->tc_min_deg;
-  // one warp (mma kernel) or one accumulator slot (tcgen05 kernel) carries a whole row: rows up to 8192 ratings stay
-  // whole on those paths; the FP32 kernel (other ranks) shares a CTA between NG rows and cuts at 4096
-  row.heavy_t = (row.use_tc || (h->KP == 64 && h->use_mma)) ? HEAVY_T_TC : HEAVY_T;
+  row.use_pair = !row.use_tc && h->KP == 64 && h->use_mma && h->use_pair;
+  // one warp (mma kernels) or one accumulator slot (tcgen05 kernel) carries a whole row.  Pair kernel: rows up to 1024
+  // ratings stay whole, longer rows become 512-rating parts of the same kernel (two-level summation); round-1 mma /
+  // tcgen05 kernels: rows up to 8192 ratings whole, longer rows as 2016-rating parts on the FP32 kernel; FP32 kernel
+  // (other ranks): cut at 4096
+  row.heavy_t = row.use_pair ? h->pair_seg_t : (row.use_tc || (h->KP == 64 && h->use_mma)) ? HEAVY_T_TC : HEAVY_T;
+  row.part_len = row.use_pair ? h->pair_part : PART;
   local_rows_kernel<<<nblk(row.R + 1, 256), 256, 0, st>>>(ptr_full, rk * row.R, row.R, be[0], row.inv, row.deg,
                                                            row.npos, h->cfg.implicit_prefs, row.ptr, row.nreg,
                                                            h->d_counts, row.heavy_t);
@@ -499,7 +510,7 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
   row.n_heavy = counts[1];
   dfree(h, ptr_full);
   if (row.n_heavy > 0) {
-    // cut the heavy rows (local rows [0, n_heavy), longest first) into parts of PART ratings
+    // cut the heavy rows (local rows [0, n_heavy), longest first) into parts of part_len ratings
     std::vector<long long> hp((size_t)row.n_heavy + 1);
     CK(h, cudaMemcpyAsync(hp.data(), row.ptr, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
@@ -507,9 +518,9 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
     std::vector<int> rpp((size_t)row.n_heavy + 1);
     for (int r = 0; r < row.n_heavy; ++r) {
       rpp[r] = (int)pb.size();
-      for (long long b = hp[r]; b < hp[r + 1]; b += PART) {
+      for (long long b = hp[r]; b < hp[r + 1]; b += row.part_len) {
         pb.push_back(b);
-        pe.push_back(b + PART < hp[r + 1] ? b + PART : hp[r + 1]);
+        pe.push_back(b + row.part_len < hp[r + 1] ? b + row.part_len : hp[r + 1]);
       }
     }
     rpp[row.n_heavy] = (int)pb.size();
@@ -772,6 +783,63 @@ static cudaError_t launch_tc(pio_als_handle* h, Side& dst, const SolveParams& p,
   return e;
 }
 
+// Rank 33..64, pair kernel (als_pair_kernel.cuh): persistent one-warp CTAs, twelve per SM.  Long rows first (their
+// 512-rating parts as work items, then the finish kernel), then the rows that stay whole.
+static cudaError_t launch_pair(pio_als_handle* h, Side& dst, const SolveParams& p0, bool imp) {
+  cudaError_t e = cudaSuccess;
+  static bool attr_set[64] = {};
+  const size_t smem = pr::smem_bytes(1);
+  if (h->cfg.device < 64 && !attr_set[h->cfg.device]) {
+    const void* ks[4] = {(const void*)pr::als_solve_pair_kernel<true>, (const void*)pr::als_solve_pair_kernel<false>,
+                         (const void*)pr::als_finish_pair_kernel<true>, (const void*)pr::als_finish_pair_kernel<false>};
+    for (const void* kf : ks) {
+      if ((e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
+    }
+    attr_set[h->cfg.device] = true;
+  }
+  const int max_ctas = 12 * h->sm_count;
+  auto sk = imp ? pr::als_solve_pair_kernel<true> : pr::als_solve_pair_kernel<false>;
+  if (dst.n_heavy > 0) {
+    if (!dst.partial) {
+      if ((e = cudaMallocAsync((void**)&dst.partial, sizeof(float) * (size_t)dst.n_parts * pr::PART_FLOATS, h->stream)) != cudaSuccess) return e;
+    }
+    SolveParams pp = p0;
+    pp.wl_beg = dst.part_beg;
+    pp.wl_end = dst.part_end;
+    pp.partial = dst.partial;
+    pp.n_items = dst.n_parts;
+    pp.row_begin = 0;
+    pp.row_end = dst.n_heavy;
+    int grid = (dst.n_parts + 1) / 2;
+    if (grid > max_ctas) grid = max_ctas;
+    sk<<<grid, 32, smem, h->stream>>>(pp, dst.n_parts);
+    LAUNCHED(h);
+    ++h->st.solve_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    auto fk = imp ? pr::als_finish_pair_kernel<true> : pr::als_finish_pair_kernel<false>;
+    int fgrid = (dst.n_heavy + 1) / 2;
+    if (fgrid > max_ctas) fgrid = max_ctas;
+    fk<<<fgrid, 32, smem, h->stream>>>(pp, dst.row_part_ptr, dst.n_heavy);
+    LAUNCHED(h);
+    ++h->st.solve_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  const int nlight = dst.n_active - dst.n_heavy;
+  if (nlight > 0) {
+    SolveParams p = p0;
+    p.row_begin = dst.n_heavy;
+    p.row_end = dst.n_active;
+    int grid = (nlight + 1) / 2;
+    if (grid > max_ctas) grid = max_ctas;
+    sk<<<grid, 32, smem, h->stream>>>(p, nlight);
+    LAUNCHED(h);
+    ++h->st.solve_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  return e;
+}
+
 template <class Cfg>
 static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& src) {
   SolveParams p;
@@ -793,6 +861,7 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
   p.wl_end = nullptr;
   p.partial = nullptr;
   p.n_items = 0;
+  if (dst.use_pair && Cfg::KP == 64) return launch_pair(h, dst, p, imp);
   // very long rows: their parts run as ordinary light batch items that emit partial normal equations
   if (dst.n_heavy > 0) {
     if (!dst.partial) {
@@ -982,7 +1051,12 @@ static int create_common(pio_als_handle* h) {
     h->tc_min_deg = (env && env[0] == '1') ? 0.0 : 256.0;
     if (const char* md = getenv("PIO_ALS_TC_MIN_DEG")) h->tc_min_deg = atof(md);
     if (const char* sp = getenv("PIO_ALS_TC_SPLIT")) h->tc_split = sp[0] == '1';
-    if (const char* mm_ = getenv("PIO_ALS_MMA")) h->use_mma = mm_[0] != '0';
+    if (const char* mm_ = getenv("PIO_ALS_MMA")) {
+      h->use_mma = mm_[0] != '0';
+      h->use_pair = mm_[0] != '1';
+    }
+    if (const char* v = getenv("PIO_ALS_SEG_T")) h->pair_seg_t = atoi(v) > 0 ? atoi(v) : PAIR_SEG_T;
+    if (const char* v = getenv("PIO_ALS_PART")) h->pair_part = atoi(v) >= 8 ? (atoi(v) + 7) / 8 * 8 : PAIR_PART;
   }
   h->gram_blocks = 2 * h->sm_count;
   if (cudaMallocAsync((void**)&h->yty, sizeof(float) * h->KP * h->KP, h->stream) != cudaSuccess ||
@@ -1188,8 +1262,8 @@ int pio_als_get_phase_ms(pio_als_handle* h, double out[8]) {
   for (int i = 0; i < 8; ++i) out[i] = h->phase_ms[i];
   // kernel of the rows below the heavy-row threshold: 0 = FP32 (als_solve_kernel), 1 = tcgen05, 2 = mma.sync
   const bool mma = h->KP == 64 && h->use_mma;
-  out[4] = h->I.use_tc ? 1.0 : (mma ? 2.0 : 0.0);
-  out[5] = h->U.use_tc ? 1.0 : (mma ? 2.0 : 0.0);
+  out[4] = h->I.use_tc ? 1.0 : h->I.use_pair ? 3.0 : (mma ? 2.0 : 0.0);
+  out[5] = h->U.use_tc ? 1.0 : h->U.use_pair ? 3.0 : (mma ? 2.0 : 0.0);
   return PIO_ALS_OK;
 }
 
@@ -1517,6 +1591,94 @@ __attribute__((visibility("default"))) int pio_als_debug_timing(pio_als_handle* 
   return cudaMemcpy(out, h->d_timing, m * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? PIO_ALS_OK : PIO_ALS_ERR_CUDA;
 }
 
+#define CK0(call)                                                                                         \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+/* debug only (not in pio_als.h): the lockstep Cholesky of als_lockstep.cuh on n dense SPD systems (A: n x N x N
+ * row-major, b: n x N; HOST buffers), N = 64 or 128; x = (A + ridge I)^-1 b.  reps > 1 repeats fill + solve for timing
+ * (ms_out = device time of the launch).  Used by tests/test_gpu_lockstep.py and tools/bench_solver.py. */
+extern "C++" {
+template <int N>
+__global__ void __launch_bounds__(32) lockstep_probe_kernel(const float* __restrict__ A, const float* __restrict__ b, int n,
+                                                            float ridge, float* __restrict__ x, int reps, int* fail) {
+  using LL = LsLayout<N>;
+  constexpr int LANES = N / 4, NM = 32 / LANES;
+  extern __shared__ __align__(16) float sm[];
+  float* bvec = sm + NM * LL::STRIDE;
+  float* colbuf = bvec + NM * 80 + (N > 64 ? N : 0);
+  const int lane = threadIdx.x & 31, grp = lane / LANES;
+  for (int base = blockIdx.x * NM; base < n; base += gridDim.x * NM) {
+    for (int rep = 0; rep < reps; ++rep) {
+      for (int m = 0; m < NM; ++m) {
+        const int mi = base + m;
+        float* slot = sm + m * LL::STRIDE;
+        for (int o = lane; o < N * N; o += 32) {
+          const int r = o / N, c = o % N;
+          if (c <= r) slot[LL::at(r, c)] = mi < n ? A[(size_t)mi * N * N + o] : (r == c ? 1.f : 0.f);
+        }
+        for (int o = lane; o < N; o += 32) bvec[m * (N > 64 ? N : 80) + o] = mi < n ? b[(size_t)mi * N + o] : 0.f;
+      }
+      __syncwarp();
+      const int mine = base + grp;
+      chol_lockstep<N, false>(sm + grp * LL::STRIDE, bvec + grp * (N > 64 ? N : 80), nullptr, ridge, N, colbuf + grp * 80,
+                              x + (size_t)(mine < n ? mine : 0) * N, mine < n, fail);
+      __syncwarp();
+    }
+  }
+}
+}  // extern "C++"
+
+__attribute__((visibility("default"))) int pio_als_debug_lockstep(int device, int N, int n, const float* A, const float* b,
+                                                                  float ridge, float* x, int reps, float* ms_out,
+                                                                  int* fail_out) {
+  if ((N != 64 && N != 128) || n < 1 || !A || !b || !x) return PIO_ALS_ERR_ARG;
+  CK0(cudaSetDevice(device));
+  float *dA = nullptr, *db = nullptr, *dx = nullptr;
+  int* dfail = nullptr;
+  CK0(cudaMalloc((void**)&dA, sizeof(float) * (size_t)n * N * N));
+  CK0(cudaMalloc((void**)&db, sizeof(float) * (size_t)n * N));
+  CK0(cudaMalloc((void**)&dx, sizeof(float) * (size_t)n * N));
+  CK0(cudaMalloc((void**)&dfail, sizeof(int)));
+  CK0(cudaMemset(dfail, 0, sizeof(int)));
+  CK0(cudaMemcpy(dA, A, sizeof(float) * (size_t)n * N * N, cudaMemcpyHostToDevice));
+  CK0(cudaMemcpy(db, b, sizeof(float) * (size_t)n * N, cudaMemcpyHostToDevice));
+  const int nm = N == 64 ? 2 : 1;
+  const size_t smem = sizeof(float) * (size_t)(nm * (N == 64 ? LsLayout<64>::STRIDE : LsLayout<128>::STRIDE) + 2 * 80 + 2 * 80 + 256);
+  cudaDeviceProp pr_;
+  CK0(cudaGetDeviceProperties(&pr_, device));
+  int grid = (n + nm - 1) / nm;
+  const int cap = pr_.multiProcessorCount * (N == 64 ? 12 : 6);
+  if (grid > cap) grid = cap;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  if (N == 64) {
+    CK0(cudaFuncSetAttribute(lockstep_probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK0(cudaFuncSetAttribute(lockstep_probe_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    cudaEventRecord(e0);
+    lockstep_probe_kernel<64><<<grid, 32, smem>>>(dA, db, n, ridge, dx, reps < 1 ? 1 : reps, dfail);
+  } else {
+    CK0(cudaFuncSetAttribute(lockstep_probe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK0(cudaFuncSetAttribute(lockstep_probe_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    cudaEventRecord(e0);
+    lockstep_probe_kernel<128><<<grid, 32, smem>>>(dA, db, n, ridge, dx, reps < 1 ? 1 : reps, dfail);
+  }
+  cudaEventRecord(e1);
+  CK0(cudaDeviceSynchronize());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = ms;
+  CK0(cudaMemcpy(x, dx, sizeof(float) * (size_t)n * N, cudaMemcpyDeviceToHost));
+  if (fail_out) CK0(cudaMemcpy(fail_out, dfail, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dA); cudaFree(db); cudaFree(dx); cudaFree(dfail);
+  return PIO_ALS_OK;
+}
+
 int pio_als_get_stats(const pio_als_handle* h, pio_als_stats* out) {
   if (!h || !out) return PIO_ALS_ERR_ARG;
   *out = h->st;
@@ -1534,12 +1696,6 @@ int pio_als_synth_ratings_device(int device, int32_t n_users, int32_t n_items, i
 }
 
 // ---- NaiveBayes ---------------------------------------------------------------------------------
-#define CK0(call)                                                                                         \
-  do {                                                                                                    \
-    cudaError_t e_ = (call);                                                                              \
-    if (e_ != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
-  } while (0)
-
 int pio_nb_train(int device, const int32_t* label, const float* x, int64_t n, int n_feat, int n_class, double lambda,
                  double* pi, double* theta) {
   if (!label || !x || !pi || !theta || n <= 0 || n_feat < 1 || n_class < 1)

@@ -144,7 +144,7 @@ def test_config_c1_recommendation_template(native, oracle):
     assert np.abs(pg - po).max() <= 1e-3 * max(1.0, np.abs(po).max())
 
 
-@pytest.mark.parametrize("path", ["fp32", "mma", "tcgen05"])
+@pytest.mark.parametrize("path", ["fp32", "mma", "pair", "tcgen05"])
 def test_heavy_rows_split_mode(native, oracle, monkeypatch, path):
     """Items with far more ratings than the heavy-row threshold are cut into 2016-rating parts (part launch on the FP32
     kernel + als_finish_kernel); the rows below the threshold go through each of the three rank-64 kernels in turn
@@ -155,6 +155,9 @@ def test_heavy_rows_split_mode(native, oracle, monkeypatch, path):
         monkeypatch.setenv("PIO_ALS_TC", "0")
         monkeypatch.setenv("PIO_ALS_MMA", "0")
     elif path == "mma":
+        monkeypatch.setenv("PIO_ALS_TC", "0")
+        monkeypatch.setenv("PIO_ALS_MMA", "1")
+    elif path == "pair":
         monkeypatch.setenv("PIO_ALS_TC", "0")
     nu, ni, nnz = 20000, 40, 400000
     u, i, r = synth.synth_ratings(nu, ni, nnz, seed=9, implicit=True)
@@ -178,19 +181,22 @@ def test_rank64_kernel_selection(native, oracle, monkeypatch):
     for implicit in (True, False):
         u, i, r = synth.synth_ratings(nu, ni, nnz, seed=21, implicit=implicit)
         res = {}
-        for path, env in (("tcgen05", {}), ("mma", {"PIO_ALS_TC": "0"}), ("fp32", {"PIO_ALS_TC": "0", "PIO_ALS_MMA": "0"})):
+        for path, env in (("tcgen05", {}), ("pair", {"PIO_ALS_TC": "0"}), ("mma", {"PIO_ALS_TC": "0", "PIO_ALS_MMA": "1"}),
+                          ("fp32", {"PIO_ALS_TC": "0", "PIO_ALS_MMA": "0"})):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             m, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 4, 0.05, implicit, 1.0)
             ph = m.phase_ms()
-            assert ph["item_kernel"] == path and ph["user_kernel"] == ("fp32" if path == "fp32" else "mma"), ph
+            assert ph["item_kernel"] == path and ph["user_kernel"] == {"fp32": "fp32", "mma": "mma"}.get(path, "pair"), ph
             eu, ei = frob_rel(g[0], o[0]), frob_rel(g[1], o[1])
             assert eu <= TOL and ei <= TOL, (path, implicit, eu, ei)
             res[path] = g
             for k in env:
                 monkeypatch.delenv(k)
-        assert frob_rel(res["mma"][1], res["fp32"][1]) <= TOL and frob_rel(res["tcgen05"][1], res["fp32"][1]) <= TOL
-        assert not np.array_equal(res["mma"][1], res["fp32"][1]) and not np.array_equal(res["mma"][1], res["tcgen05"][1])
+        for a in ("mma", "pair", "tcgen05"):
+            assert frob_rel(res[a][1], res["fp32"][1]) <= TOL
+        assert not np.array_equal(res["pair"][1], res["fp32"][1]) and not np.array_equal(res["pair"][1], res["tcgen05"][1])
+        assert not np.array_equal(res["pair"][1], res["mma"][1])
 
 
 @pytest.mark.parametrize("rank", [8, 64])    # 8: FP32 kernel, 64: mma.sync kernel
