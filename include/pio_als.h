@@ -29,7 +29,7 @@
  *       examples/scala-parallel-recommendation/blacklist-items/src/main/scala/ALSAlgorithm.scala:117-158
  *   pio_als_similar replaces the cosine scan + getTopN
  *       examples/scala-parallel-similarproduct/multi-events-multi-algos/src/main/scala/ALSAlgorithm.scala:138-234
- *   pio_als_save / pio_als_load replace ALSModel.save / ALSModel.apply
+ *   pio_als_save / pio_als_load / pio_als_model_import replace ALSModel.save / ALSModel.apply
  *       examples/scala-parallel-recommendation/blacklist-items/src/main/scala/ALSModel.scala:63-100
  *   pio_nb_train / pio_nb_predict replace NaiveBayes.train / model.predict
  *       examples/scala-parallel-classification/add-algorithm/src/main/scala/NaiveBayesAlgorithm.scala:41-57
@@ -50,7 +50,7 @@ extern "C" {
 #define PIO_API
 #endif
 
-#define PIO_ALS_ABI_VERSION 1
+#define PIO_ALS_ABI_VERSION 2
 
 /* status codes */
 #define PIO_ALS_OK 0
@@ -148,19 +148,37 @@ PIO_API int pio_als_train(pio_als_handle* h, const int32_t* user, const int32_t*
                           const float* user_init, const float* item_init, int n_iters,
                           float* user_out, float* item_out, uint8_t* user_has, uint8_t* item_has);
 
-/* Top-k scoring on a trained (or loaded) handle; HOST buffers.
- * recommend: for each users[q]: score_i = <x_u, y_i> over items that own a factor and have
- *   item_mask[i] == 0 (nullable = no filter); out_items/out_scores are n x topk, best first,
- *   padded with -1 / 0; out_count[q] (nullable) = number of valid entries (0 for an unknown user).
- *   Ties: smaller item index first. */
+/* Top-k scoring on a trained (or loaded / imported) handle; HOST buffers.  topk >= 1, any size (more than 128 results
+ * per query are produced in several passes over the item matrix).
+ * recommend: for each users[q]: score_i = <x_u, y_i> (fp64, index order) over items that own a factor and have
+ *   item_mask[i] == 0 (nullable = no filter), times item_weight[i] if item_weight != NULL (fp64; the ecommerce
+ *   template's weightedItems, examples/scala-parallel-ecommercerecommendation/adjust-score/src/main/scala/
+ *   ECommAlgorithm.scala:258-266,490-497); out_items/out_scores are n x topk, best first, padded with -1 / 0;
+ *   out_count[q] (nullable) = number of valid entries (0 for an unknown user).  Ties: smaller item index first. */
 PIO_API int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk,
-                              const uint8_t* item_mask, int32_t* out_items, float* out_scores,
-                              int32_t* out_count);
-/* similar: score_i = sum_q cosine(y_q, y_i) over query items that own a factor; candidates are
- *   items owning a factor, not in the query, item_mask[i]==0, score > 0. */
+                              const uint8_t* item_mask, const double* item_weight, int32_t* out_items,
+                              float* out_scores, int32_t* out_count);
+/* similar: score_i = (sum_q cosine(y_q, y_i)) * item_weight[i] over query items that own a factor; candidates are
+ *   items owning a factor, item_mask[i] == 0, score > 0, and -- unless PIO_ALS_SIM_KEEP_QUERY_ITEMS is set -- not in
+ *   the query (similarproduct: `!queryList.contains(i)`, multi-events ALSAlgorithm.scala:243-245; the ecommerce
+ *   template's predictSimilar has no such rule, train-with-rate-event ECommAlgorithm.scala:492-525 -> pass the flag). */
+#define PIO_ALS_SIM_KEEP_QUERY_ITEMS 1
 PIO_API int pio_als_similar(pio_als_handle* h, const int32_t* query_items, int nq, int topk,
-                            const uint8_t* item_mask, int32_t* out_items, float* out_scores,
-                            int32_t* out_count);
+                            const uint8_t* item_mask, const double* item_weight, int flags, int32_t* out_items,
+                            float* out_scores, int32_t* out_count);
+/* n_queries similar() queries in one call (batchPredict / offline evaluation): query j = q_items[q_ptr[j] .. q_ptr[j+1]);
+ * out_items/out_scores are n_queries x topk, out_count n_queries.  Same arithmetic as pio_als_similar. */
+PIO_API int pio_als_similar_batch(pio_als_handle* h, const int64_t* q_ptr, const int32_t* q_items, int n_queries,
+                                  int topk, const uint8_t* item_mask, const double* item_weight, int flags,
+                                  int32_t* out_items, float* out_scores, int32_t* out_count);
+
+/* A scoring handle from factors held by the caller (HOST, row-major n x rank; has flags nullable = every row owns a
+ * factor): what ALSModel.apply / a P2LAlgorithm's driver-local Map[Int, Array[Double]] model becomes on the device
+ * (examples/scala-parallel-similarproduct/multi-events-multi-algos/src/main/scala/ALSAlgorithm.scala:39-55,131).
+ * cfg: rank, n_users, n_items, device (+ lambda / alpha / implicit_prefs kept as metadata); n_users may be 0 with
+ * user_factors == NULL for an item-only model (similarproduct). */
+PIO_API int pio_als_model_import(const pio_als_config* cfg, const float* user_factors, const float* item_factors,
+                                 const uint8_t* user_has, const uint8_t* item_has, pio_als_handle** out);
 
 /* Model persistence (one little-endian file: header, has flags, fp32 factors). */
 PIO_API int pio_als_save(pio_als_handle* h, const char* path);

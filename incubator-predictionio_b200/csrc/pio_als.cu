@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <deque>
+#include <exception>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -468,8 +469,9 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
   CK(h, radix_sort_pairs(ka, va, kb, vb, (size_t)nnz, row.bits + col.bits, st, &in_b, &h->st.kernel_launches));
   const uint64_t* ks = in_b ? kb : ka;
   const uint32_t* vs = in_b ? vb : va;
+  Scratch tmp(h);
   long long* ptr_full = nullptr;
-  CK(h, dalloc(h, &ptr_full, (size_t)row.n_internal + 1));
+  CK(h, tmp.alloc(&ptr_full, (size_t)row.n_internal + 1));
   build_ptr_kernel<<<nblk(nnz, 256), 256, 0, st>>>(ks, nnz, col.bits, row.n_internal, ptr_full);
   LAUNCHED(h);
   long long be[2];
@@ -508,7 +510,6 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
   CK(h, cudaStreamSynchronize(st));
   row.n_active = counts[0];
   row.n_heavy = counts[1];
-  dfree(h, ptr_full);
   if (row.n_heavy > 0) {
     // cut the heavy rows (local rows [0, n_heavy), longest first) into parts of part_len ratings
     std::vector<long long> hp((size_t)row.n_heavy + 1);
@@ -582,12 +583,13 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
   if (bad) return fail(h, PIO_ALS_ERR_ARG, "%d ratings have a user/item index out of range", bad);
 
   const size_t nmax = (size_t)(nnz > U.n ? nnz : U.n) > (size_t)I.n ? (size_t)(nnz > U.n ? nnz : U.n) : (size_t)I.n;
+  Scratch tmp(h);   // sort buffers and dedup output: released on every exit path, including the CK() early returns
   uint64_t *ka = nullptr, *kb = nullptr;
   uint32_t *va = nullptr, *vb = nullptr;
-  CK(h, dalloc(h, &ka, nmax));
-  CK(h, dalloc(h, &kb, nmax));
-  CK(h, dalloc(h, &va, nmax));
-  CK(h, dalloc(h, &vb, nmax));
+  CK(h, tmp.alloc(&ka, nmax));
+  CK(h, tmp.alloc(&kb, nmax));
+  CK(h, tmp.alloc(&va, nmax));
+  CK(h, tmp.alloc(&vb, nmax));
 
   // 1. optional dedup of repeated (user,item) pairs
   const int* cu = d_user;
@@ -605,7 +607,7 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
     const uint64_t* ks = in_b ? kb : ka;
     const uint32_t* vs = in_b ? vb : va;
     uint32_t* flag = nullptr;
-    CK(h, dalloc(h, &flag, (size_t)nnz));
+    CK(h, tmp.alloc(&flag, (size_t)nnz));
     head_flags_kernel<<<nblk(nnz, 256), 256, 0, st>>>(ks, nnz, flag);
     LAUNCHED(h);
     uint32_t last_flag = 0, last_pos = 0;
@@ -614,12 +616,11 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
     CK(h, cudaMemcpyAsync(&last_pos, flag + nnz - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
     n2 = (long long)last_pos + last_flag;
-    CK(h, dalloc(h, &du_, (size_t)n2));
-    CK(h, dalloc(h, &di_, (size_t)n2));
-    CK(h, dalloc(h, &dr_, (size_t)n2));
+    CK(h, tmp.alloc(&du_, (size_t)n2));
+    CK(h, tmp.alloc(&di_, (size_t)n2));
+    CK(h, tmp.alloc(&dr_, (size_t)n2));
     dedup_compact_kernel<<<nblk(nnz, 256), 256, 0, st>>>(ks, vs, flag, nnz, bi, d_rating, d_ts, dedup, du_, di_, dr_);
     LAUNCHED(h);
-    dfree(h, flag);
     cu = du_;
     ci = di_;
     cr = dr_;
@@ -663,8 +664,6 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
     LAUNCHED(h);
   }
   h->have_init = false;
-  dfree(h, du_); dfree(h, di_); dfree(h, dr_);
-  dfree(h, ka); dfree(h, kb); dfree(h, va); dfree(h, vb);
   CK(h, cudaStreamSynchronize(st));
   int au[2] = {U.n_active, I.n_active};
   h->st.n_users_active = au[0];
@@ -1311,10 +1310,12 @@ int pio_als_train(pio_als_handle* h, const int32_t* user, const int32_t* item, c
   return pio_als_get_factors(h, user_out, item_out, user_has, item_has);
 }
 
+// Scoring passes: at most TK_MAXK results per pass; a query asking for more runs further passes, each bounded by the last
+// result of the one before (topk.cuh below_bound).
 int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, const uint8_t* item_mask,
-                      int32_t* out_items, float* out_scores, int32_t* out_count) {
+                      const double* item_weight, int32_t* out_items, float* out_scores, int32_t* out_count) {
   if (!h) return PIO_ALS_ERR_ARG;
-  if (n < 0 || topk < 1 || topk > TK_MAXK) return fail(h, PIO_ALS_ERR_ARG, "topk must be in 1..%d", TK_MAXK);
+  if (n < 0 || topk < 1) return fail(h, PIO_ALS_ERR_ARG, "topk must be >= 1 and n >= 0");
   if (n == 0) return PIO_ALS_OK;
   if (!users || !out_items || !out_scores) return fail(h, PIO_ALS_ERR_ARG, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
@@ -1326,9 +1327,11 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
   int* d_users = nullptr;
   float* d_xq = nullptr;
   uint8_t *d_valid = nullptr, *d_mask = nullptr;
-  ScoreIdx* d_cand = nullptr;
+  double* d_weight = nullptr;
+  ScoreIdx *d_cand = nullptr, *d_bound = nullptr;
   int *d_oi = nullptr, *d_oc = nullptr;
   float* d_os = nullptr;
+  const int pass_max = topk < TK_MAXK ? topk : TK_MAXK;
   // batched scoring: groups of SB_QB queries share every staged item tile; GX persistent CTAs per group
   const int ngroups = (n + SB_QB - 1) / SB_QB;
   const int ntiles = (h->I.n_internal + SB_THREADS - 1) / SB_THREADS;
@@ -1336,7 +1339,7 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
   if (gx > (ntiles + 7) / 8) gx = (ntiles + 7) / 8;   // at least eight tiles per CTA: the pools must warm up
   if (gx < 1) gx = 1;
   const size_t sb_smem = sizeof(double) * (size_t)KP * SB_QB + sb_tile_bytes(KP) +
-                         (sizeof(double) + sizeof(int)) * (size_t)SB_QB * topk;
+                         (sizeof(double) + sizeof(int)) * (size_t)SB_QB * pass_max;
   {
     static size_t attr_smem[64] = {};
     if (h->cfg.device < 64 && attr_smem[h->cfg.device] < sb_smem) {
@@ -1347,7 +1350,7 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
   CK(h, tmp.alloc(&d_users, (size_t)n));
   CK(h, tmp.alloc(&d_xq, (size_t)n * KP));
   CK(h, tmp.alloc(&d_valid, (size_t)n));
-  CK(h, tmp.alloc(&d_cand, (size_t)n * gx * topk));
+  CK(h, tmp.alloc(&d_cand, (size_t)n * gx * pass_max));
   CK(h, tmp.alloc(&d_oi, (size_t)n * topk));
   CK(h, tmp.alloc(&d_os, (size_t)n * topk));
   CK(h, tmp.alloc(&d_oc, (size_t)n));
@@ -1356,20 +1359,29 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
     CK(h, tmp.alloc(&d_mask, (size_t)h->I.n));
     CK(h, cudaMemcpyAsync(d_mask, item_mask, (size_t)h->I.n, cudaMemcpyHostToDevice, st));
   }
+  if (item_weight) {
+    CK(h, tmp.alloc(&d_weight, (size_t)h->I.n));
+    CK(h, cudaMemcpyAsync(d_weight, item_weight, sizeof(double) * (size_t)h->I.n, cudaMemcpyHostToDevice, st));
+  }
+  if (topk > TK_MAXK) CK(h, tmp.alloc(&d_bound, (size_t)n));
   gather_rows_kernel<<<n, 64, 0, st>>>(h->U.F, KP, d_users, n, h->U.perm, h->U.deg, h->U.n, d_xq, d_valid);
   LAUNCHED(h);
-  // grid.y is limited to 65535 query groups per launch
-  for (int g0 = 0; g0 < ngroups; g0 += 32768) {
-    const int ng = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
-    const int q0 = g0 * SB_QB;
-    const int nq = n - q0 < ng * SB_QB ? n - q0 : ng * SB_QB;
-    score_dot_topk_batched_kernel<<<dim3(gx, ng), SB_THREADS, sb_smem, st>>>(
-        h->I.F, h->I.n_internal, KP, d_xq + (size_t)q0 * KP, d_valid + q0, nq, h->I.cand_ext, d_mask, topk,
-        d_cand + (size_t)q0 * gx * topk);
+  for (int done = 0; done < topk; done += TK_MAXK) {
+    const int pk = topk - done < TK_MAXK ? topk - done : TK_MAXK;
+    // grid.y is limited to 65535 query groups per launch
+    for (int g0 = 0; g0 < ngroups; g0 += 32768) {
+      const int ng = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
+      const int q0 = g0 * SB_QB;
+      const int nq = n - q0 < ng * SB_QB ? n - q0 : ng * SB_QB;
+      score_dot_topk_batched_kernel<<<dim3(gx, ng), SB_THREADS, sb_smem, st>>>(
+          h->I.F, h->I.n_internal, KP, d_xq + (size_t)q0 * KP, d_valid + q0, nq, h->I.cand_ext, d_mask, d_weight,
+          (done > 0) ? d_bound + q0 : nullptr, pk, d_cand + (size_t)q0 * gx * pk);
+      LAUNCHED(h);
+    }
+    // the candidate lists of a query are [gx][pk] entries, stored with stride pk
+    topk_merge_kernel<<<n, TK_THREADS, 0, st>>>(d_cand, gx * pk, pk, topk, done, d_oi, d_os, d_oc, d_bound);
     LAUNCHED(h);
   }
-  topk_merge_kernel<<<n, TK_THREADS, 0, st>>>(d_cand, gx * topk, topk, d_oi, d_os, d_oc);
-  LAUNCHED(h);
   CK(h, cudaMemcpyAsync(out_items, d_oi, sizeof(int) * (size_t)n * topk, cudaMemcpyDeviceToHost, st));
   CK(h, cudaMemcpyAsync(out_scores, d_os, sizeof(float) * (size_t)n * topk, cudaMemcpyDeviceToHost, st));
   if (out_count) CK(h, cudaMemcpyAsync(out_count, d_oc, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -1377,23 +1389,20 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
   return PIO_ALS_OK;
 }
 
-int pio_als_similar(pio_als_handle* h, const int32_t* query_items, int nq, int topk, const uint8_t* item_mask,
-                    int32_t* out_items, float* out_scores, int32_t* out_count) {
-  if (!h) return PIO_ALS_ERR_ARG;
-  if (nq < 0 || topk < 1 || topk > TK_MAXK) return fail(h, PIO_ALS_ERR_ARG, "topk must be in 1..%d", TK_MAXK);
-  if (!out_items || !out_scores || (nq > 0 && !query_items)) return fail(h, PIO_ALS_ERR_ARG, "null argument");
-  std::lock_guard<std::mutex> lk(h->mu);
-  if (!h->I.F || !h->I.cand_ext) return fail(h, PIO_ALS_ERR_STATE, "no model");
+namespace pio {
+// one similar() query with mask / weights already on the device; results to HOST out arrays (topk entries)
+static int similar_one(pio_als_handle* h, const int32_t* query_items, int nq, int topk, const uint8_t* d_mask,
+                       const double* d_weight, int flags, int32_t* out_items, float* out_scores, int32_t* out_count) {
   for (int t = 0; t < topk; ++t) { out_items[t] = -1; out_scores[t] = 0.f; }
   if (out_count) *out_count = 0;
   if (nq == 0) return PIO_ALS_OK;
-  CK(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = h->stream;
   const int KP = h->KP, k = h->cfg.rank;
+  const int keep_query = (flags & PIO_ALS_SIM_KEEP_QUERY_ITEMS) ? 1 : 0;
   Scratch tmp(h);
   int* d_q = nullptr;
   float* d_qf = nullptr;
-  uint8_t *d_valid = nullptr, *d_mask = nullptr;
+  uint8_t* d_valid = nullptr;
   CK(h, tmp.alloc(&d_q, (size_t)nq));
   CK(h, tmp.alloc(&d_qf, (size_t)nq * KP));
   CK(h, tmp.alloc(&d_valid, (size_t)nq));
@@ -1407,59 +1416,103 @@ int pio_als_similar(pio_als_handle* h, const int32_t* query_items, int nq, int t
   std::vector<int> keep;
   for (int q = 0; q < nq; ++q)
     if (valid[q]) keep.push_back(q);
-  int rc = PIO_ALS_OK;
-  if (!keep.empty()) {
-    float* d_qc = nullptr;
-    CK(h, tmp.alloc(&d_qc, keep.size() * (size_t)KP));
-    for (size_t j = 0; j < keep.size(); ++j)
-      CK(h, cudaMemcpyAsync(d_qc + j * KP, d_qf + (size_t)keep[j] * KP, sizeof(float) * KP, cudaMemcpyDeviceToDevice, st));
-    if (item_mask) {
-      CK(h, tmp.alloc(&d_mask, (size_t)h->I.n));
-      CK(h, cudaMemcpyAsync(d_mask, item_mask, (size_t)h->I.n, cudaMemcpyHostToDevice, st));
+  if (keep.empty()) return PIO_ALS_OK;
+  float* d_qc = nullptr;
+  CK(h, tmp.alloc(&d_qc, keep.size() * (size_t)KP));
+  for (size_t j = 0; j < keep.size(); ++j)
+    CK(h, cudaMemcpyAsync(d_qc + j * KP, d_qf + (size_t)keep[j] * KP, sizeof(float) * KP, cudaMemcpyDeviceToDevice, st));
+  const int pass_max = topk < TK_MAXK ? topk : TK_MAXK;
+  // batched kernel (query vectors resident in shared memory) unless the query is too large for it
+  const int nqv = (int)keep.size();
+  const int nqp = (nqv + SC_G - 1) / SC_G * SC_G;
+  constexpr int SC_WARPS = SB_THREADS / 32;   // one candidate pool per warp
+  const size_t sc_smem = sizeof(double) * ((size_t)KP * nqp + nqp) + sizeof(float) * (size_t)SB_THREADS * (KP + 4) +
+                         (sizeof(double) + sizeof(int)) * (size_t)SC_WARPS * pass_max + sizeof(int) * (size_t)nq + 16;
+  const bool batched = sc_smem <= 100 * 1024;
+  int ntiles = (h->I.n_internal + TK_TILE - 1) / TK_TILE;
+  if (batched) {
+    const int nt = (h->I.n_internal + SB_THREADS - 1) / SB_THREADS;
+    ntiles = 2 * h->sm_count < (nt + 7) / 8 ? 2 * h->sm_count : (nt + 7) / 8;   // = CTAs (>= 8 tiles each)
+    static size_t attr_smem[64] = {};
+    if (h->cfg.device < 64 && attr_smem[h->cfg.device] < sc_smem) {
+      CK(h, cudaFuncSetAttribute(score_cos_topk_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+      attr_smem[h->cfg.device] = sc_smem;
     }
-    // batched kernel (query vectors resident in shared memory) unless the query is too large for it
-    const int nqv = (int)keep.size();
-    const int nqp = (nqv + SC_G - 1) / SC_G * SC_G;
-    constexpr int SC_WARPS = SB_THREADS / 32;   // one candidate pool per warp
-    const size_t sc_smem = sizeof(double) * ((size_t)KP * nqp + nqp) + sizeof(float) * (size_t)SB_THREADS * (KP + 4) +
-                           (sizeof(double) + sizeof(int)) * (size_t)SC_WARPS * topk + sizeof(int) * (size_t)nq + 16;
-    const bool batched = sc_smem <= 100 * 1024;
-    int ntiles = (h->I.n_internal + TK_TILE - 1) / TK_TILE;
-    if (batched) {
-      const int nt = (h->I.n_internal + SB_THREADS - 1) / SB_THREADS;
-      ntiles = 2 * h->sm_count < (nt + 7) / 8 ? 2 * h->sm_count : (nt + 7) / 8;   // = CTAs (>= 8 tiles each)
-      static size_t attr_smem[64] = {};
-      if (h->cfg.device < 64 && attr_smem[h->cfg.device] < sc_smem) {
-        CK(h, cudaFuncSetAttribute(score_cos_topk_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
-        attr_smem[h->cfg.device] = sc_smem;
-      }
-    }
-    ScoreIdx* d_cand = nullptr;
-    int *d_oi = nullptr, *d_oc = nullptr;
-    float* d_os = nullptr;
-    const int npools = batched ? ntiles * SC_WARPS : ntiles;   // candidate lists of topk entries left for the merge
-    CK(h, tmp.alloc(&d_cand, (size_t)npools * topk));
-    CK(h, tmp.alloc(&d_oi, (size_t)topk));
-    CK(h, tmp.alloc(&d_os, (size_t)topk));
-    CK(h, tmp.alloc(&d_oc, 1));
+  }
+  ScoreIdx *d_cand = nullptr, *d_bound = nullptr;
+  int *d_oi = nullptr, *d_oc = nullptr;
+  float* d_os = nullptr;
+  const int npools = batched ? ntiles * SC_WARPS : ntiles;   // candidate lists of pass_k entries left for the merge
+  CK(h, tmp.alloc(&d_cand, (size_t)npools * pass_max));
+  CK(h, tmp.alloc(&d_oi, (size_t)topk));
+  CK(h, tmp.alloc(&d_os, (size_t)topk));
+  CK(h, tmp.alloc(&d_oc, 1));
+  if (topk > TK_MAXK) CK(h, tmp.alloc(&d_bound, 1));
+  for (int done = 0; done < topk; done += TK_MAXK) {
+    const int pk = topk - done < TK_MAXK ? topk - done : TK_MAXK;
+    const ScoreIdx* bnd = done > 0 ? d_bound : nullptr;
     if (batched)
       score_cos_topk_batched_kernel<<<ntiles, SB_THREADS, sc_smem, st>>>(h->I.F, h->I.n_internal, KP, k, d_qc, d_q, nq, nqv,
-                                                                         h->I.cand_ext, d_mask, topk, d_cand);
+                                                                         h->I.cand_ext, d_mask, d_weight, bnd, keep_query, pk,
+                                                                         d_cand);
     else
-      score_cos_topk_kernel<<<ntiles, TK_THREADS, 0, st>>>(h->I.F, h->I.n_internal, KP, k, d_qc, d_q, nq, nqv,
-                                                           h->I.cand_ext, d_mask, topk, d_cand);
+      score_cos_topk_kernel<<<ntiles, TK_THREADS, 0, st>>>(h->I.F, h->I.n_internal, KP, k, d_qc, d_q, nq, nqv, h->I.cand_ext,
+                                                           d_mask, d_weight, bnd, keep_query, pk, d_cand);
     LAUNCHED(h);
-    topk_merge_kernel<<<1, TK_THREADS, 0, st>>>(d_cand, npools * topk, topk, d_oi, d_os, d_oc);
+    topk_merge_kernel<<<1, TK_THREADS, 0, st>>>(d_cand, npools * pk, pk, topk, done, d_oi, d_os, d_oc, d_bound);
     LAUNCHED(h);
-    CK(h, cudaMemcpyAsync(out_items, d_oi, sizeof(int) * topk, cudaMemcpyDeviceToHost, st));
-    CK(h, cudaMemcpyAsync(out_scores, d_os, sizeof(float) * topk, cudaMemcpyDeviceToHost, st));
-    int cnt = 0;
-    CK(h, cudaMemcpyAsync(&cnt, d_oc, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(h, cudaStreamSynchronize(st));
-    if (out_count) *out_count = cnt;
   }
+  CK(h, cudaMemcpyAsync(out_items, d_oi, sizeof(int) * topk, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaMemcpyAsync(out_scores, d_os, sizeof(float) * topk, cudaMemcpyDeviceToHost, st));
+  int cnt = 0;
+  CK(h, cudaMemcpyAsync(&cnt, d_oc, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(h, cudaStreamSynchronize(st));
-  return rc;
+  if (out_count) *out_count = cnt;
+  return PIO_ALS_OK;
+}
+}  // namespace pio
+
+int pio_als_similar_batch(pio_als_handle* h, const int64_t* q_ptr, const int32_t* q_items, int n_queries, int topk,
+                          const uint8_t* item_mask, const double* item_weight, int flags, int32_t* out_items,
+                          float* out_scores, int32_t* out_count) {
+  if (!h) return PIO_ALS_ERR_ARG;
+  if (n_queries < 0 || topk < 1) return fail(h, PIO_ALS_ERR_ARG, "topk must be >= 1 and n_queries >= 0");
+  if (n_queries == 0) return PIO_ALS_OK;
+  if (!q_ptr || !out_items || !out_scores) return fail(h, PIO_ALS_ERR_ARG, "null argument");
+  for (int j = 0; j < n_queries; ++j)
+    if (q_ptr[j + 1] < q_ptr[j] || (q_ptr[j + 1] > q_ptr[j] && !q_items))
+      return fail(h, PIO_ALS_ERR_ARG, "q_ptr must be non-decreasing offsets into q_items");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->I.F || !h->I.cand_ext) return fail(h, PIO_ALS_ERR_STATE, "no model");
+  CK(h, cudaSetDevice(h->cfg.device));
+  Scratch tmp(h);
+  uint8_t* d_mask = nullptr;
+  double* d_weight = nullptr;
+  if (item_mask) {
+    CK(h, tmp.alloc(&d_mask, (size_t)h->I.n));
+    CK(h, cudaMemcpyAsync(d_mask, item_mask, (size_t)h->I.n, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (item_weight) {
+    CK(h, tmp.alloc(&d_weight, (size_t)h->I.n));
+    CK(h, cudaMemcpyAsync(d_weight, item_weight, sizeof(double) * (size_t)h->I.n, cudaMemcpyHostToDevice, h->stream));
+  }
+  for (int j = 0; j < n_queries; ++j) {
+    int32_t cnt = 0;
+    const int rc = similar_one(h, q_items + q_ptr[j], (int)(q_ptr[j + 1] - q_ptr[j]), topk, d_mask, d_weight, flags,
+                               out_items + (size_t)j * topk, out_scores + (size_t)j * topk, &cnt);
+    if (rc) return rc;
+    if (out_count) out_count[j] = cnt;
+  }
+  CK(h, cudaStreamSynchronize(h->stream));
+  return PIO_ALS_OK;
+}
+
+int pio_als_similar(pio_als_handle* h, const int32_t* query_items, int nq, int topk, const uint8_t* item_mask,
+                    const double* item_weight, int flags, int32_t* out_items, float* out_scores, int32_t* out_count) {
+  if (!h) return PIO_ALS_ERR_ARG;
+  if (nq < 0) return fail(h, PIO_ALS_ERR_ARG, "nq < 0");
+  const int64_t ptr[2] = {0, nq};
+  return pio_als_similar_batch(h, ptr, query_items, 1, topk, item_mask, item_weight, flags, out_items, out_scores, out_count);
 }
 
 // ---- persistence ------------------------------------------------------------------------------
@@ -1471,26 +1524,30 @@ struct ModelHeader {
 
 int pio_als_save(pio_als_handle* h, const char* path) {
   if (!h || !path) return PIO_ALS_ERR_ARG;
-  const size_t nu = h->cfg.n_users, ni = h->cfg.n_items, k = h->cfg.rank;
-  std::vector<float> uf(nu * k), itf(ni * k);
-  std::vector<uint8_t> uh(nu), ih(ni);
-  int rc = pio_als_get_factors(h, uf.data(), itf.data(), uh.data(), ih.data());
-  if (rc) return rc;
-  FILE* f = fopen(path, "wb");
-  if (!f) return fail(h, PIO_ALS_ERR_IO, "cannot open %s for writing", path);
-  ModelHeader hd{};
-  memcpy(hd.magic, "PIOALS01", 8);
-  hd.version = 1;
-  hd.rank = h->cfg.rank;
-  hd.implicit_prefs = h->cfg.implicit_prefs;
-  hd.n_users = h->cfg.n_users;
-  hd.n_items = h->cfg.n_items;
-  hd.lambda = h->cfg.lambda;
-  hd.alpha = h->cfg.alpha;
-  bool ok = fwrite(&hd, sizeof hd, 1, f) == 1 && fwrite(uh.data(), 1, nu, f) == nu && fwrite(ih.data(), 1, ni, f) == ni &&
-            fwrite(uf.data(), sizeof(float), nu * k, f) == nu * k && fwrite(itf.data(), sizeof(float), ni * k, f) == ni * k;
-  ok = (fclose(f) == 0) && ok;
-  return ok ? PIO_ALS_OK : fail(h, PIO_ALS_ERR_IO, "short write to %s", path);
+  try {
+    const size_t nu = h->cfg.n_users, ni = h->cfg.n_items, k = h->cfg.rank;
+    std::vector<float> uf(nu * k), itf(ni * k);
+    std::vector<uint8_t> uh(nu), ih(ni);
+    int rc = pio_als_get_factors(h, uf.data(), itf.data(), uh.data(), ih.data());
+    if (rc) return rc;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(h, PIO_ALS_ERR_IO, "cannot open %s for writing", path);
+    ModelHeader hd{};
+    memcpy(hd.magic, "PIOALS01", 8);
+    hd.version = 1;
+    hd.rank = h->cfg.rank;
+    hd.implicit_prefs = h->cfg.implicit_prefs;
+    hd.n_users = h->cfg.n_users;
+    hd.n_items = h->cfg.n_items;
+    hd.lambda = h->cfg.lambda;
+    hd.alpha = h->cfg.alpha;
+    bool ok = fwrite(&hd, sizeof hd, 1, f) == 1 && fwrite(uh.data(), 1, nu, f) == nu && fwrite(ih.data(), 1, ni, f) == ni &&
+              fwrite(uf.data(), sizeof(float), nu * k, f) == nu * k && fwrite(itf.data(), sizeof(float), ni * k, f) == ni * k;
+    ok = (fclose(f) == 0) && ok;
+    return ok ? PIO_ALS_OK : fail(h, PIO_ALS_ERR_IO, "short write to %s", path);
+  } catch (const std::exception& e) {   // bad_alloc etc. must not cross the C boundary
+    return fail(h, PIO_ALS_ERR_IO, "pio_als_save: %s", e.what());
+  }
 }
 
 __global__ void load_side_kernel(const uint8_t* has, int n, int* perm, int* inv, uint32_t* deg, uint32_t* npos) {
@@ -1498,8 +1555,71 @@ __global__ void load_side_kernel(const uint8_t* has, int n, int* perm, int* inv,
   if (r >= n) return;
   perm[r] = r;
   inv[r] = r;
-  deg[r] = has[r] ? 1u : 0u;
+  deg[r] = (!has || has[r]) ? 1u : 0u;
   npos[r] = deg[r];
+}
+
+int pio_als_model_import(const pio_als_config* cfg_in, const float* user_factors, const float* item_factors,
+                         const uint8_t* user_has, const uint8_t* item_has, pio_als_handle** out) {
+  if (!cfg_in || !out) return fail(nullptr, PIO_ALS_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (!item_factors) return fail(nullptr, PIO_ALS_ERR_ARG, "item_factors is null");
+  pio_als_config cfg = *cfg_in;
+  cfg.world_size = 1;
+  cfg.world_rank = 0;
+  const bool item_only = cfg.n_users == 0 && !user_factors;
+  if (item_only) cfg.n_users = 1;   // an item-only model (similarproduct) carries one factor-less placeholder user
+  else if (!user_factors) return fail(nullptr, PIO_ALS_ERR_ARG, "user_factors is null but n_users > 0");
+  pio_als_handle* h = nullptr;
+  int rc = pio_als_create(&cfg, &h);
+  if (rc) return rc;
+  cudaStream_t st = h->stream;
+  const size_t k = (size_t)cfg.rank;
+  const uint8_t zero = 0;
+  struct { Side* s; size_t n; const uint8_t* has; const float* fac; } jobs[2] = {
+      {&h->U, (size_t)cfg.n_users, item_only ? &zero : user_has, user_factors}, {&h->I, (size_t)cfg.n_items, item_has, item_factors}};
+  auto body = [&]() -> int {
+    for (auto& j : jobs) {
+      Side& s = *j.s;
+      s.n = (int)j.n;
+      s.R = s.n;
+      s.n_internal = s.n;
+      s.bits = ceil_log2((uint64_t)s.n);
+      CK(h, dalloc(h, &s.perm, j.n)); CK(h, dalloc(h, &s.inv, j.n)); CK(h, dalloc(h, &s.deg, j.n));
+      CK(h, dalloc(h, &s.npos, j.n)); CK(h, dalloc(h, &s.cand_ext, j.n));
+      CK(h, dalloc(h, &s.F, j.n * (size_t)h->KP));
+      Scratch tmp(h);
+      uint8_t* dh = nullptr;
+      float* dfac = nullptr;
+      if (j.has) {
+        CK(h, tmp.alloc(&dh, j.n));
+        CK(h, cudaMemcpyAsync(dh, j.has, j.n, cudaMemcpyHostToDevice, st));
+      }
+      load_side_kernel<<<nblk(s.n, 256), 256, 0, st>>>(dh, s.n, s.perm, s.inv, s.deg, s.npos);
+      LAUNCHED(h);
+      if (j.fac) {
+        CK(h, tmp.alloc(&dfac, j.n * k));
+        CK(h, cudaMemcpyAsync(dfac, j.fac, sizeof(float) * j.n * k, cudaMemcpyHostToDevice, st));
+        scatter_init_kernel<<<nblk((long long)s.n * h->KP, 256), 256, 0, st>>>(dfac, s.n, (int)k, h->KP, s.perm, s.deg, s.F);
+        LAUNCHED(h);
+      } else {
+        CK(h, cudaMemsetAsync(s.F, 0, sizeof(float) * j.n * (size_t)h->KP, st));
+      }
+      cand_ext_kernel<<<nblk(s.n, 256), 256, 0, st>>>(s.inv, s.deg, s.n, s.cand_ext);
+      LAUNCHED(h);
+      CK(h, cudaStreamSynchronize(st));   // the host sources may go away after this call
+    }
+    return PIO_ALS_OK;
+  };
+  rc = body();
+  if (rc) {
+    g_create_error = h->err;
+    pio_als_destroy(h);
+    return rc;
+  }
+  h->trained = true;
+  *out = h;
+  return PIO_ALS_OK;
 }
 
 int pio_als_load(const char* path, int device, pio_als_handle** out) {
@@ -1512,66 +1632,40 @@ int pio_als_load(const char* path, int device, pio_als_handle** out) {
     fclose(f);
     return fail(nullptr, PIO_ALS_ERR_IO, "%s is not a PIOALS01 model file", path);
   }
-  const size_t nu = hd.n_users, ni = hd.n_items, k = hd.rank;
-  std::vector<float> uf(nu * k), itf(ni * k);
-  std::vector<uint8_t> uh(nu), ih(ni);
-  bool ok = fread(uh.data(), 1, nu, f) == nu && fread(ih.data(), 1, ni, f) == ni &&
-            fread(uf.data(), sizeof(float), nu * k, f) == nu * k && fread(itf.data(), sizeof(float), ni * k, f) == ni * k;
-  fclose(f);
-  if (!ok) return fail(nullptr, PIO_ALS_ERR_IO, "%s is truncated", path);
-  pio_als_config cfg{};
-  cfg.abi_version = PIO_ALS_ABI_VERSION;
-  cfg.rank = hd.rank;
-  cfg.implicit_prefs = hd.implicit_prefs;
-  cfg.n_users = hd.n_users;
-  cfg.n_items = hd.n_items;
-  cfg.device = device;
-  cfg.world_size = 1;
-  cfg.lambda = hd.lambda;
-  cfg.alpha = hd.alpha;
-  pio_als_handle* h = nullptr;
-  int rc = pio_als_create(&cfg, &h);
-  if (rc) return rc;
-  cudaStream_t st = h->stream;
-  struct { Side* s; size_t n; const uint8_t* has; const float* fac; } jobs[2] = {{&h->U, nu, uh.data(), uf.data()},
-                                                                                {&h->I, ni, ih.data(), itf.data()}};
-  auto body = [&]() -> int {
-    for (auto& j : jobs) {
-      Side& s = *j.s;
-      s.n = (int)j.n;
-      s.R = s.n;
-      s.n_internal = s.n;
-      s.bits = ceil_log2((uint64_t)s.n);
-      CK(h, dalloc(h, &s.perm, j.n)); CK(h, dalloc(h, &s.inv, j.n)); CK(h, dalloc(h, &s.deg, j.n));
-      CK(h, dalloc(h, &s.npos, j.n)); CK(h, dalloc(h, &s.cand_ext, j.n));
-      CK(h, dalloc(h, &s.F, j.n * (size_t)h->KP));
-      uint8_t* dh = nullptr;
-      float* tmp = nullptr;
-      CK(h, dalloc(h, &dh, j.n));
-      CK(h, dalloc(h, &tmp, j.n * k));
-      CK(h, cudaMemcpyAsync(dh, j.has, j.n, cudaMemcpyHostToDevice, st));
-      CK(h, cudaMemcpyAsync(tmp, j.fac, sizeof(float) * j.n * k, cudaMemcpyHostToDevice, st));
-      load_side_kernel<<<nblk(s.n, 256), 256, 0, st>>>(dh, s.n, s.perm, s.inv, s.deg, s.npos);
-      LAUNCHED(h);
-      scatter_init_kernel<<<nblk((long long)s.n * h->KP, 256), 256, 0, st>>>(tmp, s.n, (int)k, h->KP, s.perm, s.deg, s.F);
-      LAUNCHED(h);
-      cand_ext_kernel<<<nblk(s.n, 256), 256, 0, st>>>(s.inv, s.deg, s.n, s.cand_ext);
-      LAUNCHED(h);
-      dfree(h, dh);
-      dfree(h, tmp);
-    }
-    CK(h, cudaStreamSynchronize(st));
-    return PIO_ALS_OK;
-  };
-  rc = body();
-  if (rc) {
-    g_create_error = h->err;
-    pio_als_destroy(h);
-    return rc;
+  // a corrupt header must not turn into a huge allocation: check the fields and the file size first
+  if (hd.rank < 1 || hd.rank > 128 || hd.n_users < 1 || hd.n_items < 1) {
+    fclose(f);
+    return fail(nullptr, PIO_ALS_ERR_IO, "%s: corrupt header (rank %d, %d users, %d items)", path, hd.rank, hd.n_users, hd.n_items);
   }
-  h->trained = true;
-  *out = h;
-  return PIO_ALS_OK;
+  const size_t nu = hd.n_users, ni = hd.n_items, k = hd.rank;
+  const long long expect = (long long)sizeof hd + (long long)(nu + ni) + (long long)sizeof(float) * (long long)((nu + ni) * k);
+  if (fseek(f, 0, SEEK_END) != 0 || ftell(f) != expect || fseek(f, (long)sizeof hd, SEEK_SET) != 0) {
+    fclose(f);
+    return fail(nullptr, PIO_ALS_ERR_IO, "%s is truncated or has trailing bytes (expected %lld bytes)", path, expect);
+  }
+  try {
+    std::vector<float> uf(nu * k), itf(ni * k);
+    std::vector<uint8_t> uh(nu), ih(ni);
+    bool ok = fread(uh.data(), 1, nu, f) == nu && fread(ih.data(), 1, ni, f) == ni &&
+              fread(uf.data(), sizeof(float), nu * k, f) == nu * k && fread(itf.data(), sizeof(float), ni * k, f) == ni * k;
+    fclose(f);
+    f = nullptr;
+    if (!ok) return fail(nullptr, PIO_ALS_ERR_IO, "%s is truncated", path);
+    pio_als_config cfg{};
+    cfg.abi_version = PIO_ALS_ABI_VERSION;
+    cfg.rank = hd.rank;
+    cfg.implicit_prefs = hd.implicit_prefs;
+    cfg.n_users = hd.n_users;
+    cfg.n_items = hd.n_items;
+    cfg.device = device;
+    cfg.world_size = 1;
+    cfg.lambda = hd.lambda;
+    cfg.alpha = hd.alpha;
+    return pio_als_model_import(&cfg, uf.data(), itf.data(), uh.data(), ih.data(), out);
+  } catch (const std::exception& e) {
+    if (f) fclose(f);
+    return fail(nullptr, PIO_ALS_ERR_IO, "pio_als_load: %s", e.what());
+  }
 }
 
 /* debug only (not in pio_als.h): copies the A/b dump of the last tensor-core half-step (rows in internal order) */

@@ -29,6 +29,15 @@ __device__ __forceinline__ bool better(double s1, int i1, double s2, int i2) {
   return (s1 > s2) || (s1 == s2 && i1 < i2);
 }
 
+// Multi-pass selection (topk > TK_MAXK): a pass only accepts candidates strictly worse than the last result of the
+// previous pass.  bound.i == TK_NO_BOUND: accept everything (first pass); TK_EXHAUSTED: the previous pass ran out of
+// candidates, accept nothing.
+constexpr int TK_NO_BOUND = -2;
+constexpr int TK_EXHAUSTED = -3;
+__device__ __forceinline__ bool below_bound(const ScoreIdx& b, double s, int i) {
+  return b.i == TK_NO_BOUND || (b.i >= 0 && better(b.s, b.i, s, i));
+}
+
 // Block-wide selection: every thread holds TK_ITEMS candidates (score, index; index -1 = none).
 // Extracts the best `topk` in order and writes them to out[0..topk).
 __device__ __forceinline__ void block_select_topk(double (&sc)[TK_ITEMS], int (&ix)[TK_ITEMS], int topk,
@@ -197,6 +206,7 @@ __global__ void __launch_bounds__(SB_THREADS, 2)
 score_dot_topk_batched_kernel(const float* __restrict__ Y, int n_items, int kp,
                               const float* __restrict__ xq, const uint8_t* __restrict__ qvalid, int n_queries,
                               const int* __restrict__ cand_ext, const uint8_t* __restrict__ mask,
+                              const double* __restrict__ weight, const ScoreIdx* __restrict__ bound,
                               int topk, ScoreIdx* __restrict__ cand) {
   extern __shared__ __align__(16) unsigned char sb_smem[];
   const int row = kp + 4;                                         // floats per staged row (16-byte skew per row)
@@ -216,8 +226,15 @@ score_dot_topk_batched_kernel(const float* __restrict__ Y, int n_items, int kp,
   // warp w owns the pools of queries w*QPW .. w*QPW+QPW-1 of the group
   constexpr int QPW = SB_QB / (SB_THREADS / 32);
   WarpPool wp[QPW];
+  ScoreIdx bnd[QPW];
 #pragma unroll
-  for (int j = 0; j < QPW; ++j) { wp[j].thr = 0.0; wp[j].wid = -1; wp[j].worst = 0; wp[j].cnt = 0; }
+  for (int j = 0; j < QPW; ++j) {
+    wp[j].thr = 0.0; wp[j].wid = -1; wp[j].worst = 0; wp[j].cnt = 0;
+    const int q = q0 + warp * QPW + j;
+    bnd[j].s = 0.0;
+    bnd[j].i = TK_NO_BOUND;
+    if (bound && q < n_queries) bnd[j] = bound[q];
+  }
   unsigned qmask = 0;   // queries of this group that take candidates
   for (int q = 0; q < SB_QB; ++q)
     if (q0 + q < n_queries && qvalid[q0 + q]) qmask |= 1u << q;
@@ -259,6 +276,11 @@ score_dot_topk_batched_kernel(const float* __restrict__ Y, int n_items, int kp,
         }
       }
     }
+    if (weight && ext >= 0) {   // per-item score weight (ecommerce adjust-score): adjustedScore = s * weights(i)
+      const double w = weight[ext];
+#pragma unroll
+      for (int q = 0; q < SB_QB; ++q) acc[q] = acc[q] * w;
+    }
     // exchange: every thread publishes its SB_QB scores, then each warp feeds the pools it owns (no locks)
     __syncthreads();   // the staged rows are dead
 #pragma unroll
@@ -271,7 +293,8 @@ score_dot_topk_batched_kernel(const float* __restrict__ Y, int n_items, int kp,
       if ((qmask >> q) & 1u) {
         for (int it = lane; it < SB_THREADS; it += 32) {
           const int e = sext[it];
-          wpool_offer(wp[j], e >= 0, scs[q * SB_THREADS + it], e, topk, hs + (size_t)q * topk, hi + (size_t)q * topk);
+          const double sv = scs[q * SB_THREADS + it];
+          wpool_offer(wp[j], e >= 0 && below_bound(bnd[j], sv, e), sv, e, topk, hs + (size_t)q * topk, hi + (size_t)q * topk);
         }
       }
     }
@@ -302,10 +325,15 @@ __global__ void __launch_bounds__(SB_THREADS, 2)
 score_cos_topk_batched_kernel(const float* __restrict__ Y, int n_items, int kp, int k,
                               const float* __restrict__ qf, const int* __restrict__ qid, int nq_all, int nqv,
                               const int* __restrict__ cand_ext, const uint8_t* __restrict__ mask,
+                              const double* __restrict__ weight, const ScoreIdx* __restrict__ bound, int keep_query,
                               int topk, ScoreIdx* __restrict__ cand) {
   extern __shared__ __align__(16) unsigned char sb_smem[];
   const int row = kp + 4;
   const int nqp = (nqv + SC_G - 1) / SC_G * SC_G;
+  ScoreIdx bnd;
+  bnd.s = 0.0;
+  bnd.i = TK_NO_BOUND;
+  if (bound) bnd = *bound;
   double* xd = reinterpret_cast<double*>(sb_smem);                     // [kp][nqp]
   double* s1 = xd + (size_t)kp * nqp;                                   // [nqp] sqrt(n1) of every query vector
   float* tile = reinterpret_cast<float*>(s1 + nqp);                    // [SB_THREADS][row]
@@ -349,7 +377,7 @@ score_cos_topk_batched_kernel(const float* __restrict__ Y, int n_items, int kp, 
     const int i = base + tid;
     int ext = (i < n_items) ? cand_ext[i] : -1;
     if (ext >= 0 && mask && mask[ext]) ext = -1;
-    if (ext >= 0)
+    if (ext >= 0 && !keep_query)
       for (int t = 0; t < nq_all; ++t)
         if (sq[t] == ext) { ext = -1; break; }
     double score = 0.0;
@@ -392,7 +420,8 @@ score_cos_topk_batched_kernel(const float* __restrict__ Y, int n_items, int kp, 
           }
       }
     }
-    wpool_offer(wp, ext >= 0 && score > 0.0, score, ext, topk, ps, pi);   // each warp pools the items it scored
+    if (weight && ext >= 0) score = score * weight[ext];
+    wpool_offer(wp, ext >= 0 && score > 0.0 && below_bound(bnd, score, ext), score, ext, topk, ps, pi);   // each warp pools the items it scored
   }
   __syncwarp();
   for (int t = lane; t < topk; t += 32) {
@@ -410,7 +439,12 @@ __global__ void __launch_bounds__(TK_THREADS)
 score_cos_topk_kernel(const float* __restrict__ Y, int n_items, int kp, int k,
                       const float* __restrict__ qf, const int* __restrict__ qid, int nq_all, int nqv,
                       const int* __restrict__ cand_ext, const uint8_t* __restrict__ mask,
+                      const double* __restrict__ weight, const ScoreIdx* __restrict__ bound, int keep_query,
                       int topk, ScoreIdx* __restrict__ cand) {
+  ScoreIdx bnd;
+  bnd.s = 0.0;
+  bnd.i = TK_NO_BOUND;
+  if (bound) bnd = *bound;
   double sc[TK_ITEMS];
   int ix[TK_ITEMS];
 #pragma unroll
@@ -421,7 +455,8 @@ score_cos_topk_kernel(const float* __restrict__ Y, int n_items, int kp, int k,
     const int ext = i < n_items ? cand_ext[i] : -1;
     if (ext >= 0 && !(mask && mask[ext])) {
       bool isq = false;
-      for (int t = 0; t < nq_all; ++t) isq |= (qid[t] == ext);
+      if (!keep_query)
+        for (int t = 0; t < nq_all; ++t) isq |= (qid[t] == ext);
       if (!isq) {
         const float* f = Y + (size_t)i * kp;
         double score = 0.0;
@@ -437,7 +472,8 @@ score_cos_topk_kernel(const float* __restrict__ Y, int n_items, int kp, int k,
           const double n1n2 = sqrt(n1) * sqrt(n2);
           score += (n1n2 == 0.0) ? 0.0 : d / n1n2;
         }
-        if (score > 0.0) { sc[j] = score; ix[j] = ext; }
+        if (weight) score = score * weight[ext];
+        if (score > 0.0 && below_bound(bnd, score, ext)) { sc[j] = score; ix[j] = ext; }
       }
     }
   }
@@ -448,8 +484,9 @@ score_cos_topk_kernel(const float* __restrict__ Y, int n_items, int kp, int k,
 // The candidates are offered to one shared-memory pool (almost all are rejected by the threshold pre-check once it is
 // full); the survivors are ordered by rank counting (ids are distinct, so better() is a total order).
 __global__ void __launch_bounds__(TK_THREADS)
-topk_merge_kernel(const ScoreIdx* __restrict__ cand, int n_cand, int topk, int* __restrict__ out_items,
-                  float* __restrict__ out_scores, int* __restrict__ out_count) {
+topk_merge_kernel(const ScoreIdx* __restrict__ cand, int n_cand, int topk, int out_stride, int out_off,
+                  int* __restrict__ out_items, float* __restrict__ out_scores, int* __restrict__ out_count,
+                  ScoreIdx* __restrict__ bound_out) {
   __shared__ double hs[TK_MAXK];
   __shared__ int hi[TK_MAXK];
   __shared__ double hthr;
@@ -472,19 +509,28 @@ topk_merge_kernel(const ScoreIdx* __restrict__ cand, int n_cand, int topk, int* 
   }
   __syncthreads();
   const int cnt = hcnt;
+  int* oi = out_items + (size_t)blockIdx.x * out_stride + out_off;
+  float* os = out_scores + (size_t)blockIdx.x * out_stride + out_off;
   for (int t = threadIdx.x; t < topk; t += TK_THREADS) {
     if (t >= cnt) {   // fewer candidates than topk: the tail stays empty
-      out_items[(size_t)blockIdx.x * topk + t] = -1;
-      out_scores[(size_t)blockIdx.x * topk + t] = 0.f;
+      oi[t] = -1;
+      os[t] = 0.f;
     }
     if (t < cnt) {
       int rank = 0;
       for (int u = 0; u < cnt; ++u) rank += (u != t) && better(hs[u], hi[u], hs[t], hi[t]);
-      out_items[(size_t)blockIdx.x * topk + rank] = hi[t];
-      out_scores[(size_t)blockIdx.x * topk + rank] = (float)hs[t];
+      oi[rank] = hi[t];
+      os[rank] = (float)hs[t];
+      if (bound_out && rank == topk - 1) {   // the last result of a full pass bounds the next pass
+        bound_out[blockIdx.x].s = hs[t];
+        bound_out[blockIdx.x].i = hi[t];
+      }
     }
   }
-  if (threadIdx.x == 0 && out_count) out_count[blockIdx.x] = cnt;
+  if (threadIdx.x == 0) {
+    if (out_count && (out_off == 0 || cnt > 0)) out_count[blockIdx.x] = out_off + cnt;
+    if (bound_out && cnt < topk) bound_out[blockIdx.x].i = TK_EXHAUSTED;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

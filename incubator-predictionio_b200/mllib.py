@@ -80,12 +80,17 @@ class MatrixFactorizationModel:
         items, scores, cnt = self._handle().recommend(np.array([user], np.int32), num, mask)
         return [Rating(user, int(items[0, t]), float(scores[0, t])) for t in range(int(cnt[0]))]
 
-    def recommendProductsForUsers(self, users: np.ndarray, num: int, item_mask: Optional[np.ndarray] = None):
+    def recommendProductsForUsers(self, users: np.ndarray, num: int, item_mask: Optional[np.ndarray] = None,
+                                  item_weight: Optional[np.ndarray] = None):
         """Batched top-N (what batchPredict's cartesian + groupBy computes, ALSAlgorithm.scala:117-158)."""
-        return self._handle().recommend(np.ascontiguousarray(users, np.int32), num, item_mask)
+        return self._handle().recommend(np.ascontiguousarray(users, np.int32), num, item_mask, item_weight)
 
-    def similarProducts(self, query_items: Sequence[int], num: int, item_mask: Optional[np.ndarray] = None):
-        return self._handle().similar(np.asarray(list(query_items), np.int32), num, item_mask)
+    def similarProducts(self, query_items: Sequence[int], num: int, item_mask: Optional[np.ndarray] = None,
+                        item_weight: Optional[np.ndarray] = None, exclude_query: bool = True):
+        """exclude_query=True: similarproduct's `!queryList.contains(i)` rule; False: ecommerce predictSimilar, whose
+        isCandidateItem has no such rule (train-with-rate-event ECommAlgorithm.scala:492-525,527-557)."""
+        return self._handle().similar(np.asarray(list(query_items), np.int32), num, item_mask, item_weight,
+                                      keep_query_items=not exclude_query)
 
     def predict(self, user: int, product: int) -> float:
         return float(np.dot(self.userFeatures[user].astype(np.float64), self.productFeatures[product].astype(np.float64)))

@@ -19,16 +19,17 @@ REPO_ROOT = PKG_DIR.parent
 LIB_PATH = PKG_DIR / "libpio_als.so"
 CSRC = PKG_DIR / "csrc"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 DEDUP_NONE, DEDUP_SUM, DEDUP_KEEP_LAST = 0, 1, 2
 INIT_CALLER, INIT_HASH = 0, 1
+SIM_KEEP_QUERY_ITEMS = 1
 ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NUMERIC, ERR_IO, ERR_COMM = -1, -2, -3, -4, -5, -6
 
 EXPORTED_SYMBOLS = [
     "pio_als_abi_version", "pio_als_device_count", "pio_als_nccl_unique_id", "pio_als_create",
     "pio_als_destroy", "pio_als_last_error", "pio_als_set_ratings_coo", "pio_als_set_ratings_coo_device",
     "pio_als_set_init", "pio_als_run", "pio_als_get_factors", "pio_als_train", "pio_als_recommend",
-    "pio_als_similar", "pio_als_save", "pio_als_load", "pio_als_get_stats", "pio_als_get_phase_ms",
+    "pio_als_similar", "pio_als_similar_batch", "pio_als_model_import", "pio_als_save", "pio_als_load", "pio_als_get_stats", "pio_als_get_phase_ms",
     "pio_als_synth_ratings_device", "pio_nb_train", "pio_nb_predict",
 ]
 
@@ -217,32 +218,55 @@ class NativeALS:
         return uf, itf, uh, ih
 
     # -- scoring ----------------------------------------------------------------------------
-    def recommend(self, users, topk, item_mask=None):
+    def _mask_weight(self, item_mask, item_weight):
+        mk = None if item_mask is None else np.ascontiguousarray(item_mask, np.uint8)
+        if mk is not None and mk.shape != (self.n_items,):
+            raise ValueError("item_mask must have n_items entries")
+        wt = None if item_weight is None else np.ascontiguousarray(item_weight, np.float64)
+        if wt is not None and wt.shape != (self.n_items,):
+            raise ValueError("item_weight must have n_items entries")
+        return mk, wt
+
+    def recommend(self, users, topk, item_mask=None, item_weight=None):
         users = np.ascontiguousarray(users, np.int32)
         n = users.shape[0]
         oi = np.full((n, topk), -1, np.int32)
         os_ = np.zeros((n, topk), np.float32)
         oc = np.zeros(n, np.int32)
-        mk = None if item_mask is None else np.ascontiguousarray(item_mask, np.uint8)
-        if mk is not None and mk.shape != (self.n_items,):
-            raise ValueError("item_mask must have n_items entries")
+        mk, wt = self._mask_weight(item_mask, item_weight)
         self._check(lib().pio_als_recommend(self._h, _ptr(users, C.c_int32), C.c_int(n), C.c_int(topk),
-                                            _ptr(mk, C.c_uint8), _ptr(oi, C.c_int32), _ptr(os_, C.c_float),
-                                            _ptr(oc, C.c_int32)))
+                                            _ptr(mk, C.c_uint8), _ptr(wt, C.c_double), _ptr(oi, C.c_int32),
+                                            _ptr(os_, C.c_float), _ptr(oc, C.c_int32)))
         return oi, os_, oc
 
-    def similar(self, query_items, topk, item_mask=None):
+    def similar(self, query_items, topk, item_mask=None, item_weight=None, keep_query_items=False):
         q = np.ascontiguousarray(query_items, np.int32)
         oi = np.full(topk, -1, np.int32)
         os_ = np.zeros(topk, np.float32)
         oc = C.c_int32(0)
-        mk = None if item_mask is None else np.ascontiguousarray(item_mask, np.uint8)
-        if mk is not None and mk.shape != (self.n_items,):
-            raise ValueError("item_mask must have n_items entries")
+        mk, wt = self._mask_weight(item_mask, item_weight)
         self._check(lib().pio_als_similar(self._h, _ptr(q, C.c_int32), C.c_int(q.shape[0]), C.c_int(topk),
-                                          _ptr(mk, C.c_uint8), _ptr(oi, C.c_int32), _ptr(os_, C.c_float),
-                                          C.byref(oc)))
+                                          _ptr(mk, C.c_uint8), _ptr(wt, C.c_double),
+                                          C.c_int(SIM_KEEP_QUERY_ITEMS if keep_query_items else 0),
+                                          _ptr(oi, C.c_int32), _ptr(os_, C.c_float), C.byref(oc)))
         return oi, os_, int(oc.value)
+
+    def similar_batch(self, queries, topk, item_mask=None, item_weight=None, keep_query_items=False):
+        """queries: sequence of item-index sequences; returns (items [n, topk], scores [n, topk], count [n])."""
+        n = len(queries)
+        ptr = np.zeros(n + 1, np.int64)
+        ptr[1:] = np.cumsum([len(q) for q in queries])
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(q, np.int32) for q in queries]) if n and ptr[-1] else
+                                    np.zeros(0, np.int32), np.int32)
+        oi = np.full((n, topk), -1, np.int32)
+        os_ = np.zeros((n, topk), np.float32)
+        oc = np.zeros(n, np.int32)
+        mk, wt = self._mask_weight(item_mask, item_weight)
+        self._check(lib().pio_als_similar_batch(self._h, _ptr(ptr, C.c_int64), _ptr(flat, C.c_int32), C.c_int(n),
+                                                C.c_int(topk), _ptr(mk, C.c_uint8), _ptr(wt, C.c_double),
+                                                C.c_int(SIM_KEEP_QUERY_ITEMS if keep_query_items else 0),
+                                                _ptr(oi, C.c_int32), _ptr(os_, C.c_float), _ptr(oc, C.c_int32)))
+        return oi, os_, oc
 
     # -- persistence / introspection -----------------------------------------------------------
     def save(self, path: str):
@@ -257,6 +281,27 @@ class NativeALS:
         # read the header for the shape
         hdr = np.fromfile(path, dtype=np.int32, count=8)
         return cls(rank=int(hdr[3]), n_users=int(hdr[5]), n_items=int(hdr[6]), _handle=h)
+
+    @classmethod
+    def from_factors(cls, user_factors, item_factors, user_has=None, item_has=None, device: int = 0, lam=0.0,
+                     implicit=False, alpha=1.0) -> "NativeALS":
+        """pio_als_model_import: a scoring handle from host factors (user_factors may be None: item-only model)."""
+        itf = np.ascontiguousarray(item_factors, np.float32)
+        ni, k = itf.shape
+        uf = None if user_factors is None else np.ascontiguousarray(user_factors, np.float32)
+        nu = 0 if uf is None else uf.shape[0]
+        cfg = Config()
+        cfg.abi_version, cfg.rank, cfg.implicit_prefs = ABI_VERSION, int(k), int(bool(implicit))
+        cfg.n_users, cfg.n_items, cfg.device, cfg.world_size = int(nu), int(ni), int(device), 1
+        cfg.lambda_, cfg.alpha = float(lam), float(alpha)
+        uh = None if user_has is None else np.ascontiguousarray(user_has, np.uint8)
+        ih = None if item_has is None else np.ascontiguousarray(item_has, np.uint8)
+        h = C.c_void_p()
+        rc = lib().pio_als_model_import(C.byref(cfg), _ptr(uf, C.c_float), _ptr(itf, C.c_float), _ptr(uh, C.c_uint8),
+                                        _ptr(ih, C.c_uint8), C.byref(h))
+        if rc != 0:
+            raise NativeError(rc, lib().pio_als_last_error(None).decode())
+        return cls(rank=int(k), n_users=max(int(nu), 1), n_items=int(ni), _handle=h)
 
     def stats(self) -> dict:
         st = Stats()

@@ -208,23 +208,55 @@ class ECommAlgorithm(P2LAlgorithm):
                     mask[i] = 1
         return mask
 
+    def weightedItems(self) -> List[dict]:
+        """Latest `$set` of the constraint entity "weightedItems": [{"items": [...], "weight": w}, ...]
+        (adjust-score/src/main/scala/ECommAlgorithm.scala:402-429); Nil when the event does not exist."""
+        try:
+            cons = LEventStore.findByEntity(self.ap.appName, "constraint", "weightedItems", eventNames=["$set"],
+                                            limit=1, latest=True)
+        except FileNotFoundError:
+            return []
+        if not cons:
+            return []
+        return list(cons[0].properties.get("weights") or [])
+
+    def _weights(self, model: ECommModel) -> Optional[np.ndarray]:
+        """weights: Map[Int, Double].withDefaultValue(1.0) as a dense fp64 vector (adjust-score :258-266); later groups
+        overwrite earlier ones like `.toMap` does.  None when no weight group is set (nothing to multiply)."""
+        groups = self.weightedItems()
+        if not groups:
+            return None
+        w = np.ones(len(model.mf.productHas), np.float64)
+        for g in groups:
+            for item in g.get("items", []):
+                idx = model.itemStringIntMap.get(item)
+                if idx is not None:
+                    w[idx] = float(g["weight"])
+        return w
+
     def predict(self, model: ECommModel, query: Query) -> PredictedResult:
         black = {b for b in (model.itemStringIntMap.get(x) for x in self.genBlackList(query)) if b is not None}
         mask = self._mask(model, query, black)
+        weights = self._weights(model)
         uidx = model.userStringIntMap.get(query.user)
         top: List = []
         if uidx is not None and model.mf.userHas[uidx]:
-            items, scores, cnt = model.mf.recommendProductsForUsers(np.array([uidx], np.int32), query.num, mask)
-            top = [(int(items[0, t]), float(scores[0, t])) for t in range(int(cnt[0])) if scores[0, t] > 0]  # keep > 0
+            # predictKnownUser: dot product x weight, keep > 0 (best first, so filtering the top-N is the same thing)
+            items, scores, cnt = model.mf.recommendProductsForUsers(np.array([uidx], np.int32), query.num, mask, weights)
+            top = [(int(items[0, t]), float(scores[0, t])) for t in range(int(cnt[0])) if scores[0, t] > 0]
         else:
             recent = {model.itemStringIntMap.get(x) for x in self.getRecentItems(query)}
             recent.discard(None)
             recent = {r for r in recent if model.mf.productHas[r]}
-            if recent:  # predictSimilar: sum of cosines, > 0 only (query items stay candidates there: re-add not needed)
-                items, scores, cnt = model.mf.similarProducts(sorted(recent), query.num, mask)
+            if recent:
+                # predictSimilar: sum of cosines x weight, > 0 only.  isCandidateItem has no "not a query item" rule here
+                # (ECommAlgorithm.scala:492-525,527-557): recent items stay candidates unless blacklisted / seen.
+                items, scores, cnt = model.mf.similarProducts(sorted(recent), query.num, mask, weights, exclude_query=False)
                 top = [(int(items[t]), float(scores[t])) for t in range(cnt)]
-            else:       # predictDefault: popularity count
-                cand = [(i, float(model.popularCount.get(i, 0))) for i in range(len(mask)) if not mask[i]]
+            else:       # predictDefault: popularity count x weight (no > 0 filter in the reference)
+                wv = weights if weights is not None else None
+                cand = [(i, float(model.popularCount.get(i, 0)) * (float(wv[i]) if wv is not None else 1.0))
+                        for i in range(len(mask)) if not mask[i]]
                 cand.sort(key=lambda kv: (-kv[1], kv[0]))
                 top = cand[:query.num]
         return PredictedResult([ItemScore(model.itemIntStringMap(i), s) for i, s in top])

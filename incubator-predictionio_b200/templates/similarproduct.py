@@ -253,12 +253,14 @@ class Serving(LServing):
     def serve(self, query: Query, predictedResults) -> PredictedResult:
         std = []
         for pr in predictedResults:
-            if len(predictedResults) > 1 and len(pr.itemScores) > 1:
-                sc = np.array([x.score for x in pr.itemScores], np.float64)
-                mean, sd = sc.mean(), sc.std(ddof=1)  # breeze meanAndVariance -> sample stddev
-                std.append([ItemScore(x.item, 0.0 if sd == 0 else (x.score - mean) / sd) for x in pr.itemScores])
-            else:
+            if query.num == 1:            # "if query 1 item, don't standardize" (Serving.scala:33-35)
                 std.append(list(pr.itemScores))
+                continue
+            # otherwise every algorithm's scores are z-scored, also when only one algorithm is deployed (:36-57)
+            sc = np.array([x.score for x in pr.itemScores], np.float64)
+            mean = sc.mean() if sc.size else 0.0
+            sd = sc.std(ddof=1) if sc.size > 1 else 0.0   # breeze meanAndVariance: sample variance, 0 for n <= 1
+            std.append([ItemScore(x.item, 0.0 if sd == 0 else (x.score - mean) / sd) for x in pr.itemScores])
         comb: Dict[str, float] = {}
         for lst in std:
             for x in lst:

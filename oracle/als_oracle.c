@@ -386,8 +386,10 @@ static void topk_insert(scored_t *heap, int *n, int k, double s, int32_t i) {
 ORACLE_API void oracle_recommend(int32_t n_items, int k, const float *user_f,
                                  const uint8_t *user_has, const float *item_f,
                                  const uint8_t *item_has, const int32_t *users, int n_q,
-                                 int topk, const uint8_t *mask, int32_t *out_items,
-                                 float *out_scores, int32_t *out_count) {
+                                 int topk, const uint8_t *mask, const double *weight,
+                                 int32_t *out_items, float *out_scores, int32_t *out_count) {
+  /* weight (nullable): adjustedScore = s * weights(i), the ecommerce template's weightedItems
+   * (examples/scala-parallel-ecommercerecommendation/adjust-score/src/main/scala/ECommAlgorithm.scala:490-497) */
 #pragma omp parallel for schedule(dynamic, 1)
   for (int q = 0; q < n_q; ++q) {
     scored_t *best = (scored_t *)malloc(sizeof(scored_t) * (size_t)(topk > 0 ? topk : 1));
@@ -401,6 +403,7 @@ ORACLE_API void oracle_recommend(int32_t n_items, int k, const float *user_f,
         const float *y = item_f + (size_t)i * k;
         double s = 0.0;
         for (int t = 0; t < k; ++t) s += (double)x[t] * (double)y[t];
+        if (weight) s = s * weight[i];
         topk_insert(best, &n, topk, s, i);
       }
     }
@@ -419,8 +422,9 @@ ORACLE_API void oracle_recommend(int32_t n_items, int k, const float *user_f,
  * factor are skipped (:146-149). */
 ORACLE_API void oracle_similar(int32_t n_items, int k, const float *item_f,
                                const uint8_t *item_has, const int32_t *query, int nq,
-                               int topk, const uint8_t *mask, int32_t *out_items,
-                               float *out_scores, int32_t *out_count) {
+                               int topk, const uint8_t *mask, const double *weight,
+                               int keep_query /* ecommerce predictSimilar: query items stay candidates */,
+                               int32_t *out_items, float *out_scores, int32_t *out_count) {
   scored_t *best = (scored_t *)malloc(sizeof(scored_t) * (size_t)(topk > 0 ? topk : 1));
   int n = 0;
   int nvalid = 0;
@@ -432,7 +436,7 @@ ORACLE_API void oracle_similar(int32_t n_items, int k, const float *item_f,
       if (mask && mask[i]) continue;
       int is_query = 0;
       for (int q = 0; q < nq; ++q) if (query[q] == i) is_query = 1;
-      if (is_query) continue;
+      if (is_query && !keep_query) continue;
       const float *f = item_f + (size_t)i * k;
       double score = 0.0;
       for (int q = 0; q < nq; ++q) {
@@ -448,6 +452,7 @@ ORACLE_API void oracle_similar(int32_t n_items, int k, const float *item_f,
         const double n1n2 = sqrt(n1) * sqrt(n2);
         score += (n1n2 == 0.0) ? 0.0 : d / n1n2;
       }
+      if (weight) score = score * weight[i];
       if (score > 0.0) topk_insert(best, &n, topk, score, i);
     }
   }

@@ -159,7 +159,7 @@ def als_train(n_users, n_items, user, item, rating, rank, iters, lam, implicit, 
     return uf, itf, uh[:n_users], ih[:n_items]
 
 
-def recommend(user_f, user_has, item_f, item_has, users, topk, mask=None):
+def recommend(user_f, user_has, item_f, item_has, users, topk, mask=None, weight=None):
     user_f = np.ascontiguousarray(user_f, np.float32)
     item_f = np.ascontiguousarray(item_f, np.float32)
     users = np.ascontiguousarray(users, np.int32)
@@ -171,14 +171,15 @@ def recommend(user_f, user_has, item_f, item_has, users, topk, mask=None):
     uh = None if user_has is None else np.ascontiguousarray(user_has, np.uint8)
     ih = None if item_has is None else np.ascontiguousarray(item_has, np.uint8)
     mk = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    wt = None if weight is None else np.ascontiguousarray(weight, np.float64)
     lib().oracle_recommend(C.c_int32(n_items), C.c_int(k), _p(user_f, C.c_float), _p(uh, C.c_uint8),
                            _p(item_f, C.c_float), _p(ih, C.c_uint8), _p(users, C.c_int32), C.c_int(nq),
-                           C.c_int(topk), _p(mk, C.c_uint8), _p(oi, C.c_int32), _p(os_, C.c_float),
+                           C.c_int(topk), _p(mk, C.c_uint8), _p(wt, C.c_double), _p(oi, C.c_int32), _p(os_, C.c_float),
                            _p(oc, C.c_int32))
     return oi, os_, oc
 
 
-def similar(item_f, item_has, query, topk, mask=None):
+def similar(item_f, item_has, query, topk, mask=None, weight=None, keep_query=False):
     item_f = np.ascontiguousarray(item_f, np.float32)
     query = np.ascontiguousarray(query, np.int32)
     n_items, k = item_f.shape
@@ -187,9 +188,10 @@ def similar(item_f, item_has, query, topk, mask=None):
     oc = C.c_int32(0)
     ih = None if item_has is None else np.ascontiguousarray(item_has, np.uint8)
     mk = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    wt = None if weight is None else np.ascontiguousarray(weight, np.float64)
     lib().oracle_similar(C.c_int32(n_items), C.c_int(k), _p(item_f, C.c_float), _p(ih, C.c_uint8),
                          _p(query, C.c_int32), C.c_int(query.shape[0]), C.c_int(topk), _p(mk, C.c_uint8),
-                         _p(oi, C.c_int32), _p(os_, C.c_float), C.byref(oc))
+                         _p(wt, C.c_double), C.c_int(int(keep_query)), _p(oi, C.c_int32), _p(os_, C.c_float), C.byref(oc))
     return oi, os_, int(oc.value)
 
 

@@ -298,6 +298,76 @@ def test_recommend_and_similar_are_bit_exact(native, oracle):
             assert np.array_equal(gi, oi) and np.array_equal(gs, os_) and gc == oc
 
 
+def test_scoring_weights_query_items_large_topk_and_batch(native, oracle):
+    """ABI v2 scoring semantics, all bit-exact against the oracle: per-item score weights (ecommerce adjust-score
+    ECommAlgorithm.scala:258-266,490-497), query items kept as candidates (ecommerce predictSimilar, :492-525), more
+    than 128 results per query (several bounded passes), the batch entry point, and an imported (item-only) model."""
+    nu, ni, nnz = 2000, 3000, 40000
+    u, i, r = synth.synth_ratings(nu, ni, nnz, seed=12, implicit=True)
+    m = native.NativeALS(24, nu, ni, lam=0.01, implicit=True)
+    m.set_ratings(u, i, r, dedup=1)
+    m.set_init(synth.synth_init_factors(nu, 24, 2, 0))
+    m.run(2)
+    uf, itf, uh, ih = m.get_factors()
+    rng = np.random.default_rng(5)
+    w = np.ones(ni, np.float64)
+    w[rng.integers(0, ni, 300)] = rng.choice([0.0, 0.5, 2.0, 3.25, -1.0], 300)
+    mask = (np.arange(ni) % 7 == 0).astype(np.uint8)
+    users = np.array([3, 4, 5, 1999, -1], np.int32)
+    for topk in (10, 128, 129, 300, 1000):
+        for mk, wt in ((None, None), (mask, w), (None, w)):
+            gi, gs, gc = m.recommend(users, topk, mk, wt)
+            oi, os_, oc = oracle.recommend(uf, uh, itf, ih, users, topk, mk, wt)
+            assert np.array_equal(gc, oc) and np.array_equal(gi, oi) and np.array_equal(gs, os_), (topk, mk is None, wt is None)
+    have = np.flatnonzero(ih)
+    queries = [[int(have[0])], [int(have[3]), int(have[10]), int(have[50])], [int(have[7]), int(have[8])], []]
+    for topk in (20, 200):
+        for keep in (False, True):
+            for mk, wt in ((None, None), (mask, w)):
+                for q in queries:
+                    q = np.array(q, np.int32)
+                    gi, gs, gc = m.similar(q, topk, mk, wt, keep_query_items=keep)
+                    oi, os_, oc = oracle.similar(itf, ih, q, topk, mk, wt, keep)
+                    assert gc == oc and np.array_equal(gi, oi) and np.array_equal(gs, os_), (topk, keep, q)
+                bi, bs, bc = m.similar_batch(queries, topk, mk, wt, keep_query_items=keep)
+                for j, q in enumerate(queries):
+                    oi, os_, oc = oracle.similar(itf, ih, np.array(q, np.int32), topk, mk, wt, keep)
+                    assert bc[j] == oc and np.array_equal(bi[j], oi) and np.array_equal(bs[j], os_)
+    # keep_query really changes the answer: the query item itself is the most similar item
+    gi, _, _ = m.similar(np.array([int(have[3])], np.int32), 5, keep_query_items=True)
+    assert gi[0] == have[3]
+    # imported models score like the trained handle (full and item-only)
+    m2 = native.NativeALS.from_factors(uf, itf, uh, ih)
+    for x, y in zip(m.recommend(users, 10), m2.recommend(users, 10)):
+        assert np.array_equal(x, y)
+    m3 = native.NativeALS.from_factors(None, itf, None, ih)
+    q = np.array(queries[1], np.int32)
+    for x, y in zip(m.similar(q, 20), m3.similar(q, 20)):
+        assert np.array_equal(x, y)
+    gi, gs, gc = m3.recommend(np.array([0], np.int32), 5)
+    assert gc[0] == 0
+
+
+def test_load_rejects_corrupt_files(native, tmp_path):
+    nu, ni = 50, 40
+    u, i, r = synth.synth_ratings(nu, ni, 800, seed=8, implicit=False)
+    m = native.NativeALS(6, nu, ni, lam=0.01)
+    m.set_ratings(u, i, r)
+    m.set_init(synth.synth_init_factors(nu, 6, 2, 0))
+    m.run(1)
+    p = tmp_path / "model.pioals"
+    m.save(p)
+    raw = bytearray(p.read_bytes())
+    for name, mut in (("truncated", raw[:-10]), ("huge_users", raw[:20] + (2 ** 31 - 1).to_bytes(4, "little") + raw[24:]),
+                      ("negative_rank", raw[:12] + (-5).to_bytes(4, "little", signed=True) + raw[16:]),
+                      ("bad_magic", b"XXXXXXXX" + raw[8:])):
+        q = tmp_path / f"{name}.pioals"
+        q.write_bytes(bytes(mut))
+        with pytest.raises(native.NativeError) as ei:
+            native.NativeALS.load(q)
+        assert ei.value.code == native.ERR_IO, name
+
+
 def test_save_load_round_trip(native, oracle, tmp_path):
     nu, ni, nnz = 800, 200, 9000
     u, i, r = synth.synth_ratings(nu, ni, nnz, seed=8, implicit=False)
