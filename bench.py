@@ -572,7 +572,9 @@ def main():
         del prob
     if not args.no_topk and args.gpus == 1:
         try:
-            out["topk"] = topk_bench(native, o, cores, m, nu, ni, k, uf_T, itf_T, uh, ih, peaks, dev)
+            # the handle holds the factors of its LAST run: iteration W+K+1 when the parity iteration ran
+            cur_u, cur_i = (uf_T1, itf_T1) if want_parity else (uf_T, itf_T)
+            out["topk"] = topk_bench(native, o, cores, m, nu, ni, k, cur_u, cur_i, uh, ih, peaks, dev)
         except Exception as e:   # a scoring failure must not hide the training line
             out["topk"] = {"error": repr(e)}
             rc = rc or 4

@@ -26,6 +26,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "als_lockstep.cuh"
+
 namespace pio {
 
 struct SolveParams {
@@ -66,7 +68,11 @@ struct SolveCfg {
   static constexpr int BLK = TB * TB + 8;       // padded block stride inside a slot (floats)
   static constexpr int SLOT = G * BLK;
   static constexpr bool WARP_CHOL = KP <= 64;
-  static constexpr int LM = WARP_CHOL ? 0 : KP * (KP + 1);  // cooperative Cholesky scratch
+  // rank 65..128: every row goes through the work-list path -- the kernel emits (partial) normal equations in the
+  // LsLayout<128> slot layout and als_finish_ls128_kernel sums the parts and runs the lockstep Cholesky
+  static constexpr bool LS_PARTIAL = KP == 128;
+  static constexpr int PART_FLOATS = LS_PARTIAL ? LsLayout<LS_PARTIAL ? KP : 64>::SIZE + KP : SLOT + KP;
+  static constexpr int LM = 0;
 
   // the Cholesky slots alias the (dead) staging ring and b partials
   __host__ __device__ static constexpr int region0() {
@@ -296,81 +302,6 @@ __device__ __forceinline__ void chol_solve_warp(float* slot, const float* bvec, 
 }
 
 // ------------------------------------------------------------------------------------------
-// Cooperative Cholesky + solve for N > 64 (rank 65..128): whole CTA, matrix unpacked to smem.
-// Parity path for the rank-128 configuration; not yet tuned.
-// ------------------------------------------------------------------------------------------
-template <int N, int TB, int BLK, bool IMPLICIT, int NT>
-__device__ void chol_solve_cta(const float* slot, const float* bvec, const float* yty, float ridge,
-                               int k, float* Lm /* N x (N+1) */, float* dst_row, int* fail) {
-  constexpr int NB = N / TB;
-  constexpr int LD = N + 1;
-  const int tid = threadIdx.x;
-  __shared__ float s_inv;
-  __shared__ int s_bad;
-  if (tid == 0) s_bad = 0;
-  for (int o = tid; o < N * N; o += NT) {
-    const int i = o / N, c = o % N;
-    if (c <= i) {
-      const int cb = c / TB, a = c % TB, ib = i / TB, b = i % TB;
-      float v = slot[(cb * NB - cb * (cb - 1) / 2 + ib - cb) * BLK + a * TB + b];
-      if (IMPLICIT) v += yty[i * N + c];
-      if (c == i) v += ridge + (i >= k ? 1.f : 0.f);
-      Lm[i * LD + c] = v;
-    }
-  }
-  float* y = Lm + N;  // column N of every row is free: y[i] at Lm[i*LD + N]
-  for (int i = tid; i < N; i += NT) Lm[i * LD + N] = bvec[i];
-  __syncthreads();
-  for (int j = 0; j < N; ++j) {
-    if (tid == 0) {
-      float d = Lm[j * LD + j];
-      if (!(d > 0.f)) { s_bad = 1; d = 1.f; }
-      float inv = rsqrt_fast(d);
-      inv = inv * (1.5f - 0.5f * d * inv * inv);
-      s_inv = inv;
-      Lm[j * LD + j] = d * inv;
-    }
-    __syncthreads();
-    const float inv = s_inv;
-    for (int i = j + 1 + tid; i < N; i += NT) Lm[i * LD + j] *= inv;
-    __syncthreads();
-    const int m = N - 1 - j;
-    for (int o = tid; o < m * m; o += NT) {
-      const int i = j + 1 + o / m, c = j + 1 + o % m;
-      if (c <= i) Lm[i * LD + c] -= Lm[i * LD + j] * Lm[c * LD + j];
-    }
-    __syncthreads();
-  }
-  (void)y;
-  if (tid < 32) {  // triangular solves by one warp (lanes stride the rows)
-    const int lane = tid;
-    for (int j = 0; j < N; ++j) {  // forward
-      float yj = 0.f;
-      if (lane == 0) {
-        yj = Lm[j * LD + N] / Lm[j * LD + j];
-        Lm[j * LD + N] = yj;
-      }
-      yj = __shfl_sync(0xffffffffu, yj, 0);
-      for (int i = j + 1 + lane; i < N; i += 32) Lm[i * LD + N] -= Lm[i * LD + j] * yj;
-      __syncwarp();
-    }
-    for (int i = N - 1; i >= 0; --i) {  // backward
-      float xi = 0.f;
-      if (lane == 0) {
-        xi = Lm[i * LD + N] / Lm[i * LD + i];
-        Lm[i * LD + N] = xi;
-      }
-      xi = __shfl_sync(0xffffffffu, xi, 0);
-      for (int j = lane; j < i; j += 32) Lm[j * LD + N] -= Lm[i * LD + j] * xi;
-      __syncwarp();
-    }
-    for (int i = lane; i < N; i += 32) dst_row[i] = Lm[i * LD + N];
-    if (lane == 0 && s_bad) atomicAdd(fail, 1);
-  }
-  __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------
 // The half-step kernel.
 // ------------------------------------------------------------------------------------------
 template <class Cfg, bool IMPLICIT>
@@ -583,6 +514,35 @@ als_solve_kernel(const SolveParams p) {
   __syncthreads();  // ring + bpart are dead from here on (the slots alias them)
   if (p.partial) {
     // part of a long row: emit the partial normal equations; als_finish_kernel sums the parts and solves
+    if (Cfg::LS_PARTIAL) {
+      // lower triangle in the LsLayout<KP> slot layout: this thread's block holds G[8 bi + a][8 bj + b] (bi <= bj), i.e. the
+      // lower-triangle elements (r = 8 bj + b, c = 8 bi + a); the 8 columns of one r are two aligned chunks of four
+      using LL = LsLayout<Cfg::LS_PARTIAL ? KP : 64>;
+      if (worker && srow[g] >= 0) {
+        float* out = p.partial + (size_t)srow[g] * Cfg::PART_FLOATS;
+#pragma unroll
+        for (int b = 0; b < TB; ++b) {
+          const int r = TB * bj + b, rb = r >> 4, rr = r & 15;
+#pragma unroll
+          for (int hh = 0; hh < TB / 4; ++hh) {
+            const int c0 = TB * bi + 4 * hh, cb = c0 >> 4, cc = c0 & 15;
+            if (cb < rb) {
+              *reinterpret_cast<float4*>(out + LL::offd(rb, cb, rr, cc)) =
+                  make_float4(acc[4 * hh + 0][b], acc[4 * hh + 1][b], acc[4 * hh + 2][b], acc[4 * hh + 3][b]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (cc + e <= rr) out[LL::diag(rb, rr, cc + e)] = acc[4 * hh + e][b];
+            }
+          }
+        }
+      }
+      for (int o = tid; o < NG * KP; o += NT) {
+        const int gg = o / KP;
+        if (srow[gg] >= 0) p.partial[(size_t)srow[gg] * Cfg::PART_FLOATS + LL::SIZE + (o % KP)] = bvec[o];
+      }
+      return;
+    }
     if (worker && srow[g] >= 0) {
       float* out = p.partial + (size_t)srow[g] * (SLOT + KP) + bid * BLK;
 #pragma unroll
@@ -618,17 +578,8 @@ als_solve_kernel(const SolveParams p) {
           slots + m * SLOT, bvec + m * KP, p.yty, ridge, p.k, colbuf + w * 2 * KP, dinvb + w * KP,
           p.dst + (size_t)(p.dst_row_offset + r) * KP, p.fail);
     }
-  } else {
-    for (int m = 0; m < NMAT; ++m) {
-      const int r = srow[m];
-      if (r < 0) continue;
-      if (p.ptr[r + 1] == p.ptr[r]) continue;
-      const float ridge = p.lambda * p.nreg[r];
-      chol_solve_cta<KP, TB, BLK, IMPLICIT, NT>(slots + m * SLOT, bvec + m * KP, p.yty, ridge, p.k,
-                                                 lm, p.dst + (size_t)(p.dst_row_offset + r) * KP,
-                                                 p.fail);
-    }
   }
+  // rank 65..128 never reaches this point: all of its rows are work-list items (LS_PARTIAL)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -657,20 +608,38 @@ als_finish_kernel(const SolveParams p, const int* __restrict__ row_part_ptr, int
     __syncwarp();
     chol_solve_warp<Cfg::WARP_CHOL ? KP : 16, Cfg::TB, Cfg::BLK, IMPLICIT>(
         slot, bv, p.yty, p.lambda * p.nreg[r], p.k, colbuf, dinv, p.dst + (size_t)(p.dst_row_offset + r) * KP, p.fail);
-  } else {
-    const int r = blockIdx.x;
-    float* slot = fsm;
-    float* bv = slot + SLOT;
-    float* lm = bv + KP;
-    const int p0 = row_part_ptr[r], p1 = row_part_ptr[r + 1];
-    for (int o = threadIdx.x; o < SLOT + KP; o += Cfg::NT) {
-      float s = 0.f;
-      for (int q = p0; q < p1; ++q) s += p.partial[(size_t)q * (SLOT + KP) + o];
-      slot[o] = s;
+  }
+}
+
+// Rank 65..128: one warp per row; fixed-order sum of the row's partial normal equations (LsLayout<128> + b) into shared
+// memory, then the lockstep Cholesky with all 32 lanes on the one 128 x 128 matrix.
+template <bool IMPLICIT>
+__global__ void __launch_bounds__(32) als_finish_ls128_kernel(const SolveParams p, const int* __restrict__ row_part_ptr,
+                                                              int row0, int n_rows, int part0) {
+  using LL = LsLayout<128>;
+  constexpr int PF = LL::SIZE + 128;
+  extern __shared__ __align__(16) float fsm128[];
+  float* slot = fsm128;
+  float* bv = slot + LL::STRIDE;
+  float* colbuf = bv + 128;
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int rr = blockIdx.x; rr < n_rows; rr += gridDim.x) {
+    const int r = row0 + rr;
+    const int p0 = row_part_ptr[r] - part0, p1 = row_part_ptr[r + 1] - part0;
+    for (int o = lane; o < PF / 4; o += 32) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = p0; q < p1; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.partial + (size_t)q * PF) + o);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      if (o < LL::SIZE / 4) reinterpret_cast<float4*>(slot)[o] = s;
+      else reinterpret_cast<float4*>(bv)[o - LL::SIZE / 4] = s;
     }
-    __syncthreads();
-    chol_solve_cta<KP, Cfg::TB, Cfg::BLK, IMPLICIT, Cfg::NT>(slot, bv, p.yty, p.lambda * p.nreg[r], p.k, lm,
-                                                             p.dst + (size_t)(p.dst_row_offset + r) * KP, p.fail);
+    __syncwarp();
+    chol_lockstep<128, IMPLICIT>(slot, bv, p.yty, p.lambda * p.nreg[r], p.k, colbuf,
+                                 p.dst + (size_t)(p.dst_row_offset + r) * 128, true, p.fail);
+    __syncwarp();
   }
 }
 

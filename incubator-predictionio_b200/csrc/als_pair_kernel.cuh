@@ -54,6 +54,35 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// First mma of a chain: C = 0 as an immediate (no registers to clear)
+__device__ __forceinline__ void mma_tf32_z(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};\n"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+
+// B fragment as one 64-bit register pair
+__device__ __forceinline__ uint64_t pack2(uint32_t x, uint32_t y) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(x), "r"(y));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_p(float (&d)[4], const uint32_t (&a)[4], uint64_t b) {
+  asm volatile(
+      "{\n .reg .b32 b0, b1;\n mov.b64 {b0, b1}, %8;\n"
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {b0,b1}, {%0,%1,%2,%3};\n}\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "l"(b));
+}
+__device__ __forceinline__ void mma_tf32_zp(float (&d)[4], const uint32_t (&a)[4], uint64_t b) {
+  asm volatile(
+      "{\n .reg .b32 b0, b1;\n mov.b64 {b0, b1}, %4;\n"
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%5,%6,%7,%8}, {b0,b1}, {%9,%9,%9,%9};\n}\n"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "l"(b), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "f"(0.f));
+}
+
 // Accumulates sum c1 y y^T (lower triangle, slot layout) and b of ratings [beg, end) into `slot` / `bv`.
 template <bool IMPLICIT>
 __device__ __forceinline__ void accumulate_row(const SolveParams& p, long long beg, long long end, float* ring,
@@ -140,25 +169,33 @@ __device__ __forceinline__ void accumulate_row(const SolveParams& p, long long b
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        uint32_t h;   // round-to-nearest TF32 part: |v - h| <= 2^-11 |v|, v - h exact (the dropped lo*lo term is 2^-22)
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v[e]));
-        hi[i][e] = h;
-        lo[i][e] = __float_as_uint(v[e] - __uint_as_float(h));
+        // Veltkamp split: h = the 11 leading bits of v rounded to nearest (exactly a TF32 value), v - h exact; three
+        // FMA-pipe instructions instead of the ~5 ALU instructions cvt.rna.tf32 expands to on sm_100.  |v - h| <= 2^-11 |v|;
+        // the dropped lo*lo term is 2^-22.
+        // (intrinsics: the compiler must not contract c - (c - v) into FMAs, which would return v itself)
+        const float c = __fmul_rn(v[e], 8193.f);       // 2^13 + 1
+        const float h = __fsub_rn(c, __fsub_rn(c, v[e]));
+        hi[i][e] = __float_as_uint(h);
+        lo[i][e] = __float_as_uint(__fsub_rn(v[e], h));
       }
     }
     // D(16i.., 8j..) += A_i B_j for the tiles on or below the diagonal: j <= 2i+1.  The tensor core adds with
     // truncation: only the 8 products of one chunk are summed inside it (small terms first), the running sum over
     // the chunks is a round-to-nearest FADD in registers.
-    int tile = 0;
+    // n-tile j outermost: its B fragments (two registers each, hi and lo) are formed once and serve every m-tile
+    // i >= j/2 below it -- SASS wants the pair in adjacent registers, so each use of a fresh pair costs two MOVs.
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j < 8; ++j) {
+      const int bi = j >> 1, be = j & 1;
+      // packed as 64-bit values: the pair is materialised once (two MOVs) and stays adjacent for all its uses
+      const uint64_t bh = pack2(hi[bi][be], hi[bi][be + 2]), bl = pack2(lo[bi][be], lo[bi][be + 2]);
 #pragma unroll
-      for (int j = 0; j <= 2 * i + 1; ++j, ++tile) {
-        const int bi = j >> 1, be = j & 1;
-        float d[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_tf32(d, lo[i], hi[bi][be], hi[bi][be + 2]);
-        mma_tf32(d, hi[i], lo[bi][be], lo[bi][be + 2]);
-        mma_tf32(d, hi[i], hi[bi][be], hi[bi][be + 2]);
+      for (int i = bi; i < 4; ++i) {
+        const int tile = i * (i + 1) + j;               // tiles of m-tile i start at sum_{i' < i} (2 i' + 2) = i (i + 1)
+        float d[4];
+        mma_tf32_zp(d, lo[i], bh);
+        mma_tf32_p(d, hi[i], bl);
+        mma_tf32_p(d, hi[i], bh);
         acc[tile][0] += d[0];
         acc[tile][1] += d[1];
         acc[tile][2] += d[2];
@@ -217,9 +254,15 @@ __device__ __forceinline__ void fill_identity(float* slot, float* bv) {
   __syncwarp();
 }
 
-template <bool IMPLICIT>
-__global__ void __launch_bounds__(32, 12) als_solve_pair_kernel(const SolveParams p, int n_items) {
-  extern __shared__ __align__(16) float smem[];
+// WARPS independent workers per CTA.  The only CTA-wide synchronisation is one barrier before the solve: the warps of
+// a CTA then walk the (fully unrolled, ~80 KB) lockstep solver together, so that an SM's instruction cache holds a few
+// positions of that code instead of twelve (ncu, one-warp CTAs: "no instruction" was the first stall reason of the
+// user half-step, 1.7 per issued instruction).
+template <bool IMPLICIT, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 12 / WARPS) als_solve_pair_kernel(const SolveParams p, int n_items) {
+  extern __shared__ __align__(16) float smem_all[];
+  const int warp = threadIdx.x >> 5;
+  float* smem = smem_all + warp * W_FLOATS;
   float* slot0 = smem;
   float* slot1 = smem + SLOT_STRIDE;
   float* ring = slot1;                  // dead whenever slot 1 is written
@@ -231,44 +274,50 @@ __global__ void __launch_bounds__(32, 12) als_solve_pair_kernel(const SolveParam
   const int npairs = (n_items + 1) >> 1;
 
 #pragma unroll 1
-  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+  for (int base = blockIdx.x * WARPS; base < npairs; base += gridDim.x * WARPS) {
+    const int pair = base + warp;
     int row0 = -1, row1 = -1;
+    if (pair < npairs) {
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      const int item = 2 * pair + h;
-      float* slot = h ? slot1 : slot0;
-      float* bv = bvec + h * VSTR;
-      if (item >= n_items) {
-        fill_identity(slot, bv);
-        continue;
-      }
-      long long beg, end;
-      if (p.partial) {
-        beg = p.wl_beg[item];
-        end = p.wl_end[item];
-      } else {
-        const int r = p.row_begin + item;
-        beg = p.ptr[r];
-        end = p.ptr[r + 1];
-        if (h) row1 = r;
-        else row0 = r;
-      }
-      accumulate_row<IMPLICIT>(p, beg, end, ring, mval, slot, bv);
-      if (p.partial) {
-        // part of a long row: emit the partial normal equation (slot layout + b); als_finish_pair_kernel sums and solves
-        float* out = p.partial + (size_t)item * PART_FLOATS;
-        for (int o = lane; o < LL::SIZE / 4; o += 32)
-          reinterpret_cast<float4*>(out)[o] = reinterpret_cast<const float4*>(slot)[o];
-        for (int o = lane; o < KP; o += 32) out[LL::SIZE + o] = bv[o];
-        __syncwarp();
+      for (int h = 0; h < 2; ++h) {
+        const int item = 2 * pair + h;
+        float* slot = h ? slot1 : slot0;
+        float* bv = bvec + h * VSTR;
+        if (item >= n_items) {
+          fill_identity(slot, bv);
+          continue;
+        }
+        long long beg, end;
+        if (p.partial) {
+          beg = p.wl_beg[item];
+          end = p.wl_end[item];
+        } else {
+          const int r = p.row_begin + item;
+          beg = p.ptr[r];
+          end = p.ptr[r + 1];
+          if (h) row1 = r;
+          else row0 = r;
+        }
+        accumulate_row<IMPLICIT>(p, beg, end, ring, mval, slot, bv);
+        if (p.partial) {
+          // part of a long row: emit the partial normal equation (slot layout + b); als_finish_pair_kernel sums and solves
+          float* out = p.partial + (size_t)item * PART_FLOATS;
+          for (int o = lane; o < LL::SIZE / 4; o += 32)
+            reinterpret_cast<float4*>(out)[o] = reinterpret_cast<const float4*>(slot)[o];
+          for (int o = lane; o < KP; o += 32) out[LL::SIZE + o] = bv[o];
+          __syncwarp();
+        }
       }
     }
     if (p.partial) continue;
-    const int myrow = grp ? row1 : row0;
-    const int rr = myrow < 0 ? p.row_begin : myrow;
-    chol_lockstep<KP, IMPLICIT>(grp ? slot1 : slot0, bvec + grp * VSTR, p.yty, p.lambda * p.nreg[rr], p.k,
-                                colbuf + grp * VSTR, p.dst + (size_t)(p.dst_row_offset + rr) * KP, myrow >= 0, p.fail);
-    __syncwarp();
+    if (WARPS > 1) __syncthreads();
+    if (pair < npairs) {
+      const int myrow = grp ? row1 : row0;
+      const int rr = myrow < 0 ? p.row_begin : myrow;
+      chol_lockstep<KP, IMPLICIT>(grp ? slot1 : slot0, bvec + grp * VSTR, p.yty, p.lambda * p.nreg[rr], p.k,
+                                  colbuf + grp * VSTR, p.dst + (size_t)(p.dst_row_offset + rr) * KP, myrow >= 0, p.fail);
+      __syncwarp();
+    }
   }
 }
 

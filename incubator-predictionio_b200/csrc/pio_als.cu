@@ -341,6 +341,7 @@ struct Side {
   int* row_part_ptr = nullptr;   // [n_heavy + 1]
   float* partial = nullptr;      // [n_parts][SLOT + KP]
   int n_parts = 0;
+  std::vector<int> h_row_part_ptr;   // host copy (rank 65..128 walks its rows in tiles)
 };
 
 enum EvKind { EV_SOLVE = 0, EV_GRAM = 1, EV_COMM = 2, EV_SOLVE_USER = 3, EV_NKIND = 4 };   // EV_SOLVE = item half-step
@@ -370,6 +371,7 @@ struct pio_als_handle {
   bool use_mma = true;        // PIO_ALS_MMA=0: FP32 kernel instead of the mma.sync kernels for rank 33..64
   bool use_pair = true;       // PIO_ALS_MMA=1: round-1 one-warp-per-row mma.sync kernel instead of the pair kernel
   int pair_seg_t = PAIR_SEG_T, pair_part = PAIR_PART;   // PIO_ALS_SEG_T / PIO_ALS_PART
+  int pair_warps = 4;         // PIO_ALS_PAIR_WARPS: warps per CTA of the pair kernel (1, 2, 4, 6 or 12)
   bool tc_split = false;      // PIO_ALS_TC_SPLIT=1: the tensor-core kernel only accumulates, a second kernel solves (measured: no gain)
   float* tc_out = nullptr;    // split mode: normal equations of one tile of rows ([rows][ASLOT + KP])
   size_t tc_out_rows = 0;
@@ -442,6 +444,7 @@ static void free_side(pio_als_handle* h, Side& s, bool keep_factors) {
   dfree(h, s.idx); dfree(h, s.val); dfree(h, s.nreg); dfree(h, s.cand_ext);
   dfree(h, s.part_beg); dfree(h, s.part_end); dfree(h, s.row_part_ptr); dfree(h, s.partial);
   s.n_parts = 0;
+  s.h_row_part_ptr.clear();
   if (!keep_factors) dfree(h, s.F);
 }
 
@@ -499,7 +502,8 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
   // ratings stay whole, longer rows become 512-rating parts of the same kernel (two-level summation); round-1 mma /
   // tcgen05 kernels: rows up to 8192 ratings whole, longer rows as 2016-rating parts on the FP32 kernel; FP32 kernel
   // (other ranks): cut at 4096
-  row.heavy_t = row.use_pair ? h->pair_seg_t : (row.use_tc || (h->KP == 64 && h->use_mma)) ? HEAVY_T_TC : HEAVY_T;
+  // rank 65..128: every row is a work-list row (FP32 Gramian kernel -> partial normal equations -> lockstep finish kernel)
+  row.heavy_t = h->KP == 128 ? 0 : row.use_pair ? h->pair_seg_t : (row.use_tc || (h->KP == 64 && h->use_mma)) ? HEAVY_T_TC : HEAVY_T;
   row.part_len = row.use_pair ? h->pair_part : PART;
   local_rows_kernel<<<nblk(row.R + 1, 256), 256, 0, st>>>(ptr_full, rk * row.R, row.R, be[0], row.inv, row.deg,
                                                            row.npos, h->cfg.implicit_prefs, row.ptr, row.nreg,
@@ -526,6 +530,7 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
     }
     rpp[row.n_heavy] = (int)pb.size();
     row.n_parts = (int)pb.size();
+    row.h_row_part_ptr = rpp;
     CK(h, dalloc(h, &row.part_beg, pb.size()));
     CK(h, dalloc(h, &row.part_end, pe.size()));
     CK(h, dalloc(h, &row.row_part_ptr, rpp.size()));
@@ -782,23 +787,29 @@ static cudaError_t launch_tc(pio_als_handle* h, Side& dst, const SolveParams& p,
   return e;
 }
 
-// Rank 33..64, pair kernel (als_pair_kernel.cuh): persistent one-warp CTAs, twelve per SM.  Long rows first (their
-// 512-rating parts as work items, then the finish kernel), then the rows that stay whole.
-static cudaError_t launch_pair(pio_als_handle* h, Side& dst, const SolveParams& p0, bool imp) {
+template <int WARPS>
+static cudaError_t launch_pair_w(pio_als_handle* h, Side& dst, const SolveParams& p0, bool imp) {
   cudaError_t e = cudaSuccess;
   static bool attr_set[64] = {};
-  const size_t smem = pr::smem_bytes(1);
+  const size_t smem = pr::smem_bytes(WARPS), fsmem = pr::smem_bytes(1);
   if (h->cfg.device < 64 && !attr_set[h->cfg.device]) {
-    const void* ks[4] = {(const void*)pr::als_solve_pair_kernel<true>, (const void*)pr::als_solve_pair_kernel<false>,
-                         (const void*)pr::als_finish_pair_kernel<true>, (const void*)pr::als_finish_pair_kernel<false>};
-    for (const void* kf : ks) {
-      if ((e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-      if ((e = cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
+    struct { const void* f; size_t sm; } ks[4] = {{(const void*)pr::als_solve_pair_kernel<true, WARPS>, smem},
+                                                 {(const void*)pr::als_solve_pair_kernel<false, WARPS>, smem},
+                                                 {(const void*)pr::als_finish_pair_kernel<true>, fsmem},
+                                                 {(const void*)pr::als_finish_pair_kernel<false>, fsmem}};
+    for (auto& kf : ks) {
+      if ((e = cudaFuncSetAttribute(kf.f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf.sm)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(kf.f, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
     }
     attr_set[h->cfg.device] = true;
   }
-  const int max_ctas = 12 * h->sm_count;
-  auto sk = imp ? pr::als_solve_pair_kernel<true> : pr::als_solve_pair_kernel<false>;
+  const int max_ctas = (12 / WARPS) * h->sm_count;
+  auto grid_for = [&](int items) {
+    const int npairs = (items + 1) / 2;
+    const int g = (npairs + WARPS - 1) / WARPS;
+    return g < max_ctas ? g : max_ctas;
+  };
+  auto sk = imp ? pr::als_solve_pair_kernel<true, WARPS> : pr::als_solve_pair_kernel<false, WARPS>;
   if (dst.n_heavy > 0) {
     if (!dst.partial) {
       if ((e = cudaMallocAsync((void**)&dst.partial, sizeof(float) * (size_t)dst.n_parts * pr::PART_FLOATS, h->stream)) != cudaSuccess) return e;
@@ -810,16 +821,14 @@ static cudaError_t launch_pair(pio_als_handle* h, Side& dst, const SolveParams& 
     pp.n_items = dst.n_parts;
     pp.row_begin = 0;
     pp.row_end = dst.n_heavy;
-    int grid = (dst.n_parts + 1) / 2;
-    if (grid > max_ctas) grid = max_ctas;
-    sk<<<grid, 32, smem, h->stream>>>(pp, dst.n_parts);
+    sk<<<grid_for(dst.n_parts), 32 * WARPS, smem, h->stream>>>(pp, dst.n_parts);
     LAUNCHED(h);
     ++h->st.solve_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     auto fk = imp ? pr::als_finish_pair_kernel<true> : pr::als_finish_pair_kernel<false>;
     int fgrid = (dst.n_heavy + 1) / 2;
-    if (fgrid > max_ctas) fgrid = max_ctas;
-    fk<<<fgrid, 32, smem, h->stream>>>(pp, dst.row_part_ptr, dst.n_heavy);
+    if (fgrid > 12 * h->sm_count) fgrid = 12 * h->sm_count;
+    fk<<<fgrid, 32, fsmem, h->stream>>>(pp, dst.row_part_ptr, dst.n_heavy);
     LAUNCHED(h);
     ++h->st.solve_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -829,14 +838,24 @@ static cudaError_t launch_pair(pio_als_handle* h, Side& dst, const SolveParams& 
     SolveParams p = p0;
     p.row_begin = dst.n_heavy;
     p.row_end = dst.n_active;
-    int grid = (nlight + 1) / 2;
-    if (grid > max_ctas) grid = max_ctas;
-    sk<<<grid, 32, smem, h->stream>>>(p, nlight);
+    sk<<<grid_for(nlight), 32 * WARPS, smem, h->stream>>>(p, nlight);
     LAUNCHED(h);
     ++h->st.solve_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   return e;
+}
+
+// Rank 33..64, pair kernel (als_pair_kernel.cuh): persistent CTAs of pair_warps independent warps, twelve warps per
+// SM.  Long rows first (their 512-rating parts as work items, then the finish kernel), then the rows that stay whole.
+static cudaError_t launch_pair(pio_als_handle* h, Side& dst, const SolveParams& p0, bool imp) {
+  switch (h->pair_warps) {
+    case 1: return launch_pair_w<1>(h, dst, p0, imp);
+    case 2: return launch_pair_w<2>(h, dst, p0, imp);
+    case 6: return launch_pair_w<6>(h, dst, p0, imp);
+    case 12: return launch_pair_w<12>(h, dst, p0, imp);
+    default: return launch_pair_w<4>(h, dst, p0, imp);
+  }
 }
 
 template <class Cfg>
@@ -861,6 +880,49 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
   p.partial = nullptr;
   p.n_items = 0;
   if (dst.use_pair && Cfg::KP == 64) return launch_pair(h, dst, p, imp);
+  if (Cfg::LS_PARTIAL) {
+    // rank 65..128: rows in tiles; per tile one Gramian launch over the tile's parts and one lockstep finish launch
+    constexpr int TILE_ROWS = 32768;
+    const int nrows = dst.n_heavy;   // == n_active (heavy_t = 0)
+    if (nrows == 0) return cudaSuccess;
+    const std::vector<int>& rpp = dst.h_row_part_ptr;
+    if (!dst.partial) {
+      int mx = 0;
+      for (int r0 = 0; r0 < nrows; r0 += TILE_ROWS) {
+        const int r1 = r0 + TILE_ROWS < nrows ? r0 + TILE_ROWS : nrows;
+        mx = rpp[r1] - rpp[r0] > mx ? rpp[r1] - rpp[r0] : mx;
+      }
+      if ((e = cudaMallocAsync((void**)&dst.partial, sizeof(float) * (size_t)mx * Cfg::PART_FLOATS, h->stream)) != cudaSuccess) return e;
+    }
+    static bool fattr[64] = {};
+    const size_t fsmem = sizeof(float) * (size_t)(LsLayout<128>::STRIDE + 128 + 80);
+    if (h->cfg.device < 64 && !fattr[h->cfg.device]) {
+      if ((e = cudaFuncSetAttribute(als_finish_ls128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(als_finish_ls128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)) != cudaSuccess) return e;
+      fattr[h->cfg.device] = true;
+    }
+    for (int r0 = 0; r0 < nrows; r0 += TILE_ROWS) {
+      const int r1 = r0 + TILE_ROWS < nrows ? r0 + TILE_ROWS : nrows;
+      const int part0 = rpp[r0], np = rpp[r1] - rpp[r0];
+      SolveParams pp = p;
+      pp.wl_beg = dst.part_beg + part0;
+      pp.wl_end = dst.part_end + part0;
+      pp.partial = dst.partial;
+      pp.n_items = np;
+      pp.row_begin = 0;
+      pp.row_end = nrows;
+      const int grid = (np + Cfg::NG - 1) / Cfg::NG;
+      e = imp ? launch_solve_one<Cfg, true>(h, pp, grid, h->stream) : launch_solve_one<Cfg, false>(h, pp, grid, h->stream);
+      if (e != cudaSuccess) return e;
+      int fgrid = r1 - r0 < 6 * h->sm_count ? r1 - r0 : 6 * h->sm_count;
+      if (imp) als_finish_ls128_kernel<true><<<fgrid, 32, fsmem, h->stream>>>(pp, dst.row_part_ptr, r0, r1 - r0, part0);
+      else als_finish_ls128_kernel<false><<<fgrid, 32, fsmem, h->stream>>>(pp, dst.row_part_ptr, r0, r1 - r0, part0);
+      LAUNCHED(h);
+      ++h->st.solve_launches;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return e;
+  }
   // very long rows: their parts run as ordinary light batch items that emit partial normal equations
   if (dst.n_heavy > 0) {
     if (!dst.partial) {
@@ -879,8 +941,7 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
     // finish: sum the parts of every heavy row in fixed order, then Cholesky
     {
       static bool fattr[64] = {};
-      const size_t fsmem = Cfg::WARP_CHOL ? sizeof(float) * 4 * (Cfg::SLOT + 4 * Cfg::KP)
-                                          : sizeof(float) * (Cfg::SLOT + Cfg::KP + Cfg::LM);
+      const size_t fsmem = sizeof(float) * 4 * (Cfg::SLOT + 4 * Cfg::KP);
       auto fk = imp ? als_finish_kernel<Cfg, true> : als_finish_kernel<Cfg, false>;
       if (h->cfg.device < 64 && !fattr[h->cfg.device]) {
         if ((e = cudaFuncSetAttribute(als_finish_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)) != cudaSuccess) return e;
@@ -1054,6 +1115,7 @@ static int create_common(pio_als_handle* h) {
       h->use_mma = mm_[0] != '0';
       h->use_pair = mm_[0] != '1';
     }
+    if (const char* v = getenv("PIO_ALS_PAIR_WARPS")) h->pair_warps = atoi(v);
     if (const char* v = getenv("PIO_ALS_SEG_T")) h->pair_seg_t = atoi(v) > 0 ? atoi(v) : PAIR_SEG_T;
     if (const char* v = getenv("PIO_ALS_PART")) h->pair_part = atoi(v) >= 8 ? (atoi(v) + 7) / 8 * 8 : PAIR_PART;
   }
