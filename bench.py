@@ -349,7 +349,8 @@ def main():
     config = {"workload": wl_name, "lambda": LAMBDA, "alpha": ALPHA, "seed": SEED,
               "dedup": "sum" if implicit else "none",
               "l2": "inputs (1.6 GB of CSR + 282 MB of factors per iteration at c2) exceed the 126 MB L2",
-              "parallelism": f"row-sharded x{args.gpus}, factor all-gather per half-iteration" if args.gpus > 1 else "1 GPU"}
+              "parallelism": (f"rows and input events sharded x{args.gpus}, ratings routed to row owners by NCCL send/recv, "
+                              "factor all-gather per half-iteration") if args.gpus > 1 else "1 GPU"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -381,14 +382,20 @@ def main():
             torch.cuda.synchronize()
 
     # ---- inputs resident in HBM ----------------------------------------------------------
-    du = torch.empty(nnz, dtype=torch.int32, device="cuda")
-    di = torch.empty(nnz, dtype=torch.int32, device="cuda")
-    dr = torch.empty(nnz, dtype=torch.float32, device="cuda")
-    native.synth_ratings_device(dev, nu, ni, nnz, SEED, implicit, 0, du.data_ptr(), di.data_ptr(), dr.data_ptr())
+    # N > 1: every rank generates and holds only ITS slice of the events (pio_als_set_ratings_coo_sharded_device); the
+    # library routes the ratings to the owners of their rows.  No rank holds the full COO.
+    per = nnz // world
+    ev_lo = rank * per
+    ev_hi = nnz if rank == world - 1 else ev_lo + per
+    n_loc = ev_hi - ev_lo
+    du = torch.empty(n_loc, dtype=torch.int32, device="cuda")
+    di = torch.empty(n_loc, dtype=torch.int32, device="cuda")
+    dr = torch.empty(n_loc, dtype=torch.float32, device="cuda")
+    native.synth_ratings_device(dev, nu, ni, n_loc, SEED, implicit, ev_lo, du.data_ptr(), di.data_ptr(), dr.data_ptr())
     dedup = native.DEDUP_SUM if implicit else native.DEDUP_NONE
     m = native.NativeALS(k, nu, ni, lam=LAMBDA, implicit=implicit, alpha=ALPHA, seed=SEED, device=dev,
                          world_size=world, world_rank=rank, nccl_id=nccl_id, init_mode=native.INIT_HASH)
-    m.set_ratings_device(du.data_ptr(), di.data_ptr(), dr.data_ptr(), nnz, dedup=dedup)
+    m.set_ratings_device(du.data_ptr(), di.data_ptr(), dr.data_ptr(), n_loc, dedup=dedup, sharded=world > 1)
     ingest_ms = m.stats()["last_ingest_ms"]
     nnz_eff = m.stats()["nnz"]
     m.run(max(args.warmup, 0))
@@ -417,7 +424,7 @@ def main():
     value = args.steps / (dev_ms / 1e3)
 
     # factors after W + K iterations (checksum; source of the parity iteration); then one more iteration for parity
-    want_parity = not args.no_parity
+    want_parity = not args.no_parity and nnz <= 200_000_000   # the host-side CSR of a 1 B-rating workload takes minutes
     uf_T = itf_T = uf_T1 = itf_T1 = uh = ih = None
     if rank == 0:
         uf_T, itf_T, uh, ih = m.get_factors()
@@ -430,37 +437,50 @@ def main():
     # ---- end to end through the C ABI with host buffers ------------------------------------
     e2e = None
     if not args.no_e2e:
-        hu = torch.empty(nnz, dtype=torch.int32).pin_memory()
-        hi = torch.empty(nnz, dtype=torch.int32).pin_memory()
-        hr = torch.empty(nnz, dtype=torch.float32).pin_memory()
+        hu = torch.empty(n_loc, dtype=torch.int32).pin_memory()
+        hi = torch.empty(n_loc, dtype=torch.int32).pin_memory()
+        hr = torch.empty(n_loc, dtype=torch.float32).pin_memory()
         hu.copy_(du)
         hi.copy_(di)
         hr.copy_(dr)
-        out_u = torch.empty((nu, k), dtype=torch.float32).pin_memory()
-        out_i = torch.empty((ni, k), dtype=torch.float32).pin_memory()
+        out_u = torch.empty((nu, k), dtype=torch.float32).pin_memory() if rank == 0 else None
+        out_i = torch.empty((ni, k), dtype=torch.float32).pin_memory() if rank == 0 else None
         m2 = native.NativeALS(k, nu, ni, lam=LAMBDA, implicit=implicit, alpha=ALPHA, seed=SEED, device=dev,
                               world_size=world, world_rank=rank, nccl_id=None if world == 1 else nccl_id_2(native, rank, world),
                               init_mode=native.INIT_HASH)
-        m2.train(hu.numpy(), hi.numpy(), hr.numpy(), 1, dedup=dedup, out_user=out_u.numpy(), out_item=out_i.numpy())  # warm-up
+
+        def train_call(a, b, c, ou, oi, iters):
+            """What a JNI ALS.train binding does: ratings in (this rank's slice), K iterations, factors out (rank 0)."""
+            if world == 1:
+                m2.train(a, b, c, iters, dedup=dedup, out_user=ou, out_item=oi)
+            else:
+                m2.set_ratings_sharded(a, b, c, dedup=dedup)
+                m2.run(iters)
+                if rank == 0:
+                    m2.get_factors(out_user=ou, out_item=oi)
 
         def timed_train(a, b, c, ou, oi):
             barrier()
             t0 = time.perf_counter()
-            m2.train(a, b, c, args.steps, dedup=dedup, out_user=ou, out_item=oi)
+            train_call(a, b, c, ou, oi, args.steps)
             barrier()
-            s = time.perf_counter() - t0
+            s_ = time.perf_counter() - t0
             if world > 1:
                 import torch.distributed as dist
-                t = torch.tensor([s], dtype=torch.float64, device="cuda")
+                t = torch.tensor([s_], dtype=torch.float64, device="cuda")
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                s = float(t.item())
-            return s
+                s_ = float(t.item())
+            return s_
 
-        e2e_s = timed_train(hu.numpy(), hi.numpy(), hr.numpy(), out_u.numpy(), out_i.numpy())
+        ou_np = out_u.numpy() if rank == 0 else None
+        oi_np = out_i.numpy() if rank == 0 else None
+        train_call(hu.numpy(), hi.numpy(), hr.numpy(), ou_np, oi_np, 1)   # warm-up
+        e2e_s = timed_train(hu.numpy(), hi.numpy(), hr.numpy(), ou_np, oi_np)
         st2 = m2.stats()
         # the same call with ordinary pageable arrays (what a JNI caller holding GetPrimitiveArrayCritical arrays passes)
         pu, pi_, pr = (np.array(x.numpy(), copy=True) for x in (hu, hi, hr))
-        pou, poi = np.empty((nu, k), np.float32), np.empty((ni, k), np.float32)
+        pou = np.empty((nu, k), np.float32) if rank == 0 else None
+        poi = np.empty((ni, k), np.float32) if rank == 0 else None
         e2e_pageable_s = timed_train(pu, pi_, pr, pou, poi)
         del pu, pi_, pr, pou, poi
         h2d_call, d2h_call = 12 * nnz, 4 * (nu + ni) * k + (nu + ni)
@@ -470,8 +490,9 @@ def main():
                "h2d_bytes_per_call": h2d_call, "d2h_bytes_per_call": d2h_call,
                "host_memory": "pinned", "value_pageable_host_memory": args.steps / e2e_pageable_s,
                "ingest_ms": st2["last_ingest_ms"], "run_ms": st2["last_run_ms"],
-               "note": "one pio_als_train call = H2D of the COO triplets + ingest + K iterations + D2H of the factors; the "
-                       "copies happen once per call, so bytes per step = bytes per call / K"}
+               "note": "one training call = H2D of the COO triplets (N > 1: every rank copies only its 1/N slice, "
+                       "pio_als_set_ratings_coo_sharded) + ingest + K iterations + D2H of the factors (rank 0); the copies "
+                       "happen once per call, so bytes per step = bytes per call / K"}
         m2.close()
         del hu, hi, hr, out_u, out_i
 
@@ -555,8 +576,14 @@ def main():
     if need_host:
         o, cores = load_oracle()
     if want_parity or (not args.no_cpu_baseline and args.gpus == 1):
-        coo = (du.cpu().numpy(), di.cpu().numpy(), dr.cpu().numpy())
         del du, di, dr
+        torch.cuda.empty_cache()
+        fu = torch.empty(nnz, dtype=torch.int32, device="cuda")
+        fi = torch.empty(nnz, dtype=torch.int32, device="cuda")
+        fr = torch.empty(nnz, dtype=torch.float32, device="cuda")
+        native.synth_ratings_device(dev, nu, ni, nnz, SEED, implicit, 0, fu.data_ptr(), fi.data_ptr(), fr.data_ptr())
+        coo = (fu.cpu().numpy(), fi.cpu().numpy(), fr.cpu().numpy())
+        del fu, fi, fr
         prob = build_host_problem(o, nu, ni, k, implicit, coo)
         del coo
         if want_parity:

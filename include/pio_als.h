@@ -124,6 +124,19 @@ PIO_API int pio_als_set_ratings_coo(pio_als_handle* h, const int32_t* user, cons
 PIO_API int pio_als_set_ratings_coo_device(pio_als_handle* h, const int32_t* d_user,
                                            const int32_t* d_item, const float* d_rating,
                                            int64_t nnz, int dedup_mode, const int64_t* d_ts);
+/* world_size > 1, sharded input: every rank passes ITS OWN slice of the events (HOST / DEVICE variants), the slices are
+ * disjoint and rank r's slice precedes rank r + 1's in event order (what matters for PIO_ALS_DEDUP_SUM's fold order
+ * and PIO_ALS_DEDUP_KEEP_LAST's ties).  The library routes every rating to the rank that owns its user row and to the
+ * rank that owns its item row (NCCL send/recv) and sums the degrees over the ranks: no rank holds the full COO -- the
+ * way an RDD[Rating] partition per executor reaches the GPUs (the reference shuffles the ratings into ALS's in/out
+ * blocks).  A rank's slice may be empty; the union may not.  Collective: all ranks must call it.
+ * With world_size == 1 it is pio_als_set_ratings_coo[_device]. */
+PIO_API int pio_als_set_ratings_coo_sharded(pio_als_handle* h, const int32_t* user, const int32_t* item,
+                                            const float* rating, int64_t nnz_local, int dedup_mode,
+                                            const int64_t* ts);
+PIO_API int pio_als_set_ratings_coo_sharded_device(pio_als_handle* h, const int32_t* d_user, const int32_t* d_item,
+                                                   const float* d_rating, int64_t nnz_local, int dedup_mode,
+                                                   const int64_t* d_ts);
 /* Initial factors, HOST, row-major n_users x rank / n_items x rank (item_factors may be NULL:
  * MLlib overwrites item factors in the first half-step). Rows that own no rating are zeroed. */
 PIO_API int pio_als_set_init(pio_als_handle* h, const float* user_factors, const float* item_factors);

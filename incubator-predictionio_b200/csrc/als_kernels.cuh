@@ -652,7 +652,11 @@ constexpr int GRAM_ROWS = 32;
 
 template <int KP>
 __global__ void __launch_bounds__(GRAM_THREADS)
-gram_partial_kernel(const float* __restrict__ X, const int* __restrict__ p2i, int n_rows, double* __restrict__ partial) {
+gram_partial_kernel(const float* __restrict__ X, const int* __restrict__ p2i, int n_rows, double* __restrict__ partial,
+                    int block0, int n_blocks) {
+  // The rows are cut into n_blocks position ranges; this launch covers the ranges block0 .. block0 + gridDim.x - 1 (a
+  // sharded run gives every rank a contiguous share of the ranges and all-gathers the partials: the reduction below then
+  // adds the same n_blocks partials in the same order on every rank and on a single GPU).
   // rows are visited in degree-rank position order (p2i: position -> internal id), which does not depend on how the
   // rows are dealt to ranks: a sharded run sums YtY in exactly the order of the single-GPU run
   constexpr int TM = KP / 16;
@@ -663,8 +667,9 @@ gram_partial_kernel(const float* __restrict__ X, const int* __restrict__ p2i, in
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < TM; ++j) acc[i][j] = 0.0;
-  const int per = (n_rows + gridDim.x - 1) / gridDim.x;
-  const int r0 = blockIdx.x * per;
+  const int blk = block0 + blockIdx.x;
+  const int per = (n_rows + n_blocks - 1) / n_blocks;
+  const int r0 = min(n_rows, blk * per);
   const int r1 = min(n_rows, r0 + per);
   for (int base = r0; base < r1; base += GRAM_ROWS) {
     const int nr = min(GRAM_ROWS, r1 - base);
@@ -690,7 +695,7 @@ gram_partial_kernel(const float* __restrict__ X, const int* __restrict__ p2i, in
     }
     __syncthreads();
   }
-  double* out = partial + (size_t)blockIdx.x * KP * KP;
+  double* out = partial + (size_t)blk * KP * KP;
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll

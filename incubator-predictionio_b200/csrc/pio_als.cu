@@ -68,6 +68,11 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
@@ -84,9 +89,15 @@ static NcclApi& nccl_api() {
     api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
     api.CommInitRank = (decltype(api.CommInitRank))dlsym(lib, "ncclCommInitRank");
     api.AllGather = (decltype(api.AllGather))dlsym(lib, "ncclAllGather");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(lib, "ncclAllReduce");
+    api.Send = (decltype(api.Send))dlsym(lib, "ncclSend");
+    api.Recv = (decltype(api.Recv))dlsym(lib, "ncclRecv");
+    api.GroupStart = (decltype(api.GroupStart))dlsym(lib, "ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))dlsym(lib, "ncclGroupEnd");
     api.CommDestroy = (decltype(api.CommDestroy))dlsym(lib, "ncclCommDestroy");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(lib, "ncclGetErrorString");
-    api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy;
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.AllReduce && api.Send &&
+             api.Recv && api.GroupStart && api.GroupEnd;
   });
   return api;
 }
@@ -170,6 +181,26 @@ __global__ void assign_internal_kernel(const uint32_t* order, int n, int W, int 
   inv[internal] = row;
   rpos[row] = p;       // degree-rank position: independent of the number of GPUs
   p2i[p] = internal;
+}
+// sharded ingest: destination rank of every event (by user residue for the dedup pass, by row owner for the CSR passes)
+__global__ void dest_mod_kernel(const int* u, long long n, int W, uint64_t* keys, uint32_t* pay) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) {
+    keys[e] = (uint64_t)((uint32_t)u[e] % (uint32_t)W);
+    pay[e] = (uint32_t)e;
+  }
+}
+__global__ void dest_owner_kernel(const int* rowext, long long n, const int* perm, int R, uint64_t* keys, uint32_t* pay) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) {
+    keys[e] = (uint64_t)(perm[rowext[e]] / R);
+    pay[e] = (uint32_t)e;
+  }
+}
+template <class T>
+__global__ void gather_by_index_kernel(const T* in, const uint32_t* idx, long long n, T* out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) out[e] = in[idx[e]];
 }
 __global__ void fill_int_kernel(int* a, long long n, int v) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,6 +403,13 @@ struct pio_als_handle {
   bool use_pair = true;       // PIO_ALS_MMA=1: round-1 one-warp-per-row mma.sync kernel instead of the pair kernel
   int pair_seg_t = PAIR_SEG_T, pair_part = PAIR_PART;   // PIO_ALS_SEG_T / PIO_ALS_PART
   int pair_warps = 4;         // PIO_ALS_PAIR_WARPS: warps per CTA of the pair kernel (1, 2, 4, 6 or 12)
+  // half-step pipeline (pair-kernel sides): long rows (parts + finish) run on `aux` next to the whole rows on `stream`;
+  // the destination rows are cut into n_pieces local ranges and the all-gather of a finished range runs on `comm_st`
+  // while the next range is solved (world_size > 1)
+  cudaStream_t aux = nullptr, comm_st = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_heavy = nullptr, ev_piece[8] = {}, ev_comm = nullptr;
+  int n_pieces = 1;           // PIO_ALS_PIECES (1..8); default 4 when world_size > 1
+  bool pieces_done = false;   // the last launch_solve recorded ev_piece[] / ev_heavy (pair path)
   bool tc_split = false;      // PIO_ALS_TC_SPLIT=1: the tensor-core kernel only accumulates, a second kernel solves (measured: no gain)
   float* tc_out = nullptr;    // split mode: normal equations of one tile of rows ([rows][ASLOT + KP])
   size_t tc_out_rows = 0;
@@ -463,20 +501,33 @@ static EvPair& next_ev(pio_als_handle* h, int kind) {
 
 // ---- ingest ---------------------------------------------------------------------------------
 static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* rowext, const int* colext,
-                      const float* rating, long long nnz, uint64_t* ka, uint32_t* va, uint64_t* kb, uint32_t* vb) {
+                      const float* rating, long long nnz, long long nnz_global) {
+  // nnz ratings are present on this rank (all of them in replicated mode, those of the rows it owns in sharded mode);
+  // nnz_global = ratings after dedup over all ranks (kernel choice must agree on every rank)
   cudaStream_t st = h->stream;
   const int W = h->cfg.world_size, rk = h->cfg.world_rank;
-  make_keys_int_kernel<<<nblk(nnz, 256), 256, 0, st>>>(rowext, colext, nnz, row.perm, col.rpos, col.bits, ka, va);
-  LAUNCHED(h);
+  Scratch tmp(h);
+  uint64_t *ka = nullptr, *kb = nullptr;
+  uint32_t *va = nullptr, *vb = nullptr;
+  CK(h, tmp.alloc(&ka, (size_t)nnz));
+  CK(h, tmp.alloc(&kb, (size_t)nnz));
+  CK(h, tmp.alloc(&va, (size_t)nnz));
+  CK(h, tmp.alloc(&vb, (size_t)nnz));
   bool in_b = false;
-  CK(h, radix_sort_pairs(ka, va, kb, vb, (size_t)nnz, row.bits + col.bits, st, &in_b, &h->st.kernel_launches));
+  if (nnz > 0) {
+    make_keys_int_kernel<<<nblk(nnz, 256), 256, 0, st>>>(rowext, colext, nnz, row.perm, col.rpos, col.bits, ka, va);
+    LAUNCHED(h);
+    CK(h, radix_sort_pairs(ka, va, kb, vb, (size_t)nnz, row.bits + col.bits, st, &in_b, &h->st.kernel_launches));
+  }
   const uint64_t* ks = in_b ? kb : ka;
   const uint32_t* vs = in_b ? vb : va;
-  Scratch tmp(h);
   long long* ptr_full = nullptr;
   CK(h, tmp.alloc(&ptr_full, (size_t)row.n_internal + 1));
-  build_ptr_kernel<<<nblk(nnz, 256), 256, 0, st>>>(ks, nnz, col.bits, row.n_internal, ptr_full);
-  LAUNCHED(h);
+  CK(h, cudaMemsetAsync(ptr_full, 0, sizeof(long long) * ((size_t)row.n_internal + 1), st));
+  if (nnz > 0) {
+    build_ptr_kernel<<<nblk(nnz, 256), 256, 0, st>>>(ks, nnz, col.bits, row.n_internal, ptr_full);
+    LAUNCHED(h);
+  }
   long long be[2];
   CK(h, cudaMemcpyAsync(&be[0], ptr_full + (size_t)rk * row.R, sizeof(long long), cudaMemcpyDeviceToHost, st));
   CK(h, cudaMemcpyAsync(&be[1], ptr_full + (size_t)(rk + 1) * row.R, sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -496,7 +547,7 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
   CK(h, cudaMemsetAsync(h->d_counts, 0, 2 * sizeof(int), st));
   // kernel choice from global numbers only (ratings after dedup / rows of this side), so that every rank of a sharded
   // run and the single-GPU run take the same path for the same row
-  row.use_tc = h->use_tc && h->KP == 64 && row.n > 0 && (double)nnz / (double)row.n >= h->tc_min_deg;
+  row.use_tc = h->use_tc && h->KP == 64 && row.n > 0 && (double)nnz_global / (double)row.n >= h->tc_min_deg;
   row.use_pair = !row.use_tc && h->KP == 64 && h->use_mma && h->use_pair;
   // one warp (mma kernels) or one accumulator slot (tcgen05 kernel) carries a whole row.  Pair kernel: rows up to 1024
   // ratings stay whole, longer rows become 512-rating parts of the same kernel (two-level summation); round-1 mma /
@@ -543,8 +594,15 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
   return PIO_ALS_OK;
 }
 
-static int rank_rows(pio_als_handle* h, Side& s, uint64_t* ka, uint32_t* va, uint64_t* kb, uint32_t* vb) {
+static int rank_rows(pio_als_handle* h, Side& s) {
   cudaStream_t st = h->stream;
+  Scratch tmp(h);
+  uint64_t *ka = nullptr, *kb = nullptr;
+  uint32_t *va = nullptr, *vb = nullptr;
+  CK(h, tmp.alloc(&ka, (size_t)s.n));
+  CK(h, tmp.alloc(&kb, (size_t)s.n));
+  CK(h, tmp.alloc(&va, (size_t)s.n));
+  CK(h, tmp.alloc(&vb, (size_t)s.n));
   degree_keys_kernel<<<nblk(s.n, 256), 256, 0, st>>>(s.deg, s.n, ka, va);
   LAUNCHED(h);
   bool in_b = false;
@@ -557,17 +615,93 @@ static int rank_rows(pio_als_handle* h, Side& s, uint64_t* ka, uint32_t* va, uin
   return PIO_ALS_OK;
 }
 
-static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item, const float* d_rating,
-                         long long nnz, int dedup, const long long* d_ts) {
+// ---- sharded ingest: all-to-all exchange of event arrays ------------------------------------------------------------
+// The n events on this rank go to the ranks named by the sort keys (destination rank, payload = event index; built by the
+// caller in ka/va).  Events keep their order per destination and arrive concatenated in source-rank order, so a global
+// event order (rank r's slice precedes rank r + 1's) survives.  The received arrays are allocated in `keep`.
+struct XArr {
+  const void* in;
+  void** out;
+  size_t elem;
+};
+static int exchange_events(pio_als_handle* h, Scratch& keep, uint64_t* ka, uint32_t* va, uint64_t* kb, uint32_t* vb,
+                           long long n, XArr* arrs, int na, long long* n_out) {
   cudaStream_t st = h->stream;
-  if (nnz <= 0)
+  NcclApi& nc = nccl_api();
+  const int W = h->cfg.world_size, me = h->cfg.world_rank;
+  Scratch tmp(h);
+  bool in_b = false;
+  if (n > 0) CK(h, radix_sort_pairs(ka, va, kb, vb, (size_t)n, ceil_log2((uint64_t)W), st, &in_b, &h->st.kernel_launches));
+  const uint64_t* ks = in_b ? kb : ka;
+  const uint32_t* vs = in_b ? vb : va;
+  long long *d_off = nullptr, *d_cnt = nullptr, *d_all = nullptr;
+  CK(h, tmp.alloc(&d_off, (size_t)W + 1));
+  CK(h, tmp.alloc(&d_cnt, (size_t)W));
+  CK(h, tmp.alloc(&d_all, (size_t)W * W));
+  CK(h, cudaMemsetAsync(d_off, 0, sizeof(long long) * (W + 1), st));
+  if (n > 0) {
+    build_ptr_kernel<<<nblk(n, 256), 256, 0, st>>>(ks, n, 0, W, d_off);
+    LAUNCHED(h);
+  }
+  std::vector<long long> off(W + 1), all((size_t)W * W);
+  CK(h, cudaMemcpyAsync(off.data(), d_off, sizeof(long long) * (W + 1), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  std::vector<long long> cnt(W);
+  for (int p = 0; p < W; ++p) cnt[p] = off[p + 1] - off[p];
+  CK(h, cudaMemcpyAsync(d_cnt, cnt.data(), sizeof(long long) * W, cudaMemcpyHostToDevice, st));
+  if (nc.AllGather(d_cnt, d_all, (size_t)W, ncclInt64, h->comm, st) != ncclSuccess)
+    return fail(h, PIO_ALS_ERR_COMM, "ncclAllGather (exchange counts) failed");
+  CK(h, cudaMemcpyAsync(all.data(), d_all, sizeof(long long) * W * W, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  std::vector<long long> roff(W + 1, 0);
+  for (int src = 0; src < W; ++src) roff[src + 1] = roff[src] + all[(size_t)src * W + me];
+  const long long nrecv = roff[W];
+  if (nrecv >= (1ll << 32)) return fail(h, PIO_ALS_ERR_ARG, "more than 2^32-1 events on one rank after the exchange");
+  for (int a = 0; a < na; ++a) {
+    if (!arrs[a].in) { *arrs[a].out = nullptr; continue; }
+    unsigned char* sendbuf = nullptr;
+    unsigned char* recvbuf = nullptr;
+    CK(h, tmp.alloc(&sendbuf, (size_t)(n > 0 ? n : 1) * arrs[a].elem));
+    CK(h, keep.alloc(&recvbuf, (size_t)(nrecv > 0 ? nrecv : 1) * arrs[a].elem));
+    if (n > 0) {
+      if (arrs[a].elem == 4)
+        gather_by_index_kernel<uint32_t><<<nblk(n, 256), 256, 0, st>>>((const uint32_t*)arrs[a].in, vs, n, (uint32_t*)sendbuf);
+      else
+        gather_by_index_kernel<uint64_t><<<nblk(n, 256), 256, 0, st>>>((const uint64_t*)arrs[a].in, vs, n, (uint64_t*)sendbuf);
+      LAUNCHED(h);
+    }
+    if (nc.GroupStart() != ncclSuccess) return fail(h, PIO_ALS_ERR_COMM, "ncclGroupStart failed");
+    for (int p = 0; p < W; ++p) {
+      const long long sc = cnt[p], rc_ = all[(size_t)p * W + me];
+      if (sc > 0 && nc.Send(sendbuf + (size_t)off[p] * arrs[a].elem, (size_t)sc * arrs[a].elem, ncclInt8, p, h->comm, st) != ncclSuccess)
+        return fail(h, PIO_ALS_ERR_COMM, "ncclSend failed");
+      if (rc_ > 0 && nc.Recv(recvbuf + (size_t)roff[p] * arrs[a].elem, (size_t)rc_ * arrs[a].elem, ncclInt8, p, h->comm, st) != ncclSuccess)
+        return fail(h, PIO_ALS_ERR_COMM, "ncclRecv failed");
+    }
+    if (nc.GroupEnd() != ncclSuccess) return fail(h, PIO_ALS_ERR_COMM, "ncclGroupEnd failed");
+    *arrs[a].out = recvbuf;
+  }
+  CK(h, cudaStreamSynchronize(st));
+  *n_out = nrecv;
+  return PIO_ALS_OK;
+}
+
+// sharded == false: the arrays hold ALL events (every rank passes the same COO and keeps the rows it owns).
+// sharded == true (world_size > 1): the arrays hold this rank's slice of the events; ratings are routed to the owners of
+// their user row and of their item row by NCCL send/recv, degrees are all-reduced; no rank ever holds the full COO.
+static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item, const float* d_rating,
+                         long long nnz, int dedup, const long long* d_ts, bool sharded) {
+  cudaStream_t st = h->stream;
+  const int W = h->cfg.world_size;
+  sharded = sharded && W > 1;
+  if (nnz <= 0 && !sharded)
     return fail(h, PIO_ALS_ERR_ARG, "ratings cannot be empty (the templates require(!ratings.take(1).isEmpty))");
+  if (nnz < 0) return fail(h, PIO_ALS_ERR_ARG, "nnz < 0");
   if (nnz >= (1ll << 32)) return fail(h, PIO_ALS_ERR_ARG, "nnz must be < 2^32 per call");
   if (dedup < 0 || dedup > 2) return fail(h, PIO_ALS_ERR_ARG, "bad dedup_mode %d", dedup);
   free_side(h, h->U, true);
   free_side(h, h->I, true);
   h->have_ratings = false;
-  const int W = h->cfg.world_size;
   Side& U = h->U;
   Side& I = h->I;
   U.n = h->cfg.n_users;
@@ -578,61 +712,84 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
   I.n_internal = I.R * W;
   U.bits = ceil_log2((uint64_t)U.n_internal);
   I.bits = ceil_log2((uint64_t)I.n_internal);
+  NcclApi& nc = nccl_api();
 
   CK(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
-  validate_coo_kernel<<<nblk(nnz, 256), 256, 0, st>>>(d_user, d_item, nnz, U.n, I.n, h->d_fail);
-  LAUNCHED(h);
+  if (nnz > 0) {
+    validate_coo_kernel<<<nblk(nnz, 256), 256, 0, st>>>(d_user, d_item, nnz, U.n, I.n, h->d_fail);
+    LAUNCHED(h);
+  }
   int bad = 0;
   CK(h, cudaMemcpyAsync(&bad, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(h, cudaStreamSynchronize(st));
   if (bad) return fail(h, PIO_ALS_ERR_ARG, "%d ratings have a user/item index out of range", bad);
 
-  const size_t nmax = (size_t)(nnz > U.n ? nnz : U.n) > (size_t)I.n ? (size_t)(nnz > U.n ? nnz : U.n) : (size_t)I.n;
-  Scratch tmp(h);   // sort buffers and dedup output: released on every exit path, including the CK() early returns
-  uint64_t *ka = nullptr, *kb = nullptr;
-  uint32_t *va = nullptr, *vb = nullptr;
-  CK(h, tmp.alloc(&ka, nmax));
-  CK(h, tmp.alloc(&kb, nmax));
-  CK(h, tmp.alloc(&va, nmax));
-  CK(h, tmp.alloc(&vb, nmax));
+  Scratch tmp(h);   // everything temporary: released on every exit path, including the CK() early returns
+  // 0. sharded + dedup: first bring all events of a user to one rank (user mod W), keeping the event order
+  const int* su = d_user;
+  const int* si = d_item;
+  const float* sr = d_rating;
+  const long long* sts = d_ts;
+  long long ns = nnz;
+  if (sharded && dedup != PIO_ALS_DEDUP_NONE) {
+    Scratch xs(h);
+    uint64_t *ka = nullptr, *kb = nullptr;
+    uint32_t *va = nullptr, *vb = nullptr;
+    CK(h, xs.alloc(&ka, (size_t)nnz)); CK(h, xs.alloc(&kb, (size_t)nnz));
+    CK(h, xs.alloc(&va, (size_t)nnz)); CK(h, xs.alloc(&vb, (size_t)nnz));
+    if (nnz > 0) {
+      dest_mod_kernel<<<nblk(nnz, 256), 256, 0, st>>>(d_user, nnz, W, ka, va);
+      LAUNCHED(h);
+    }
+    void *xu = nullptr, *xi = nullptr, *xr = nullptr, *xt = nullptr;
+    XArr arrs[4] = {{d_user, &xu, 4}, {d_item, &xi, 4}, {d_rating, &xr, 4},
+                    {dedup == PIO_ALS_DEDUP_KEEP_LAST ? (const void*)d_ts : nullptr, &xt, 8}};
+    int rc = exchange_events(h, tmp, ka, va, kb, vb, nnz, arrs, 4, &ns);
+    if (rc) return rc;
+    su = (const int*)xu; si = (const int*)xi; sr = (const float*)xr; sts = (const long long*)xt;
+  }
 
-  // 1. optional dedup of repeated (user,item) pairs
-  const int* cu = d_user;
-  const int* ci = d_item;
-  const float* cr = d_rating;
-  int *du_ = nullptr, *di_ = nullptr;
-  float* dr_ = nullptr;
-  long long n2 = nnz;
-  if (dedup != PIO_ALS_DEDUP_NONE) {
+  // 1. optional dedup of repeated (user,item) pairs (all copies of a pair are on this rank)
+  const int* cu = su;
+  const int* ci = si;
+  const float* cr = sr;
+  long long n2 = ns;
+  if (dedup != PIO_ALS_DEDUP_NONE && ns > 0) {
+    Scratch ds(h);
+    uint64_t *ka = nullptr, *kb = nullptr;
+    uint32_t *va = nullptr, *vb = nullptr;
+    CK(h, ds.alloc(&ka, (size_t)ns)); CK(h, ds.alloc(&kb, (size_t)ns));
+    CK(h, ds.alloc(&va, (size_t)ns)); CK(h, ds.alloc(&vb, (size_t)ns));
     const int bu = ceil_log2((uint64_t)U.n), bi = ceil_log2((uint64_t)I.n);
-    make_keys_ext_kernel<<<nblk(nnz, 256), 256, 0, st>>>(d_user, d_item, nnz, bi, ka, va);
+    make_keys_ext_kernel<<<nblk(ns, 256), 256, 0, st>>>(su, si, ns, bi, ka, va);
     LAUNCHED(h);
     bool in_b = false;
-    CK(h, radix_sort_pairs(ka, va, kb, vb, (size_t)nnz, bu + bi, st, &in_b, &h->st.kernel_launches));
+    CK(h, radix_sort_pairs(ka, va, kb, vb, (size_t)ns, bu + bi, st, &in_b, &h->st.kernel_launches));
     const uint64_t* ks = in_b ? kb : ka;
     const uint32_t* vs = in_b ? vb : va;
     uint32_t* flag = nullptr;
-    CK(h, tmp.alloc(&flag, (size_t)nnz));
-    head_flags_kernel<<<nblk(nnz, 256), 256, 0, st>>>(ks, nnz, flag);
+    CK(h, ds.alloc(&flag, (size_t)ns));
+    head_flags_kernel<<<nblk(ns, 256), 256, 0, st>>>(ks, ns, flag);
     LAUNCHED(h);
     uint32_t last_flag = 0, last_pos = 0;
-    CK(h, cudaMemcpyAsync(&last_flag, flag + nnz - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(h, scan_exclusive_u32(flag, flag, (size_t)nnz, st, &h->st.kernel_launches));
-    CK(h, cudaMemcpyAsync(&last_pos, flag + nnz - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(&last_flag, flag + ns - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(h, scan_exclusive_u32(flag, flag, (size_t)ns, st, &h->st.kernel_launches));
+    CK(h, cudaMemcpyAsync(&last_pos, flag + ns - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
     n2 = (long long)last_pos + last_flag;
+    int *du_ = nullptr, *di_ = nullptr;
+    float* dr_ = nullptr;
     CK(h, tmp.alloc(&du_, (size_t)n2));
     CK(h, tmp.alloc(&di_, (size_t)n2));
     CK(h, tmp.alloc(&dr_, (size_t)n2));
-    dedup_compact_kernel<<<nblk(nnz, 256), 256, 0, st>>>(ks, vs, flag, nnz, bi, d_rating, d_ts, dedup, du_, di_, dr_);
+    dedup_compact_kernel<<<nblk(ns, 256), 256, 0, st>>>(ks, vs, flag, ns, bi, sr, sts, dedup, du_, di_, dr_);
     LAUNCHED(h);
     cu = du_;
     ci = di_;
     cr = dr_;
   }
-  h->st.nnz = n2;
 
-  // 2. degrees, positive-rating counts
+  // 2. degrees, positive-rating counts (sharded: summed over the ranks)
   for (Side* s : {&U, &I}) {
     CK(h, dalloc(h, &s->deg, (size_t)s->n));
     CK(h, dalloc(h, &s->npos, (size_t)s->n));
@@ -643,20 +800,62 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
     CK(h, cudaMemsetAsync(s->deg, 0, sizeof(uint32_t) * s->n, st));
     CK(h, cudaMemsetAsync(s->npos, 0, sizeof(uint32_t) * s->n, st));
   }
-  degree_kernel<<<nblk(n2, 256), 256, 0, st>>>(cu, ci, cr, n2, U.deg, I.deg, U.npos, I.npos);
-  LAUNCHED(h);
+  if (n2 > 0) {
+    degree_kernel<<<nblk(n2, 256), 256, 0, st>>>(cu, ci, cr, n2, U.deg, I.deg, U.npos, I.npos);
+    LAUNCHED(h);
+  }
+  long long n2_global = n2;
+  if (sharded) {
+    for (Side* s : {&U, &I}) {
+      if (nc.AllReduce(s->deg, s->deg, (size_t)s->n, ncclUint32, ncclSum, h->comm, st) != ncclSuccess ||
+          nc.AllReduce(s->npos, s->npos, (size_t)s->n, ncclUint32, ncclSum, h->comm, st) != ncclSuccess)
+        return fail(h, PIO_ALS_ERR_COMM, "ncclAllReduce (degrees) failed");
+    }
+    long long* d_n = nullptr;
+    CK(h, tmp.alloc(&d_n, 1));
+    CK(h, cudaMemcpyAsync(d_n, &n2, sizeof(long long), cudaMemcpyHostToDevice, st));
+    if (nc.AllReduce(d_n, d_n, 1, ncclInt64, ncclSum, h->comm, st) != ncclSuccess)
+      return fail(h, PIO_ALS_ERR_COMM, "ncclAllReduce (nnz) failed");
+    CK(h, cudaMemcpyAsync(&n2_global, d_n, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    if (n2_global <= 0)
+      return fail(h, PIO_ALS_ERR_ARG, "ratings cannot be empty (the templates require(!ratings.take(1).isEmpty))");
+  }
+  h->st.nnz = n2_global;
 
-  // 3. renumber rows: degree-descending, dealt to ranks
-  int rc = rank_rows(h, U, ka, va, kb, vb);
+  // 3. renumber rows: degree-descending, dealt to ranks (the same on every rank)
+  int rc = rank_rows(h, U);
   if (rc) return rc;
-  rc = rank_rows(h, I, ka, va, kb, vb);
+  rc = rank_rows(h, I);
   if (rc) return rc;
 
   // 4. the two CSR orientations in internal numbering (only this rank's rows are kept)
-  rc = build_side(h, U, I, cu, ci, cr, n2, ka, va, kb, vb);
-  if (rc) return rc;
-  rc = build_side(h, I, U, ci, cu, cr, n2, ka, va, kb, vb);
-  if (rc) return rc;
+  if (!sharded) {
+    rc = build_side(h, U, I, cu, ci, cr, n2, n2_global);
+    if (rc) return rc;
+    rc = build_side(h, I, U, ci, cu, cr, n2, n2_global);
+    if (rc) return rc;
+  } else {
+    struct { Side* row; Side* col; const int* rowext; const int* colext; } jobs[2] = {{&U, &I, cu, ci}, {&I, &U, ci, cu}};
+    for (auto& j : jobs) {
+      Scratch xs(h), recv(h);
+      uint64_t *ka = nullptr, *kb = nullptr;
+      uint32_t *va = nullptr, *vb = nullptr;
+      CK(h, xs.alloc(&ka, (size_t)n2)); CK(h, xs.alloc(&kb, (size_t)n2));
+      CK(h, xs.alloc(&va, (size_t)n2)); CK(h, xs.alloc(&vb, (size_t)n2));
+      if (n2 > 0) {
+        dest_owner_kernel<<<nblk(n2, 256), 256, 0, st>>>(j.rowext, n2, j.row->perm, j.row->R, ka, va);
+        LAUNCHED(h);
+      }
+      void *xrow = nullptr, *xcol = nullptr, *xr = nullptr;
+      XArr arrs[3] = {{j.rowext, &xrow, 4}, {j.colext, &xcol, 4}, {cr, &xr, 4}};
+      long long ne = 0;
+      rc = exchange_events(h, recv, ka, va, kb, vb, n2, arrs, 3, &ne);
+      if (rc) return rc;
+      rc = build_side(h, *j.row, *j.col, (const int*)xrow, (const int*)xcol, (const float*)xr, ne, n2_global);
+      if (rc) return rc;
+    }
+  }
 
   // 5. factor matrices (zero: rows without ratings must stay zero) and candidate tables
   for (Side* s : {&U, &I}) {
@@ -670,11 +869,10 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
   }
   h->have_init = false;
   CK(h, cudaStreamSynchronize(st));
-  int au[2] = {U.n_active, I.n_active};
-  h->st.n_users_active = au[0];
-  h->st.n_items_active = au[1];
+  h->st.n_users_active = U.n_active;
+  h->st.n_items_active = I.n_active;
   if (W > 1) {
-    // n_active per rank is local; report global actives via degrees instead (cheap host-side sum avoided):
+    // n_active per rank is local; the global counts are not needed by the library
     h->st.n_users_active = -1;
     h->st.n_items_active = -1;
   }
@@ -810,10 +1008,16 @@ static cudaError_t launch_pair_w(pio_als_handle* h, Side& dst, const SolveParams
     return g < max_ctas ? g : max_ctas;
   };
   auto sk = imp ? pr::als_solve_pair_kernel<true, WARPS> : pr::als_solve_pair_kernel<false, WARPS>;
+  cudaEventRecord(h->ev_start, h->stream);
   if (dst.n_heavy > 0) {
+    // long rows on the auxiliary stream: parts, then the finish kernel.  Launched first: the kernels are persistent
+    // (one full wave), so the CTAs of the whole-row launch below move in as the part CTAs retire and the finish
+    // kernel overlaps the whole-row kernel instead of waiting behind it.
     if (!dst.partial) {
       if ((e = cudaMallocAsync((void**)&dst.partial, sizeof(float) * (size_t)dst.n_parts * pr::PART_FLOATS, h->stream)) != cudaSuccess) return e;
+      cudaEventRecord(h->ev_start, h->stream);
     }
+    cudaStreamWaitEvent(h->aux, h->ev_start, 0);
     SolveParams pp = p0;
     pp.wl_beg = dst.part_beg;
     pp.wl_end = dst.part_end;
@@ -821,28 +1025,38 @@ static cudaError_t launch_pair_w(pio_als_handle* h, Side& dst, const SolveParams
     pp.n_items = dst.n_parts;
     pp.row_begin = 0;
     pp.row_end = dst.n_heavy;
-    sk<<<grid_for(dst.n_parts), 32 * WARPS, smem, h->stream>>>(pp, dst.n_parts);
+    sk<<<grid_for(dst.n_parts), 32 * WARPS, smem, h->aux>>>(pp, dst.n_parts);
     LAUNCHED(h);
     ++h->st.solve_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     auto fk = imp ? pr::als_finish_pair_kernel<true> : pr::als_finish_pair_kernel<false>;
     int fgrid = (dst.n_heavy + 1) / 2;
     if (fgrid > 12 * h->sm_count) fgrid = 12 * h->sm_count;
-    fk<<<fgrid, 32, fsmem, h->stream>>>(pp, dst.row_part_ptr, dst.n_heavy);
+    fk<<<fgrid, 32, fsmem, h->aux>>>(pp, dst.row_part_ptr, dst.n_heavy);
     LAUNCHED(h);
     ++h->st.solve_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
-  const int nlight = dst.n_active - dst.n_heavy;
-  if (nlight > 0) {
-    SolveParams p = p0;
-    p.row_begin = dst.n_heavy;
-    p.row_end = dst.n_active;
-    sk<<<grid_for(nlight), 32 * WARPS, smem, h->stream>>>(p, nlight);
-    LAUNCHED(h);
-    ++h->st.solve_launches;
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  cudaEventRecord(h->ev_heavy, h->aux);
+  // whole rows, one launch per piece of the local row range (the all-gather of a piece starts when its rows are done)
+  const int C = h->n_pieces;
+  for (int c = 0; c < C; ++c) {
+    const long long plo = (long long)dst.R * c / C, phi = (long long)dst.R * (c + 1) / C;
+    const int lo = plo > dst.n_heavy ? (int)plo : dst.n_heavy;
+    const int hi = phi < dst.n_active ? (int)phi : dst.n_active;
+    if (hi > lo) {
+      SolveParams p = p0;
+      p.row_begin = lo;
+      p.row_end = hi;
+      sk<<<grid_for(hi - lo), 32 * WARPS, smem, h->stream>>>(p, hi - lo);
+      LAUNCHED(h);
+      ++h->st.solve_launches;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    cudaEventRecord(h->ev_piece[c], h->stream);
   }
+  cudaStreamWaitEvent(h->stream, h->ev_heavy, 0);   // the half-step ends when both streams are done
+  h->pieces_done = true;
   return e;
 }
 
@@ -999,19 +1213,31 @@ static cudaError_t launch_solve(pio_als_handle* h, Side& dst, const Side& src) {
   }
 }
 
-static cudaError_t launch_gram(pio_als_handle* h, const Side& src) {
-  const int nb = h->gram_blocks;
+// YtY of the (replicated) source factors.  world_size > 1: every rank sums a contiguous share of the gram_blocks position
+// ranges from its replica and the fp64 partials are all-gathered in place; the final reduction adds the same partials in
+// the same order everywhere, so the result is bit-identical to the single-GPU one (and the 0.77 ms this cost on every
+// rank at C2 shrinks with the number of GPUs).
+static int launch_gram(pio_als_handle* h, const Side& src) {
+  const int nb = h->gram_blocks, W = h->cfg.world_size;
+  const bool shard = W > 1 && nb % W == 0;
+  const int mine = shard ? nb / W : nb, b0 = shard ? h->cfg.world_rank * mine : 0;
   switch (h->KP) {
-    case 16: gram_partial_kernel<16><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial); break;
-    case 32: gram_partial_kernel<32><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial); break;
-    case 64: gram_partial_kernel<64><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial); break;
-    default: gram_partial_kernel<128><<<nb, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial); break;
+    case 16: gram_partial_kernel<16><<<mine, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial, b0, nb); break;
+    case 32: gram_partial_kernel<32><<<mine, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial, b0, nb); break;
+    case 64: gram_partial_kernel<64><<<mine, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial, b0, nb); break;
+    default: gram_partial_kernel<128><<<mine, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial, b0, nb); break;
   }
   LAUNCHED(h);
   const int n = h->KP * h->KP;
+  if (shard) {
+    const size_t cnt = (size_t)mine * n;
+    if (nccl_api().AllGather(h->gram_partial + (size_t)b0 * n, h->gram_partial, cnt, ncclDouble, h->comm, h->stream) != ncclSuccess)
+      return fail(h, PIO_ALS_ERR_COMM, "ncclAllGather (YtY partials) failed");
+  }
   gram_reduce_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(h->gram_partial, nb, n, h->yty);
   LAUNCHED(h);
-  return cudaGetLastError();
+  CK(h, cudaGetLastError());
+  return PIO_ALS_OK;
 }
 
 static int half_step(pio_als_handle* h, Side& dst, const Side& src) {
@@ -1019,24 +1245,54 @@ static int half_step(pio_als_handle* h, Side& dst, const Side& src) {
   if (h->cfg.implicit_prefs) {
     EvPair& e = next_ev(h, EV_GRAM);
     cudaEventRecord(e.a, st);
-    CK(h, launch_gram(h, src));
+    const int grc = launch_gram(h, src);
+    if (grc) return grc;
     cudaEventRecord(e.b, st);
   }
   {
     EvPair& e = next_ev(h, &dst == &h->U ? EV_SOLVE_USER : EV_SOLVE);
     cudaEventRecord(e.a, st);
+    h->pieces_done = false;
     CK(h, launch_solve(h, dst, src));
     cudaEventRecord(e.b, st);
   }
   if (h->cfg.world_size > 1) {
+    NcclApi& nc = nccl_api();
+    const int W = h->cfg.world_size, me = h->cfg.world_rank;
     EvPair& e = next_ev(h, EV_COMM);
-    cudaEventRecord(e.a, st);
-    const size_t cnt = (size_t)dst.R * h->KP;
-    ncclResult_t r = nccl_api().AllGather(dst.F + (size_t)h->cfg.world_rank * cnt, dst.F, cnt, ncclFloat, h->comm, st);
-    if (r != ncclSuccess)
-      return fail(h, PIO_ALS_ERR_COMM, "ncclAllGather failed: %s",
-                  nccl_api().GetErrorString ? nccl_api().GetErrorString(r) : "?");
-    cudaEventRecord(e.b, st);
+    if (h->pieces_done && h->n_pieces > 1) {
+      // all-gather piece by piece on the communication stream: piece c = local rows [R c / C, R (c + 1) / C) of every
+      // rank, exchanged as soon as its rows are solved (grouped send/recv: NVSwitch gives every pair full bandwidth)
+      cudaStream_t sc = h->comm_st;
+      const int C = h->n_pieces;
+      bool first = true;
+      for (int c = 0; c < C; ++c) {
+        const long long lo = (long long)dst.R * c / C, hi = (long long)dst.R * (c + 1) / C;
+        if (hi <= lo) continue;
+        cudaStreamWaitEvent(sc, h->ev_piece[c], 0);
+        if (lo < dst.n_heavy) cudaStreamWaitEvent(sc, h->ev_heavy, 0);
+        if (first) { cudaEventRecord(e.a, st); first = false; }   // comm time reported = what is NOT hidden behind the solve
+        const size_t cnt = (size_t)(hi - lo) * h->KP;
+        if (nc.GroupStart() != ncclSuccess) return fail(h, PIO_ALS_ERR_COMM, "ncclGroupStart failed");
+        for (int p = 0; p < W; ++p) {
+          if (p == me) continue;
+          if (nc.Send(dst.F + ((size_t)me * dst.R + lo) * h->KP, cnt, ncclFloat, p, h->comm, sc) != ncclSuccess ||
+              nc.Recv(dst.F + ((size_t)p * dst.R + lo) * h->KP, cnt, ncclFloat, p, h->comm, sc) != ncclSuccess)
+            return fail(h, PIO_ALS_ERR_COMM, "ncclSend/ncclRecv (factor pieces) failed");
+        }
+        if (nc.GroupEnd() != ncclSuccess) return fail(h, PIO_ALS_ERR_COMM, "ncclGroupEnd failed");
+      }
+      cudaEventRecord(e.b, sc);
+      cudaEventRecord(h->ev_comm, sc);
+      cudaStreamWaitEvent(st, h->ev_comm, 0);
+    } else {
+      cudaEventRecord(e.a, st);
+      const size_t cnt = (size_t)dst.R * h->KP;
+      ncclResult_t r = nc.AllGather(dst.F + (size_t)me * cnt, dst.F, cnt, ncclFloat, h->comm, st);
+      if (r != ncclSuccess)
+        return fail(h, PIO_ALS_ERR_COMM, "ncclAllGather failed: %s", nc.GetErrorString ? nc.GetErrorString(r) : "?");
+      cudaEventRecord(e.b, st);
+    }
   }
   return PIO_ALS_OK;
 }
@@ -1097,18 +1353,31 @@ static int create_common(pio_als_handle* h) {
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   h->KP = pad_rank(h->cfg.rank);
+  if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->comm_st, cudaStreamNonBlocking) != cudaSuccess)
+    return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaStreamCreate");
   {
-    // tensor-core Gramian (als_tc_kernel.cuh): parity-green but not yet faster than the FP32 kernel -> opt-in
+    cudaEvent_t* evs[4] = {&h->ev_start, &h->ev_heavy, &h->ev_comm, nullptr};
+    for (int i = 0; evs[i]; ++i)
+      if (cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming) != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaEventCreate");
+    for (int i = 0; i < 8; ++i)
+      if (cudaEventCreateWithFlags(&h->ev_piece[i], cudaEventDisableTiming) != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaEventCreate");
+    h->n_pieces = h->cfg.world_size > 1 ? 4 : 1;
+    if (const char* v = getenv("PIO_ALS_PIECES")) {
+      const int n = atoi(v);
+      if (n >= 1 && n <= 8) h->n_pieces = n;
+    }
+  }
+  {
+    // Rank 33..64 kernel selection.  Default: the pair kernel (als_pair_kernel.cuh: mma.sync 3xTF32 Gramian, two rows per
+    // warp, lockstep Cholesky) for every side -- measured at C2 it is the fastest on both sides (user half-step 18.7 ms,
+    // item half-step 12.9 ms vs 17.1 ms for the tcgen05 kernel) and, with rows above 1024 ratings summed in two
+    // levels, inside the parity bound on long rows.  PIO_ALS_TC=1: the tcgen05 Gramian kernel (als_tc_kernel.cuh) for
+    // every side (PIO_ALS_TC_MIN_DEG=n: only sides averaging >= n ratings per row); PIO_ALS_MMA=1: the round-1
+    // one-warp-per-row mma.sync kernel; PIO_ALS_MMA=0: the FP32 CUDA-core kernel.
     const char* env = getenv("PIO_ALS_TC");
-    // rank 33..64 kernel selection for the rows below the heavy-row threshold.  Default: sides whose rows average >= 256
-    // ratings (the item side of the headline workload) accumulate their Gramians on tcgen05, every other side runs the
-    // one-warp-per-row mma.sync kernel.  Measured at C2: item side 15.0 ms (tcgen05) vs 13.7 ms (mma.sync), but the
-    // tcgen05 accumulator is the more accurate one on rows of thousands of ratings (mma.sync adds with truncation inside
-    // the tensor core: 1.1e-4 vs < 1e-4 against the oracle on the 10 000-ratings-per-row test), so accuracy decides.
-    // PIO_ALS_TC=0: no tcgen05 side; PIO_ALS_TC=1: every side; PIO_ALS_TC_MIN_DEG moves the threshold; PIO_ALS_MMA=0:
-    // FP32 CUDA-core kernel instead of mma.sync.
-    h->use_tc = h->KP == 64 && !(env && env[0] == '0');
-    h->tc_min_deg = (env && env[0] == '1') ? 0.0 : 256.0;
+    h->use_tc = h->KP == 64 && env && env[0] == '1';
+    h->tc_min_deg = 0.0;
     if (const char* md = getenv("PIO_ALS_TC_MIN_DEG")) h->tc_min_deg = atof(md);
     if (const char* sp = getenv("PIO_ALS_TC_SPLIT")) h->tc_split = sp[0] == '1';
     if (const char* mm_ = getenv("PIO_ALS_MMA")) {
@@ -1119,7 +1388,7 @@ static int create_common(pio_als_handle* h) {
     if (const char* v = getenv("PIO_ALS_SEG_T")) h->pair_seg_t = atoi(v) > 0 ? atoi(v) : PAIR_SEG_T;
     if (const char* v = getenv("PIO_ALS_PART")) h->pair_part = atoi(v) >= 8 ? (atoi(v) + 7) / 8 * 8 : PAIR_PART;
   }
-  h->gram_blocks = 2 * h->sm_count;
+  h->gram_blocks = (2 * h->sm_count + 7) / 8 * 8;   // a multiple of 8: the partial sums shard over 2, 4 or 8 ranks
   if (cudaMallocAsync((void**)&h->yty, sizeof(float) * h->KP * h->KP, h->stream) != cudaSuccess ||
       cudaMallocAsync((void**)&h->gram_partial, sizeof(double) * (size_t)h->gram_blocks * h->KP * h->KP, h->stream) != cudaSuccess ||
       cudaMallocAsync((void**)&h->d_fail, sizeof(int), h->stream) != cudaSuccess ||
@@ -1179,37 +1448,25 @@ void pio_als_destroy(pio_als_handle* h) {
       cudaEventDestroy(e.b);
     }
     if (h->comm) nccl_api().CommDestroy(h->comm);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_heavy) cudaEventDestroy(h->ev_heavy);
+    if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+    for (int i = 0; i < 8; ++i)
+      if (h->ev_piece[i]) cudaEventDestroy(h->ev_piece[i]);
+    if (h->aux) cudaStreamDestroy(h->aux);
+    if (h->comm_st) cudaStreamDestroy(h->comm_st);
     cudaStreamDestroy(h->stream);
   }
   delete h;
 }
 
-int pio_als_set_ratings_coo_device(pio_als_handle* h, const int32_t* d_user, const int32_t* d_item,
-                                   const float* d_rating, int64_t nnz, int dedup_mode, const int64_t* d_ts) {
+static int set_ratings_impl(pio_als_handle* h, const int32_t* user, const int32_t* item, const float* rating, int64_t nnz,
+                            int dedup_mode, const int64_t* ts, bool on_device, bool sharded) {
   if (!h) return PIO_ALS_ERR_ARG;
-  if (!d_user || !d_item || !d_rating) return fail(h, PIO_ALS_ERR_ARG, "null rating arrays");
-  std::lock_guard<std::mutex> lk(h->mu);
-  CK(h, cudaSetDevice(h->cfg.device));
-  cudaEvent_t a, b;
-  cudaEventCreate(&a);
-  cudaEventCreate(&b);
-  cudaEventRecord(a, h->stream);
-  int rc = ingest_device(h, d_user, d_item, d_rating, nnz, dedup_mode, (const long long*)d_ts);
-  cudaEventRecord(b, h->stream);
-  cudaEventSynchronize(b);
-  float ms = 0;
-  cudaEventElapsedTime(&ms, a, b);
-  h->st.last_ingest_ms = ms;
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
-  return rc;
-}
-
-int pio_als_set_ratings_coo(pio_als_handle* h, const int32_t* user, const int32_t* item, const float* rating,
-                            int64_t nnz, int dedup_mode, const int64_t* ts) {
-  if (!h) return PIO_ALS_ERR_ARG;
-  if (nnz <= 0) return fail(h, PIO_ALS_ERR_ARG, "ratings cannot be empty (the templates require(!ratings.take(1).isEmpty))");
-  if (!user || !item || !rating) return fail(h, PIO_ALS_ERR_ARG, "null rating arrays");
+  const bool may_be_empty = sharded && h->cfg.world_size > 1;   // a rank's slice may be empty, the union may not
+  if (nnz < 0 || (nnz == 0 && !may_be_empty))
+    return fail(h, PIO_ALS_ERR_ARG, "ratings cannot be empty (the templates require(!ratings.take(1).isEmpty))");
+  if (nnz > 0 && (!user || !item || !rating)) return fail(h, PIO_ALS_ERR_ARG, "null rating arrays");
   std::lock_guard<std::mutex> lk(h->mu);
   CK(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = h->stream;
@@ -1217,21 +1474,33 @@ int pio_als_set_ratings_coo(pio_als_handle* h, const int32_t* user, const int32_
   cudaEventCreate(&a);
   cudaEventCreate(&b);
   cudaEventRecord(a, st);
-  int *du = nullptr, *di = nullptr;
-  float* dr = nullptr;
-  long long* dts = nullptr;
-  CK(h, dalloc(h, &du, (size_t)nnz));
-  CK(h, dalloc(h, &di, (size_t)nnz));
-  CK(h, dalloc(h, &dr, (size_t)nnz));
-  CK(h, cudaMemcpyAsync(du, user, sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
-  CK(h, cudaMemcpyAsync(di, item, sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
-  CK(h, cudaMemcpyAsync(dr, rating, sizeof(float) * nnz, cudaMemcpyHostToDevice, st));
-  if (ts && dedup_mode == PIO_ALS_DEDUP_KEEP_LAST) {
-    CK(h, dalloc(h, &dts, (size_t)nnz));
-    CK(h, cudaMemcpyAsync(dts, ts, sizeof(long long) * nnz, cudaMemcpyHostToDevice, st));
+  int rc;
+  {
+    Scratch tmp(h);
+    const int *du = user, *di = item;
+    const float* dr = rating;
+    const long long* dts = (const long long*)ts;
+    auto stage = [&]() -> int {
+      if (on_device || nnz == 0) return PIO_ALS_OK;
+      int *tu = nullptr, *ti = nullptr;
+      float* tr = nullptr;
+      long long* tt = nullptr;
+      CK(h, tmp.alloc(&tu, (size_t)nnz));
+      CK(h, tmp.alloc(&ti, (size_t)nnz));
+      CK(h, tmp.alloc(&tr, (size_t)nnz));
+      CK(h, cudaMemcpyAsync(tu, user, sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
+      CK(h, cudaMemcpyAsync(ti, item, sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
+      CK(h, cudaMemcpyAsync(tr, rating, sizeof(float) * nnz, cudaMemcpyHostToDevice, st));
+      if (ts && dedup_mode == PIO_ALS_DEDUP_KEEP_LAST) {
+        CK(h, tmp.alloc(&tt, (size_t)nnz));
+        CK(h, cudaMemcpyAsync(tt, ts, sizeof(long long) * nnz, cudaMemcpyHostToDevice, st));
+      }
+      du = tu; di = ti; dr = tr; dts = tt;
+      return PIO_ALS_OK;
+    };
+    rc = stage();
+    if (rc == PIO_ALS_OK) rc = ingest_device(h, du, di, dr, nnz, dedup_mode, dts, sharded);
   }
-  int rc = ingest_device(h, du, di, dr, nnz, dedup_mode, dts);
-  dfree(h, du); dfree(h, di); dfree(h, dr); dfree(h, dts);
   cudaEventRecord(b, st);
   cudaEventSynchronize(b);
   float ms = 0;
@@ -1240,6 +1509,26 @@ int pio_als_set_ratings_coo(pio_als_handle* h, const int32_t* user, const int32_
   cudaEventDestroy(a);
   cudaEventDestroy(b);
   return rc;
+}
+
+int pio_als_set_ratings_coo_device(pio_als_handle* h, const int32_t* d_user, const int32_t* d_item,
+                                   const float* d_rating, int64_t nnz, int dedup_mode, const int64_t* d_ts) {
+  return set_ratings_impl(h, d_user, d_item, d_rating, nnz, dedup_mode, d_ts, true, false);
+}
+
+int pio_als_set_ratings_coo(pio_als_handle* h, const int32_t* user, const int32_t* item, const float* rating,
+                            int64_t nnz, int dedup_mode, const int64_t* ts) {
+  return set_ratings_impl(h, user, item, rating, nnz, dedup_mode, ts, false, false);
+}
+
+int pio_als_set_ratings_coo_sharded(pio_als_handle* h, const int32_t* user, const int32_t* item, const float* rating,
+                                    int64_t nnz_local, int dedup_mode, const int64_t* ts) {
+  return set_ratings_impl(h, user, item, rating, nnz_local, dedup_mode, ts, false, true);
+}
+
+int pio_als_set_ratings_coo_sharded_device(pio_als_handle* h, const int32_t* d_user, const int32_t* d_item,
+                                           const float* d_rating, int64_t nnz_local, int dedup_mode, const int64_t* d_ts) {
+  return set_ratings_impl(h, d_user, d_item, d_rating, nnz_local, dedup_mode, d_ts, true, true);
 }
 
 int pio_als_set_init(pio_als_handle* h, const float* user_factors, const float* item_factors) {

@@ -27,7 +27,8 @@ ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NUMERIC, ERR_IO, ERR_COMM = -1, -2, -3, -4, -5
 
 EXPORTED_SYMBOLS = [
     "pio_als_abi_version", "pio_als_device_count", "pio_als_nccl_unique_id", "pio_als_create",
-    "pio_als_destroy", "pio_als_last_error", "pio_als_set_ratings_coo", "pio_als_set_ratings_coo_device",
+    "pio_als_destroy", "pio_als_last_error", "pio_als_set_ratings_coo", "pio_als_set_ratings_coo_device", "pio_als_set_ratings_coo_sharded",
+    "pio_als_set_ratings_coo_sharded_device",
     "pio_als_set_init", "pio_als_run", "pio_als_get_factors", "pio_als_train", "pio_als_recommend",
     "pio_als_similar", "pio_als_similar_batch", "pio_als_model_import", "pio_als_save", "pio_als_load", "pio_als_get_stats", "pio_als_get_phase_ms",
     "pio_als_synth_ratings_device", "pio_nb_train", "pio_nb_predict",
@@ -168,11 +169,22 @@ class NativeALS:
                                                   _ptr(rating, C.c_float), C.c_int64(user.shape[0]),
                                                   C.c_int(dedup), _ptr(tsa, C.c_int64)))
 
-    def set_ratings_device(self, d_user: int, d_item: int, d_rating: int, nnz: int, dedup=DEDUP_NONE, d_ts: int = 0):
-        """Raw device pointers (ints), e.g. ``tensor.data_ptr()``."""
-        self._check(lib().pio_als_set_ratings_coo_device(self._h, C.c_void_p(d_user), C.c_void_p(d_item),
-                                                         C.c_void_p(d_rating), C.c_int64(nnz), C.c_int(dedup),
-                                                         C.c_void_p(d_ts) if d_ts else None))
+    def set_ratings_device(self, d_user: int, d_item: int, d_rating: int, nnz: int, dedup=DEDUP_NONE, d_ts: int = 0,
+                           sharded=False):
+        """Raw device pointers (ints), e.g. ``tensor.data_ptr()``.  sharded: this rank's slice of the events."""
+        f = lib().pio_als_set_ratings_coo_sharded_device if sharded else lib().pio_als_set_ratings_coo_device
+        self._check(f(self._h, C.c_void_p(d_user), C.c_void_p(d_item), C.c_void_p(d_rating), C.c_int64(nnz), C.c_int(dedup),
+                      C.c_void_p(d_ts) if d_ts else None))
+
+    def set_ratings_sharded(self, user, item, rating, dedup=DEDUP_NONE, ts=None):
+        """This rank's slice of the events (HOST arrays); collective over the ranks of the job."""
+        user = np.ascontiguousarray(user, np.int32)
+        item = np.ascontiguousarray(item, np.int32)
+        rating = np.ascontiguousarray(rating, np.float32)
+        tsa = None if ts is None else np.ascontiguousarray(ts, np.int64)
+        self._check(lib().pio_als_set_ratings_coo_sharded(self._h, _ptr(user, C.c_int32), _ptr(item, C.c_int32),
+                                                          _ptr(rating, C.c_float), C.c_int64(user.shape[0]),
+                                                          C.c_int(dedup), _ptr(tsa, C.c_int64)))
 
     def set_init(self, user_factors, item_factors=None):
         uf = np.ascontiguousarray(user_factors, np.float32)

@@ -146,25 +146,24 @@ def test_config_c1_recommendation_template(native, oracle):
 
 @pytest.mark.parametrize("path", ["fp32", "mma", "pair", "tcgen05"])
 def test_heavy_rows_split_mode(native, oracle, monkeypatch, path):
-    """Items with far more ratings than the heavy-row threshold are cut into 2016-rating parts (part launch on the FP32
-    kernel + als_finish_kernel); the rows below the threshold go through each of the three rank-64 kernels in turn
-    (tcgen05 is what the default selection picks for this item side: 10 000 ratings per row)."""
+    """Items with far more ratings than the heavy-row threshold are cut into parts (pair kernel: 512-rating parts above
+    1024 ratings, summed by als_finish_pair_kernel; the other kernels: 2016-rating parts on the FP32 kernel +
+    als_finish_kernel); the rows below the threshold go through each of the four rank-64 kernels in turn (the pair kernel
+    is the default)."""
     monkeypatch.delenv("PIO_ALS_TC", raising=False)
     monkeypatch.delenv("PIO_ALS_MMA", raising=False)
     if path == "fp32":
-        monkeypatch.setenv("PIO_ALS_TC", "0")
         monkeypatch.setenv("PIO_ALS_MMA", "0")
     elif path == "mma":
-        monkeypatch.setenv("PIO_ALS_TC", "0")
         monkeypatch.setenv("PIO_ALS_MMA", "1")
-    elif path == "pair":
-        monkeypatch.setenv("PIO_ALS_TC", "0")
+    elif path == "tcgen05":
+        monkeypatch.setenv("PIO_ALS_TC", "1")
     nu, ni, nnz = 20000, 40, 400000
     u, i, r = synth.synth_ratings(nu, ni, nnz, seed=9, implicit=True)
     m, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 3, 0.05, True, 1.0)
     assert m.phase_ms()["item_kernel"] == path
-    # mma.sync sums the eight products of a chunk with truncation inside the tensor core; on 8000-rating rows that costs
-    # about 1.1e-4 on the item factors - the reason the default selection sends long-row sides to the tcgen05 kernel
+    # the round-1 one-warp-per-row mma.sync kernel (PIO_ALS_MMA=1, not a default path any more) accumulates a whole
+    # 8000-rating row in one level and sits at 1.1e-4 here; the pair kernel sums such rows in two levels and holds 1e-4
     tol = 2e-4 if path == "mma" else TOL
     assert frob_rel(g[0], o[0]) <= tol and frob_rel(g[1], o[1]) <= tol, (frob_rel(g[0], o[0]), frob_rel(g[1], o[1]))
     _, g, o = run_both(native, oracle, nu, ni, u, i, r, 10, 3, 0.05, False, 1.0)
@@ -172,17 +171,17 @@ def test_heavy_rows_split_mode(native, oracle, monkeypatch, path):
 
 
 def test_rank64_kernel_selection(native, oracle, monkeypatch):
-    """Rank 64 default: the item side (rows average >= 256 ratings) on the tcgen05 kernel, the user side (20 ratings per
-    row) on the one-warp-per-row mma.sync kernel; PIO_ALS_TC=0 puts both on mma.sync, PIO_ALS_TC=0 + PIO_ALS_MMA=0 on the
-    FP32 kernel.  All three are within tolerance of the oracle and of each other, and really are different code paths."""
+    """Rank 64 default: both sides on the pair kernel; PIO_ALS_TC=1 + PIO_ALS_TC_MIN_DEG=256 puts the item side (rows
+    average >= 256 ratings) on the tcgen05 kernel, PIO_ALS_MMA=1 selects the round-1 mma.sync kernel, PIO_ALS_MMA=0 the
+    FP32 kernel.  All are within tolerance of the oracle and of each other, and really are different code paths."""
     for v in ("PIO_ALS_TC", "PIO_ALS_TC_MIN_DEG", "PIO_ALS_MMA"):
         monkeypatch.delenv(v, raising=False)
     nu, ni, nnz = 20000, 300, 400000
     for implicit in (True, False):
         u, i, r = synth.synth_ratings(nu, ni, nnz, seed=21, implicit=implicit)
         res = {}
-        for path, env in (("tcgen05", {}), ("pair", {"PIO_ALS_TC": "0"}), ("mma", {"PIO_ALS_TC": "0", "PIO_ALS_MMA": "1"}),
-                          ("fp32", {"PIO_ALS_TC": "0", "PIO_ALS_MMA": "0"})):
+        for path, env in (("pair", {}), ("tcgen05", {"PIO_ALS_TC": "1", "PIO_ALS_TC_MIN_DEG": "256"}),
+                          ("mma", {"PIO_ALS_MMA": "1"}), ("fp32", {"PIO_ALS_MMA": "0"})):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             m, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 4, 0.05, implicit, 1.0)
