@@ -712,7 +712,6 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
   I.n_internal = I.R * W;
   U.bits = ceil_log2((uint64_t)U.n_internal);
   I.bits = ceil_log2((uint64_t)I.n_internal);
-  NcclApi& nc = nccl_api();
 
   CK(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
   if (nnz > 0) {
@@ -806,6 +805,7 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
   }
   long long n2_global = n2;
   if (sharded) {
+    NcclApi& nc = nccl_api();   // only multi-GPU jobs touch NCCL (a single-GPU process must not load libnccl at all)
     for (Side* s : {&U, &I}) {
       if (nc.AllReduce(s->deg, s->deg, (size_t)s->n, ncclUint32, ncclSum, h->comm, st) != ncclSuccess ||
           nc.AllReduce(s->npos, s->npos, (size_t)s->n, ncclUint32, ncclSum, h->comm, st) != ncclSuccess)
