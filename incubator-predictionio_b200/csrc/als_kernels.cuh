@@ -702,12 +702,29 @@ gram_partial_kernel(const float* __restrict__ X, const int* __restrict__ p2i, in
     for (int j = 0; j < TM; ++j) out[(ty * TM + i) * KP + tx * TM + j] = acc[i][j];
 }
 
-__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nparts, int n,
-                                   float* __restrict__ out) {
+// Two-level fixed-order reduction of the per-block partials: GRAM_GROUPS group sums (each over n_blocks / GRAM_GROUPS
+// consecutive blocks, in block order), then the sum of the group sums in group order.  The grouping does not depend on
+// the number of GPUs: a sharded run computes whole groups per rank, all-gathers the group sums (KP^2 doubles each) and
+// finishes with the same second level -- bit-identical to the single-GPU result.
+constexpr int GRAM_GROUPS = 8;
+
+__global__ void gram_group_kernel(const double* __restrict__ partial, int blocks_per_group, int n, int g0,
+                                  double* __restrict__ gsum) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = g0 + blockIdx.y;
+  if (o >= n) return;
+  const double* p = partial + (size_t)g * blocks_per_group * n;
+  double s = 0.0;
+  for (int q = 0; q < blocks_per_group; ++q) s += p[(size_t)q * n + o];
+  gsum[(size_t)g * n + o] = s;
+}
+
+__global__ void gram_reduce_kernel(const double* __restrict__ gsum, int n, float* __restrict__ out) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n) return;
   double s = 0.0;
-  for (int q = 0; q < nparts; ++q) s += partial[(size_t)q * n + o];
+#pragma unroll
+  for (int g = 0; g < GRAM_GROUPS; ++g) s += gsum[(size_t)g * n + o];
   out[o] = (float)s;
 }
 

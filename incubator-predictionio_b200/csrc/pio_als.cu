@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <deque>
 #include <exception>
 #include <mutex>
@@ -392,6 +393,7 @@ struct pio_als_handle {
   Side U, I;
   float* yty = nullptr;
   double* gram_partial = nullptr;
+  double* gram_gsum = nullptr;   // [GRAM_GROUPS][KP*KP] group sums of the YtY partials
   int gram_blocks = 0;
   int* d_fail = nullptr;
   int* d_counts = nullptr;
@@ -713,6 +715,17 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
   U.bits = ceil_log2((uint64_t)U.n_internal);
   I.bits = ceil_log2((uint64_t)I.n_internal);
 
+  // PIO_ALS_INGEST_TRACE=1: wall-clock milliseconds per phase (stream drained at every mark) on stderr
+  const bool trace = getenv("PIO_ALS_INGEST_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(st);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pio_als ingest r%d] %-28s %8.3f ms\n", h->cfg.world_rank, what,
+            std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   CK(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
   if (nnz > 0) {
     validate_coo_kernel<<<nblk(nnz, 256), 256, 0, st>>>(d_user, d_item, nnz, U.n, I.n, h->d_fail);
@@ -723,6 +736,7 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
   CK(h, cudaStreamSynchronize(st));
   if (bad) return fail(h, PIO_ALS_ERR_ARG, "%d ratings have a user/item index out of range", bad);
 
+  mark("validate");
   Scratch tmp(h);   // everything temporary: released on every exit path, including the CK() early returns
   // 0. sharded + dedup: first bring all events of a user to one rank (user mod W), keeping the event order
   const int* su = d_user;
@@ -748,6 +762,7 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
     su = (const int*)xu; si = (const int*)xi; sr = (const float*)xr; sts = (const long long*)xt;
   }
 
+  mark("exchange by user residue");
   // 1. optional dedup of repeated (user,item) pairs (all copies of a pair are on this rank)
   const int* cu = su;
   const int* ci = si;
@@ -788,6 +803,7 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
     cr = dr_;
   }
 
+  mark("dedup");
   // 2. degrees, positive-rating counts (sharded: summed over the ranks)
   for (Side* s : {&U, &I}) {
     CK(h, dalloc(h, &s->deg, (size_t)s->n));
@@ -823,18 +839,22 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
   }
   h->st.nnz = n2_global;
 
+  mark("degrees (+ all-reduce)");
   // 3. renumber rows: degree-descending, dealt to ranks (the same on every rank)
   int rc = rank_rows(h, U);
   if (rc) return rc;
   rc = rank_rows(h, I);
   if (rc) return rc;
 
+  mark("rank rows");
   // 4. the two CSR orientations in internal numbering (only this rank's rows are kept)
   if (!sharded) {
     rc = build_side(h, U, I, cu, ci, cr, n2, n2_global);
     if (rc) return rc;
+    mark("build user side");
     rc = build_side(h, I, U, ci, cu, cr, n2, n2_global);
     if (rc) return rc;
+    mark("build item side");
   } else {
     struct { Side* row; Side* col; const int* rowext; const int* colext; } jobs[2] = {{&U, &I, cu, ci}, {&I, &U, ci, cu}};
     for (auto& j : jobs) {
@@ -852,8 +872,10 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
       long long ne = 0;
       rc = exchange_events(h, recv, ka, va, kb, vb, n2, arrs, 3, &ne);
       if (rc) return rc;
+      mark("exchange by row owner");
       rc = build_side(h, *j.row, *j.col, (const int*)xrow, (const int*)xcol, (const float*)xr, ne, n2_global);
       if (rc) return rc;
+      mark("build side");
     }
   }
 
@@ -869,6 +891,7 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
   }
   h->have_init = false;
   CK(h, cudaStreamSynchronize(st));
+  mark("factor buffers");
   h->st.n_users_active = U.n_active;
   h->st.n_items_active = I.n_active;
   if (W > 1) {
@@ -1213,14 +1236,16 @@ static cudaError_t launch_solve(pio_als_handle* h, Side& dst, const Side& src) {
   }
 }
 
-// YtY of the (replicated) source factors.  world_size > 1: every rank sums a contiguous share of the gram_blocks position
-// ranges from its replica and the fp64 partials are all-gathered in place; the final reduction adds the same partials in
-// the same order everywhere, so the result is bit-identical to the single-GPU one (and the 0.77 ms this cost on every
-// rank at C2 shrinks with the number of GPUs).
+// YtY of the (replicated) source factors: gram_blocks = GRAM_GROUPS x (SM count) position ranges, summed in fp64 per block,
+// then per group, then over the groups (fixed orders).  world_size > 1: every rank computes whole groups from its replica
+// and the group sums (KP^2 doubles each) are all-gathered in place -- bit-identical to the single-GPU result, and the
+// cost (0.77 ms per iteration on every rank at C2 in round 1) shrinks with the number of GPUs.
 static int launch_gram(pio_als_handle* h, const Side& src) {
-  const int nb = h->gram_blocks, W = h->cfg.world_size;
-  const bool shard = W > 1 && nb % W == 0;
-  const int mine = shard ? nb / W : nb, b0 = shard ? h->cfg.world_rank * mine : 0;
+  const int nb = h->gram_blocks, W = h->cfg.world_size, n = h->KP * h->KP;
+  const int bpg = nb / GRAM_GROUPS;
+  const bool shard = W > 1 && GRAM_GROUPS % W == 0;
+  const int my_groups = shard ? GRAM_GROUPS / W : GRAM_GROUPS, g0 = shard ? h->cfg.world_rank * my_groups : 0;
+  const int mine = my_groups * bpg, b0 = g0 * bpg;
   switch (h->KP) {
     case 16: gram_partial_kernel<16><<<mine, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial, b0, nb); break;
     case 32: gram_partial_kernel<32><<<mine, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial, b0, nb); break;
@@ -1228,13 +1253,14 @@ static int launch_gram(pio_als_handle* h, const Side& src) {
     default: gram_partial_kernel<128><<<mine, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial, b0, nb); break;
   }
   LAUNCHED(h);
-  const int n = h->KP * h->KP;
+  gram_group_kernel<<<dim3(nblk(n, 128), my_groups), 128, 0, h->stream>>>(h->gram_partial, bpg, n, g0, h->gram_gsum);
+  LAUNCHED(h);
   if (shard) {
-    const size_t cnt = (size_t)mine * n;
-    if (nccl_api().AllGather(h->gram_partial + (size_t)b0 * n, h->gram_partial, cnt, ncclDouble, h->comm, h->stream) != ncclSuccess)
-      return fail(h, PIO_ALS_ERR_COMM, "ncclAllGather (YtY partials) failed");
+    const size_t cnt = (size_t)my_groups * n;
+    if (nccl_api().AllGather(h->gram_gsum + (size_t)g0 * n, h->gram_gsum, cnt, ncclDouble, h->comm, h->stream) != ncclSuccess)
+      return fail(h, PIO_ALS_ERR_COMM, "ncclAllGather (YtY group sums) failed");
   }
-  gram_reduce_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(h->gram_partial, nb, n, h->yty);
+  gram_reduce_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(h->gram_gsum, n, h->yty);
   LAUNCHED(h);
   CK(h, cudaGetLastError());
   return PIO_ALS_OK;
@@ -1388,9 +1414,10 @@ static int create_common(pio_als_handle* h) {
     if (const char* v = getenv("PIO_ALS_SEG_T")) h->pair_seg_t = atoi(v) > 0 ? atoi(v) : PAIR_SEG_T;
     if (const char* v = getenv("PIO_ALS_PART")) h->pair_part = atoi(v) >= 8 ? (atoi(v) + 7) / 8 * 8 : PAIR_PART;
   }
-  h->gram_blocks = (2 * h->sm_count + 7) / 8 * 8;   // a multiple of 8: the partial sums shard over 2, 4 or 8 ranks
+  h->gram_blocks = GRAM_GROUPS * h->sm_count;   // a sharded run gives every rank whole groups: one CTA per SM at 8 GPUs
   if (cudaMallocAsync((void**)&h->yty, sizeof(float) * h->KP * h->KP, h->stream) != cudaSuccess ||
       cudaMallocAsync((void**)&h->gram_partial, sizeof(double) * (size_t)h->gram_blocks * h->KP * h->KP, h->stream) != cudaSuccess ||
+      cudaMallocAsync((void**)&h->gram_gsum, sizeof(double) * (size_t)GRAM_GROUPS * h->KP * h->KP, h->stream) != cudaSuccess ||
       cudaMallocAsync((void**)&h->d_fail, sizeof(int), h->stream) != cudaSuccess ||
       cudaMallocAsync((void**)&h->d_counts, 4 * sizeof(int), h->stream) != cudaSuccess)
     return fail(nullptr, PIO_ALS_ERR_CUDA, "device allocation failed");
@@ -1437,6 +1464,7 @@ void pio_als_destroy(pio_als_handle* h) {
     free_side(h, h->I, false);
     dfree(h, h->yty);
     dfree(h, h->gram_partial);
+    dfree(h, h->gram_gsum);
     dfree(h, h->d_fail);
     dfree(h, h->d_counts);
     cudaStreamSynchronize(h->stream);
