@@ -317,6 +317,46 @@ def topk_bench(native, o, cores, m, nu, ni, k, uf, itf, uh, ih, peaks, dev):
                      "frac": nq / 16.0 * scan_bytes / dt / 1e9 / peaks["hbm"],
                      "note": "algorithmic bytes = one scan of the item matrix per group of 16 queries (the kernel's "
                              "batching); fp64 score accumulation makes the DFMA pipe the real bound"}}
+    # similarproduct path (A9, BASELINE.json configs[3]): cosine top-20 over 1 M item vectors (unit-norm Gaussian, rank 64),
+    # 10 k queries of 1-5 items, one pio_als_similar_batch call on an imported item-only model
+    try:
+        from pio_b200 import synth
+        n_it, kk, nqs = 1_000_000, 64, 10_000
+        big = np.ascontiguousarray(np.resize(synth.synth_init_factors(1 << 16, kk, SEED + 1, 1), (n_it, kk)))
+        big *= (1.0 + (np.arange(n_it, dtype=np.float32) % 97)[:, None] / 97.0)      # rows differ although the pattern repeats
+        mm = native.NativeALS.from_factors(None, big, None, None, device=dev)
+        queries = [rng.integers(0, n_it, rng.integers(1, 6)).astype(np.int32) for _ in range(nqs)]
+        mm.similar_batch(queries[:64], 20)
+        t0 = time.perf_counter()
+        bi, bs, bc = mm.similar_batch(queries, 20)
+        dt = time.perf_counter() - t0
+        ns2 = 24
+        t0 = time.perf_counter()
+        ok = True
+        for j in range(ns2):
+            oi, os_, oc = o.similar(big, None, queries[j], 20)
+            ok = ok and np.array_equal(bi[j], oi) and np.array_equal(bs[j], os_)
+        cpu_dt = time.perf_counter() - t0
+        lat2 = []
+        for j in range(10):
+            t0 = time.perf_counter()
+            mm.similar(queries[j], 20)
+            lat2.append(time.perf_counter() - t0)
+        sb = n_it * kk * 4
+        out["similar_c4"] = {
+            "what": f"pio_als_similar_batch: {nqs} queries of 1-5 items, cosine top-20 over {n_it} item vectors, rank {kk}, "
+                    "one call, host buffers",
+            "value": nqs / dt, "unit": "predictions/s", "seconds": dt,
+            "bit_exact_vs_oracle_on_sample": bool(ok), "sample_queries_checked": ns2,
+            "cpu_baseline": {"value": ns2 / cpu_dt, "unit": "predictions/s", "cores": cores, "kind": "port",
+                             "sample": f"{ns2} of the same queries (oracle restatement of the similarproduct predict scan)"},
+            "roofline": {"bound": "hbm", "achieved": nqs / 8.0 * sb / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": nqs / 8.0 * sb / dt / 1e9 / peaks["hbm"],
+                         "note": "algorithmic bytes = one scan of the item matrix per group of 8 queries"},
+            "single_query_ms": float(np.median(lat2) * 1e3), "single_query_hbm_floor_ms": sb / (peaks["hbm"] * 1e9) * 1e3}
+        mm.close()
+    except Exception as e:
+        out["similar_c4"] = {"error": repr(e)}
     # single-query latency
     lat = []
     for q in range(20):

@@ -341,6 +341,9 @@ class Engine:
         return models
 
     def makeSerializableModels(self, sc, engineInstanceId, algoParamsList, algorithms, models) -> List[Any]:
+        # multi-GPU training (one process per GPU): every rank holds the same trained model, rank 0 persists it
+        if getattr(sc, "world_rank", 0) != 0:
+            return [Unit for _ in models]
         return [a.makePersistentModel(sc, f"{engineInstanceId}-{ax}-{type(a).__name__}", p, m)
                 for ax, (a, p, m) in enumerate(zip(algorithms, algoParamsList, models))]
 

@@ -319,6 +319,22 @@ __global__ void gather_rows_kernel(const float* F, int kp, const int* rows_ext, 
   if (threadIdx.x == 0 && valid) valid[q] = ok ? 1 : 0;
   (void)n;
 }
+// low-latency serving: the (few) row ids travel in the kernel parameters, no host-to-device copy
+struct IdList {
+  int v[40];
+};
+__global__ void gather_rows_ids_kernel(const float* F, int kp, IdList ids, const int* perm, const uint32_t* deg, int n_ext,
+                                       float* out, uint8_t* valid) {
+  const int q = blockIdx.x;
+  const int r = ids.v[q];
+  const bool ok = r >= 0 && r < n_ext && deg[r] > 0;
+  for (int c = threadIdx.x; c < kp; c += blockDim.x) out[(size_t)q * kp + c] = ok ? F[(size_t)perm[r] * kp + c] : 0.f;
+  if (threadIdx.x == 0 && valid) valid[q] = ok ? 1 : 0;
+}
+__global__ void copy_rows_kernel(const float* src, int kp, const int* rows, float* out) {
+  const int v = blockIdx.x;
+  for (int c = threadIdx.x; c < kp; c += blockDim.x) out[(size_t)v * kp + c] = src[(size_t)rows[v] * kp + c];
+}
 __global__ void synth_kernel(int nu, int ni, long long n, uint64_t seed, int implicit, long long start, int* u,
                              int* it, float* r) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -412,6 +428,13 @@ struct pio_als_handle {
   cudaEvent_t ev_start = nullptr, ev_heavy = nullptr, ev_piece[8] = {}, ev_comm = nullptr;
   int n_pieces = 1;           // PIO_ALS_PIECES (1..8); default 4 when world_size > 1
   bool pieces_done = false;   // the last launch_solve recorded ev_piece[] / ev_heavy (pair path)
+  // low-latency serving (few queries, topk <= 128): a persistent device arena and a mapped pinned host arena -- no
+  // allocation, no staging copies, results written by the merge kernel straight into host memory
+  unsigned char* srv_dev = nullptr;
+  size_t srv_dev_cap = 0;
+  unsigned char* srv_host = nullptr;       // cudaHostAlloc(mapped)
+  unsigned char* srv_host_dev = nullptr;   // its device address
+  size_t srv_host_cap = 0;
   bool tc_split = false;      // PIO_ALS_TC_SPLIT=1: the tensor-core kernel only accumulates, a second kernel solves (measured: no gain)
   float* tc_out = nullptr;    // split mode: normal equations of one tile of rows ([rows][ASLOT + KP])
   size_t tc_out_rows = 0;
@@ -1481,6 +1504,8 @@ void pio_als_destroy(pio_als_handle* h) {
     if (h->ev_comm) cudaEventDestroy(h->ev_comm);
     for (int i = 0; i < 8; ++i)
       if (h->ev_piece[i]) cudaEventDestroy(h->ev_piece[i]);
+    if (h->srv_dev) cudaFree(h->srv_dev);
+    if (h->srv_host) cudaFreeHost(h->srv_host);
     if (h->aux) cudaStreamDestroy(h->aux);
     if (h->comm_st) cudaStreamDestroy(h->comm_st);
     cudaStreamDestroy(h->stream);
@@ -1689,6 +1714,139 @@ int pio_als_train(pio_als_handle* h, const int32_t* user, const int32_t* item, c
   return pio_als_get_factors(h, user_out, item_out, user_has, item_has);
 }
 
+namespace pio {
+static int serve_reserve(pio_als_handle* h, size_t dev_bytes, size_t host_bytes) {
+  if (h->srv_dev_cap < dev_bytes) {
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->srv_dev) cudaFree(h->srv_dev);
+    h->srv_dev = nullptr;
+    h->srv_dev_cap = 0;
+    CK(h, cudaMalloc((void**)&h->srv_dev, dev_bytes));
+    h->srv_dev_cap = dev_bytes;
+  }
+  if (h->srv_host_cap < host_bytes) {
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->srv_host) cudaFreeHost(h->srv_host);
+    h->srv_host = nullptr;
+    h->srv_host_cap = 0;
+    CK(h, cudaHostAlloc((void**)&h->srv_host, host_bytes, cudaHostAllocMapped));
+    CK(h, cudaHostGetDevicePointer((void**)&h->srv_host_dev, h->srv_host, 0));
+    h->srv_host_cap = host_bytes;
+  }
+  return PIO_ALS_OK;
+}
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// recommend for n <= SB_QB users and topk <= TK_MAXK: three launches and one synchronisation
+static int recommend_small(pio_als_handle* h, const int32_t* users, int n, int topk, const uint8_t* item_mask,
+                           const double* item_weight, int32_t* out_items, float* out_scores, int32_t* out_count) {
+  cudaStream_t st = h->stream;
+  const int KP = h->KP;
+  const int ntiles = (h->I.n_internal + SB_THREADS - 1) / SB_THREADS;
+  int gx = 2 * h->sm_count;
+  if (gx > (ntiles + 7) / 8) gx = (ntiles + 7) / 8;
+  if (gx < 1) gx = 1;
+  const size_t o_xq = 0, o_valid = al256(o_xq + sizeof(float) * SB_QB * KP), o_cand = al256(o_valid + SB_QB),
+               o_mask = al256(o_cand + sizeof(ScoreIdx) * (size_t)SB_QB * gx * topk),
+               o_w = al256(o_mask + (item_mask ? (size_t)h->I.n : 0)),
+               dev_bytes = al256(o_w + (item_weight ? sizeof(double) * (size_t)h->I.n : 0));
+  const size_t ho_i = 0, ho_s = al256(sizeof(int) * (size_t)SB_QB * topk), ho_c = ho_s + al256(sizeof(float) * (size_t)SB_QB * topk),
+               host_bytes = ho_c + al256(sizeof(int) * SB_QB);
+  int rc = serve_reserve(h, dev_bytes, host_bytes);
+  if (rc) return rc;
+  float* d_xq = (float*)(h->srv_dev + o_xq);
+  uint8_t* d_valid = h->srv_dev + o_valid;
+  ScoreIdx* d_cand = (ScoreIdx*)(h->srv_dev + o_cand);
+  uint8_t* d_mask = item_mask ? h->srv_dev + o_mask : nullptr;
+  double* d_weight = item_weight ? (double*)(h->srv_dev + o_w) : nullptr;
+  if (item_mask) CK(h, cudaMemcpyAsync(d_mask, item_mask, (size_t)h->I.n, cudaMemcpyHostToDevice, st));
+  if (item_weight) CK(h, cudaMemcpyAsync(d_weight, item_weight, sizeof(double) * (size_t)h->I.n, cudaMemcpyHostToDevice, st));
+  const size_t sb_smem = sizeof(double) * (size_t)KP * SB_QB + sb_tile_bytes(KP) + (sizeof(double) + sizeof(int)) * (size_t)SB_QB * topk;
+  {
+    static size_t attr_smem[64] = {};
+    if (h->cfg.device < 64 && attr_smem[h->cfg.device] < sb_smem) {
+      CK(h, cudaFuncSetAttribute(score_dot_topk_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_smem));
+      attr_smem[h->cfg.device] = sb_smem;
+    }
+  }
+  IdList ids;
+  for (int q = 0; q < n; ++q) ids.v[q] = users[q];
+  gather_rows_ids_kernel<<<n, 64, 0, st>>>(h->U.F, KP, ids, h->U.perm, h->U.deg, h->U.n, d_xq, d_valid);
+  LAUNCHED(h);
+  score_dot_topk_batched_kernel<<<dim3(gx, 1), SB_THREADS, sb_smem, st>>>(h->I.F, h->I.n_internal, KP, d_xq, d_valid, n,
+                                                                         h->I.cand_ext, d_mask, d_weight, nullptr, topk, d_cand);
+  LAUNCHED(h);
+  int* m_oi = (int*)(h->srv_host_dev + ho_i);
+  float* m_os = (float*)(h->srv_host_dev + ho_s);
+  int* m_oc = (int*)(h->srv_host_dev + ho_c);
+  topk_merge_kernel<<<n, TK_THREADS, 0, st>>>(d_cand, gx * topk, topk, topk, 0, m_oi, m_os, m_oc, nullptr);
+  LAUNCHED(h);
+  CK(h, cudaStreamSynchronize(st));
+  memcpy(out_items, h->srv_host + ho_i, sizeof(int) * (size_t)n * topk);
+  memcpy(out_scores, h->srv_host + ho_s, sizeof(float) * (size_t)n * topk);
+  if (out_count) memcpy(out_count, h->srv_host + ho_c, sizeof(int) * (size_t)n);
+  return PIO_ALS_OK;
+}
+
+// one similar() query with nq <= SM_NV items and topk <= TK_MAXK: query items without a factor enter as zero vectors (their
+// cosine terms are exactly 0, like the reference skipping them), so no host round trip is needed to compact the query
+static int similar_small(pio_als_handle* h, const int32_t* query_items, int nq, int topk, const uint8_t* item_mask,
+                         const double* item_weight, int flags, int32_t* out_items, float* out_scores, int32_t* out_count) {
+  cudaStream_t st = h->stream;
+  const int KP = h->KP, k = h->cfg.rank;
+  const int ntiles = (h->I.n_internal + SB_THREADS - 1) / SB_THREADS;
+  int gx = 2 * h->sm_count;
+  if (gx > (ntiles + 7) / 8) gx = (ntiles + 7) / 8;
+  if (gx < 1) gx = 1;
+  const size_t o_qf = 0, o_cand = al256(sizeof(float) * SM_NV * KP), o_mask = al256(o_cand + sizeof(ScoreIdx) * (size_t)gx * topk),
+               o_w = al256(o_mask + (item_mask ? (size_t)h->I.n : 0)),
+               dev_bytes = al256(o_w + (item_weight ? sizeof(double) * (size_t)h->I.n : 0));
+  // mapped host arena: results, then the tiny query description the kernel reads over PCIe
+  const size_t ho_i = 0, ho_s = al256(sizeof(int) * (size_t)topk), ho_c = ho_s + al256(sizeof(float) * (size_t)topk),
+               ho_g = ho_c + 256, ho_vq = ho_g + 256, ho_qp = ho_vq + 256, ho_qid = ho_qp + 256, host_bytes = ho_qid + 256;
+  int rc = serve_reserve(h, dev_bytes, host_bytes);
+  if (rc) return rc;
+  float* d_qf = (float*)(h->srv_dev + o_qf);
+  ScoreIdx* d_cand = (ScoreIdx*)(h->srv_dev + o_cand);
+  uint8_t* d_mask = item_mask ? h->srv_dev + o_mask : nullptr;
+  double* d_weight = item_weight ? (double*)(h->srv_dev + o_w) : nullptr;
+  if (item_mask) CK(h, cudaMemcpyAsync(d_mask, item_mask, (size_t)h->I.n, cudaMemcpyHostToDevice, st));
+  if (item_weight) CK(h, cudaMemcpyAsync(d_weight, item_weight, sizeof(double) * (size_t)h->I.n, cudaMemcpyHostToDevice, st));
+  int* hg = (int*)(h->srv_host + ho_g);
+  int* hvq = (int*)(h->srv_host + ho_vq);
+  long long* hqp = (long long*)(h->srv_host + ho_qp);
+  int* hqid = (int*)(h->srv_host + ho_qid);
+  hg[0] = 0; hg[1] = nq;
+  hqp[0] = 0; hqp[1] = nq;
+  IdList ids;
+  for (int q = 0; q < nq; ++q) { ids.v[q] = query_items[q]; hvq[q] = 0; hqid[q] = query_items[q]; }
+  const size_t smem = sizeof(double) * ((size_t)KP * SM_NV + SM_NV) + sb_tile_bytes(KP) +
+                      (sizeof(double) + sizeof(int)) * (size_t)SM_QG * topk + sizeof(int) * (SM_NV + SM_QG * SM_QIDS) + 16;
+  {
+    static size_t attr_smem[64] = {};
+    if (h->cfg.device < 64 && attr_smem[h->cfg.device] < smem) {
+      CK(h, cudaFuncSetAttribute(score_cos_topk_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem[h->cfg.device] = smem;
+    }
+  }
+  gather_rows_ids_kernel<<<nq, 64, 0, st>>>(h->I.F, KP, ids, h->I.perm, h->I.deg, h->I.n, d_qf, nullptr);
+  LAUNCHED(h);
+  score_cos_topk_multi_kernel<<<dim3(gx, 1), SB_THREADS, smem, st>>>(
+      h->I.F, h->I.n_internal, KP, k, d_qf, (const int*)(h->srv_host_dev + ho_g), (const int*)(h->srv_host_dev + ho_vq),
+      (const long long*)(h->srv_host_dev + ho_qp), (const int*)(h->srv_host_dev + ho_qid), 1, h->I.cand_ext, d_mask, d_weight,
+      nullptr, (flags & PIO_ALS_SIM_KEEP_QUERY_ITEMS) ? 1 : 0, topk, d_cand);
+  LAUNCHED(h);
+  topk_merge_kernel<<<1, TK_THREADS, 0, st>>>(d_cand, gx * topk, topk, topk, 0, (int*)(h->srv_host_dev + ho_i),
+                                              (float*)(h->srv_host_dev + ho_s), (int*)(h->srv_host_dev + ho_c), nullptr);
+  LAUNCHED(h);
+  CK(h, cudaStreamSynchronize(st));
+  memcpy(out_items, h->srv_host + ho_i, sizeof(int) * (size_t)topk);
+  memcpy(out_scores, h->srv_host + ho_s, sizeof(float) * (size_t)topk);
+  if (out_count) *out_count = *(int*)(h->srv_host + ho_c);
+  return PIO_ALS_OK;
+}
+}  // namespace pio
+
 // Scoring passes: at most TK_MAXK results per pass; a query asking for more runs further passes, each bounded by the last
 // result of the one before (topk.cuh below_bound).
 int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, const uint8_t* item_mask,
@@ -1700,6 +1858,8 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
   std::lock_guard<std::mutex> lk(h->mu);
   if (!h->U.F || !h->I.F || !h->I.cand_ext) return fail(h, PIO_ALS_ERR_STATE, "no model");
   CK(h, cudaSetDevice(h->cfg.device));
+  if (n <= SB_QB && topk <= TK_MAXK)   // the serving case: one or a few queries
+    return recommend_small(h, users, n, topk, item_mask, item_weight, out_items, out_scores, out_count);
   cudaStream_t st = h->stream;
   const int KP = h->KP;
   Scratch tmp(h);
@@ -1864,6 +2024,9 @@ int pio_als_similar_batch(pio_als_handle* h, const int64_t* q_ptr, const int32_t
   std::lock_guard<std::mutex> lk(h->mu);
   if (!h->I.F || !h->I.cand_ext) return fail(h, PIO_ALS_ERR_STATE, "no model");
   CK(h, cudaSetDevice(h->cfg.device));
+  if (n_queries == 1 && q_ptr[1] - q_ptr[0] >= 1 && q_ptr[1] - q_ptr[0] <= SM_NV && topk <= TK_MAXK)   // the serving case
+    return similar_small(h, q_items + q_ptr[0], (int)(q_ptr[1] - q_ptr[0]), topk, item_mask, item_weight, flags, out_items,
+                         out_scores, out_count);
   Scratch tmp(h);
   uint8_t* d_mask = nullptr;
   double* d_weight = nullptr;
@@ -1874,6 +2037,100 @@ int pio_als_similar_batch(pio_als_handle* h, const int64_t* q_ptr, const int32_t
   if (item_weight) {
     CK(h, tmp.alloc(&d_weight, (size_t)h->I.n));
     CK(h, cudaMemcpyAsync(d_weight, item_weight, sizeof(double) * (size_t)h->I.n, cudaMemcpyHostToDevice, h->stream));
+  }
+  cudaStream_t st = h->stream;
+  const int KP = h->KP, k = h->cfg.rank;
+  const long long total = q_ptr[n_queries] - q_ptr[0];
+  bool fast = n_queries > 1 && total > 0 && total < (1ll << 31);
+  std::vector<int> gvec0, vq, vsrc;
+  if (fast) {
+    // all query item vectors in one gather; which of them own a factor decides the vector list of every query
+    int* d_qid = nullptr;
+    float* d_qf_all = nullptr;
+    uint8_t* d_valid = nullptr;
+    CK(h, tmp.alloc(&d_qid, (size_t)total));
+    CK(h, tmp.alloc(&d_qf_all, (size_t)total * KP));
+    CK(h, tmp.alloc(&d_valid, (size_t)total));
+    CK(h, cudaMemcpyAsync(d_qid, q_items + q_ptr[0], sizeof(int) * total, cudaMemcpyHostToDevice, st));
+    gather_rows_kernel<<<(unsigned)total, 64, 0, st>>>(h->I.F, KP, d_qid, (int)total, h->I.perm, h->I.deg, h->I.n, d_qf_all, d_valid);
+    LAUNCHED(h);
+    std::vector<uint8_t> valid((size_t)total);
+    CK(h, cudaMemcpyAsync(valid.data(), d_valid, (size_t)total, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    const int ngroups = (n_queries + SM_QG - 1) / SM_QG;
+    gvec0.assign((size_t)ngroups + 1, 0);
+    for (int g = 0; g < ngroups && fast; ++g) {
+      gvec0[g] = (int)vsrc.size();
+      for (int j = g * SM_QG; j < (g + 1) * SM_QG && j < n_queries; ++j)
+        for (long long t = q_ptr[j]; t < q_ptr[j + 1]; ++t)
+          if (valid[(size_t)(t - q_ptr[0])]) {
+            vsrc.push_back((int)(t - q_ptr[0]));
+            vq.push_back(j - g * SM_QG);
+          }
+      if ((int)vsrc.size() - gvec0[g] > SM_NV) fast = false;   // a group with too many query vectors: one query at a time
+    }
+    gvec0[ngroups] = (int)vsrc.size();
+    if (fast) {
+      const int nvec = (int)vsrc.size();
+      int *d_gvec0 = nullptr, *d_vq = nullptr, *d_vsrc = nullptr, *d_oi = nullptr, *d_oc = nullptr;
+      long long* d_qptr = nullptr;
+      float *d_qfc = nullptr, *d_os = nullptr;
+      ScoreIdx *d_cand = nullptr, *d_bound = nullptr;
+      std::vector<long long> rel((size_t)n_queries + 1);
+      for (int j = 0; j <= n_queries; ++j) rel[j] = q_ptr[j] - q_ptr[0];
+      CK(h, tmp.alloc(&d_gvec0, gvec0.size()));
+      CK(h, tmp.alloc(&d_vq, (size_t)(nvec > 0 ? nvec : 1)));
+      CK(h, tmp.alloc(&d_vsrc, (size_t)(nvec > 0 ? nvec : 1)));
+      CK(h, tmp.alloc(&d_qptr, rel.size()));
+      CK(h, tmp.alloc(&d_qfc, (size_t)(nvec > 0 ? nvec : 1) * KP));
+      CK(h, cudaMemcpyAsync(d_gvec0, gvec0.data(), sizeof(int) * gvec0.size(), cudaMemcpyHostToDevice, st));
+      CK(h, cudaMemcpyAsync(d_qptr, rel.data(), sizeof(long long) * rel.size(), cudaMemcpyHostToDevice, st));
+      if (nvec > 0) {
+        CK(h, cudaMemcpyAsync(d_vq, vq.data(), sizeof(int) * nvec, cudaMemcpyHostToDevice, st));
+        CK(h, cudaMemcpyAsync(d_vsrc, vsrc.data(), sizeof(int) * nvec, cudaMemcpyHostToDevice, st));
+        copy_rows_kernel<<<nvec, 64, 0, st>>>(d_qf_all, KP, d_vsrc, d_qfc);
+        LAUNCHED(h);
+      }
+      const int pass_max = topk < TK_MAXK ? topk : TK_MAXK;
+      const int ntiles = (h->I.n_internal + SB_THREADS - 1) / SB_THREADS;
+      int gx = (2 * h->sm_count + ngroups - 1) / ngroups;
+      if (gx > (ntiles + 7) / 8) gx = (ntiles + 7) / 8;
+      if (gx < 1) gx = 1;
+      const size_t smem = sizeof(double) * ((size_t)KP * SM_NV + SM_NV) + sb_tile_bytes(KP) +
+                          (sizeof(double) + sizeof(int)) * (size_t)SM_QG * pass_max + sizeof(int) * (SM_NV + SM_QG * SM_QIDS) + 16;
+      {
+        static size_t attr_smem[64] = {};
+        if (h->cfg.device < 64 && attr_smem[h->cfg.device] < smem) {
+          CK(h, cudaFuncSetAttribute(score_cos_topk_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          attr_smem[h->cfg.device] = smem;
+        }
+      }
+      CK(h, tmp.alloc(&d_cand, (size_t)n_queries * gx * pass_max));
+      CK(h, tmp.alloc(&d_oi, (size_t)n_queries * topk));
+      CK(h, tmp.alloc(&d_os, (size_t)n_queries * topk));
+      CK(h, tmp.alloc(&d_oc, (size_t)n_queries));
+      if (topk > TK_MAXK) CK(h, tmp.alloc(&d_bound, (size_t)n_queries));
+      const int keep_query = (flags & PIO_ALS_SIM_KEEP_QUERY_ITEMS) ? 1 : 0;
+      for (int done = 0; done < topk; done += TK_MAXK) {
+        const int pk = topk - done < TK_MAXK ? topk - done : TK_MAXK;
+        for (int g0 = 0; g0 < ngroups; g0 += 32768) {
+          const int ng = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
+          const int qa = g0 * SM_QG;
+          const int nq = n_queries - qa < ng * SM_QG ? n_queries - qa : ng * SM_QG;
+          score_cos_topk_multi_kernel<<<dim3(gx, ng), SB_THREADS, smem, st>>>(
+              h->I.F, h->I.n_internal, KP, k, d_qfc, d_gvec0 + g0, d_vq, d_qptr + qa, d_qid, nq, h->I.cand_ext, d_mask,
+              d_weight, done > 0 ? d_bound + qa : nullptr, keep_query, pk, d_cand + (size_t)qa * gx * pk);
+          LAUNCHED(h);
+        }
+        topk_merge_kernel<<<n_queries, TK_THREADS, 0, st>>>(d_cand, gx * pk, pk, topk, done, d_oi, d_os, d_oc, d_bound);
+        LAUNCHED(h);
+      }
+      CK(h, cudaMemcpyAsync(out_items, d_oi, sizeof(int) * (size_t)n_queries * topk, cudaMemcpyDeviceToHost, st));
+      CK(h, cudaMemcpyAsync(out_scores, d_os, sizeof(float) * (size_t)n_queries * topk, cudaMemcpyDeviceToHost, st));
+      if (out_count) CK(h, cudaMemcpyAsync(out_count, d_oc, sizeof(int) * (size_t)n_queries, cudaMemcpyDeviceToHost, st));
+      CK(h, cudaStreamSynchronize(st));
+      return PIO_ALS_OK;
+    }
   }
   for (int j = 0; j < n_queries; ++j) {
     int32_t cnt = 0;

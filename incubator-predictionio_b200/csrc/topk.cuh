@@ -432,6 +432,171 @@ score_cos_topk_batched_kernel(const float* __restrict__ Y, int n_items, int kp, 
   }
 }
 
+// ---- similarproduct scoring for MANY queries (batchPredict, pio_als_similar_batch) ---------------------------------
+// grid: (GX persistent CTAs striding over 256-item tiles, groups of SM_QG queries).  A staged tile is scored against
+// every query vector of the group (<= SM_NV vectors: xd), the per-query sums go through shared memory (scs[q][item]),
+// then warp q feeds the pool of query q (query items excluded unless keep_query, weights, score > 0, pass bound).
+// Same arithmetic, in the same order, as score_cos_topk_batched_kernel -> bit-identical results.
+//   gvec0[g] .. gvec0[g+1] : vectors of group g in qf ([total vectors][kp], query order inside a query)
+//   vq[v]                  : query (0..SM_QG-1 inside the group) of vector v
+//   qid_ptr / qid          : all query item ids (external) of every query, for the exclusion rule
+constexpr int SM_QG = 8;    // queries per group = warps per CTA
+constexpr int SM_NV = 40;   // query vectors per group held in shared memory
+constexpr int SM_QIDS = 64; // query item ids per query held in shared memory (longer lists are read from global memory)
+
+__global__ void __launch_bounds__(SB_THREADS, 2)
+score_cos_topk_multi_kernel(const float* __restrict__ Y, int n_items, int kp, int k, const float* __restrict__ qf,
+                            const int* __restrict__ gvec0, const int* __restrict__ vq, const long long* __restrict__ qid_ptr,
+                            const int* __restrict__ qid, int n_queries, const int* __restrict__ cand_ext,
+                            const uint8_t* __restrict__ mask, const double* __restrict__ weight,
+                            const ScoreIdx* __restrict__ bound, int keep_query, int topk, ScoreIdx* __restrict__ cand) {
+  extern __shared__ __align__(16) unsigned char sb_smem[];
+  const int row = kp + 4;
+  double* xd = reinterpret_cast<double*>(sb_smem);                          // [kp][SM_NV]
+  double* s1 = xd + (size_t)kp * SM_NV;                                      // [SM_NV]
+  float* tile = reinterpret_cast<float*>(s1 + SM_NV);                       // [SB_THREADS][row]; reused for scs / sext
+  const size_t tile_bytes = sb_tile_bytes(kp);
+  double* hs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tile) + tile_bytes);   // [SM_QG][topk]
+  int* hi = reinterpret_cast<int*>(hs + (size_t)SM_QG * topk);              // [SM_QG][topk]
+  int* svq = hi + (size_t)SM_QG * topk;                                      // [SM_NV]
+  int* sqid = svq + SM_NV;                                                   // [SM_QG][SM_QIDS] excluded ids of each query
+  double* scs = reinterpret_cast<double*>(tile);                            // [SM_QG][SB_THREADS]
+  int* sext = reinterpret_cast<int*>(scs + (size_t)SM_QG * SB_THREADS);     // [SB_THREADS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = blockIdx.y, q0 = grp * SM_QG;
+  const int v0 = gvec0[grp], nv = gvec0[grp + 1] - v0;
+  for (int o = tid; o < kp * SM_NV; o += SB_THREADS) {
+    const int c = o / SM_NV, t = o % SM_NV;
+    xd[o] = (t < nv) ? (double)qf[(size_t)(v0 + t) * kp + c] : 0.0;
+  }
+  for (int t = tid; t < SM_NV; t += SB_THREADS) {
+    double n1 = 0.0;
+    if (t < nv)
+      for (int c = 0; c < k; ++c) {
+        const double a = (double)qf[(size_t)(v0 + t) * kp + c];
+        n1 += a * a;
+      }
+    s1[t] = sqrt(n1);
+    svq[t] = t < nv ? vq[v0 + t] : 0;
+  }
+  // warp w owns the pool of query q0 + w
+  const int myq = q0 + warp;
+  WarpPool wp;
+  wp.thr = 0.0; wp.wid = -1; wp.worst = 0; wp.cnt = 0;
+  ScoreIdx bnd;
+  bnd.s = 0.0;
+  bnd.i = TK_NO_BOUND;
+  if (bound && myq < n_queries) bnd = bound[myq];
+  long long ib = 0, ie = 0;
+  if (myq < n_queries) { ib = qid_ptr[myq]; ie = qid_ptr[myq + 1]; }
+  const bool ids_in_smem = ie - ib <= SM_QIDS;      // the usual case: the exclusion list is read from shared memory
+  if (ids_in_smem)
+    for (int t = lane; t < (int)(ie - ib); t += 32) sqid[warp * SM_QIDS + t] = qid[ib + t];
+  __syncwarp();
+  double* ps = hs + (size_t)warp * topk;
+  int* pi = hi + (size_t)warp * topk;
+  const int ntiles = (n_items + SB_THREADS - 1) / SB_THREADS;
+  const int f4row = kp / 4;
+  for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const int base = tl * SB_THREADS;
+    __syncthreads();
+    for (int o = tid; o < SB_THREADS * f4row; o += SB_THREADS) {
+      const int r = o / f4row, c4 = o % f4row;
+      float* d = tile + (size_t)r * row + c4 * 4;
+      if (base + r < n_items) sb_cp_async16(d, Y + (size_t)(base + r) * kp + c4 * 4);
+      else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    const int i = base + tid;
+    int ext = (i < n_items) ? cand_ext[i] : -1;
+    if (ext >= 0 && mask && mask[ext]) ext = -1;
+    double sc[SM_QG];
+#pragma unroll
+    for (int q = 0; q < SM_QG; ++q) sc[q] = 0.0;
+    if (ext >= 0 && nv > 0) {
+      const float4* yrow = reinterpret_cast<const float4*>(tile + (size_t)tid * row);
+      double n2 = 0.0;
+      for (int c4 = 0; c4 < f4row; ++c4) {
+        const float4 y4 = yrow[c4];
+        const double b0 = (double)y4.x, b1 = (double)y4.y, b2 = (double)y4.z, b3 = (double)y4.w;
+        n2 = fma(b0, b0, n2);
+        n2 = fma(b1, b1, n2);
+        n2 = fma(b2, b2, n2);
+        n2 = fma(b3, b3, n2);
+      }
+      const double s2 = sqrt(n2);
+      for (int g = 0; g < nv; g += SC_G) {
+        double d[SC_G];
+#pragma unroll
+        for (int j = 0; j < SC_G; ++j) d[j] = 0.0;
+        for (int c4 = 0; c4 < f4row; ++c4) {
+          const float4 y4 = yrow[c4];
+          const float ye[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const double yd = (double)ye[e];
+            const double2* xr = reinterpret_cast<const double2*>(xd + (size_t)(c4 * 4 + e) * SM_NV + g);
+#pragma unroll
+            for (int j = 0; j < SC_G; j += 2) {
+              const double2 x2 = xr[j / 2];
+              d[j] = fma(x2.x, yd, d[j]);
+              d[j + 1] = fma(x2.y, yd, d[j + 1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < SC_G; ++j)
+          if (g + j < nv) {
+            const double n1n2 = s1[g + j] * s2;
+            const double term = (n1n2 == 0.0) ? 0.0 : d[j] / n1n2;
+            const int q = svq[g + j];
+#pragma unroll
+            for (int qq = 0; qq < SM_QG; ++qq)
+              if (qq == q) sc[qq] += term;      // vectors of a query are consecutive: the sum runs in query order
+          }
+      }
+      if (weight) {
+        const double w = weight[ext];
+#pragma unroll
+        for (int q = 0; q < SM_QG; ++q) sc[q] = sc[q] * w;
+      }
+    }
+    __syncthreads();   // the staged rows are dead
+#pragma unroll
+    for (int q = 0; q < SM_QG; ++q) scs[q * SB_THREADS + tid] = sc[q];
+    sext[tid] = ext;
+    __syncthreads();
+    if (myq < n_queries) {
+      for (int it = lane; it < SB_THREADS; it += 32) {
+        const int e = sext[it];
+        const double sv = scs[warp * SB_THREADS + it];
+        bool want = e >= 0 && sv > 0.0 && below_bound(bnd, sv, e);
+        if (want && !keep_query) {
+          if (ids_in_smem) {
+            for (int t = 0; t < (int)(ie - ib); ++t)
+              if (sqid[warp * SM_QIDS + t] == e) { want = false; break; }
+          } else {
+            for (long long t = ib; t < ie; ++t)
+              if (qid[t] == e) { want = false; break; }
+          }
+        }
+        wpool_offer(wp, want, sv, e, topk, ps, pi);
+      }
+    }
+  }
+  __syncwarp();
+  if (myq < n_queries) {
+    for (int t = lane; t < topk; t += 32) {
+      ScoreIdx e;
+      e.s = t < wp.cnt ? ps[t] : 0.0;
+      e.i = t < wp.cnt ? pi[t] : -1;
+      cand[((size_t)myq * gridDim.x + blockIdx.x) * topk + t] = e;
+    }
+  }
+}
+
 // (fallback for very large queries) one query = a set of item vectors. qf: [nqv][KP] vectors of the query items that own a factor
 // (query order kept); qid: all nq_all query item ids (external) -- every one of them is excluded
 // from the candidates (ALSAlgorithm.scala:243-245 `!queryList.contains(i)`).

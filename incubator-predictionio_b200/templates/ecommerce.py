@@ -157,7 +157,7 @@ class ECommAlgorithm(P2LAlgorithm):
             raise ValueError("requirement failed: mllibRatings cannot be empty. Please check if your events contain "
                              "valid user and item ID.")
         coo = (np.array(us, np.int32), np.array(its, np.int32), np.array(vs, np.float32), np.array(ts, np.int64))
-        seed = self.ap.seed if self.ap.seed is not None else int.from_bytes(os.urandom(7), "little")
+        seed = sc.agree_seed(self.ap.seed) if hasattr(sc, "agree_seed") else (self.ap.seed or 0)
         kw = dict(rank=self.ap.rank, iterations=self.ap.numIterations, lambda_=self.ap.lambda_, blocks=-1, seed=seed,
                   dedup="keep_last", n_users=userMap.size, n_products=itemMap.size, sc=sc)
         m = ALS.trainImplicit(coo, alpha=1.0, **kw) if self.ap.implicitPrefs else ALS.train(coo, **kw)

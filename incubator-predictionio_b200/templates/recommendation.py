@@ -179,7 +179,7 @@ class ALSAlgorithm(PAlgorithm):
         u = np.fromiter((userStringIntMap(r.user) for r in data.ratings), np.int32, n)
         i = np.fromiter((itemStringIntMap(r.item) for r in data.ratings), np.int32, n)
         v = np.fromiter((r.rating for r in data.ratings), np.float32, n)
-        seed = self.ap.seed if self.ap.seed is not None else int.from_bytes(os.urandom(7), "little")
+        seed = sc.agree_seed(self.ap.seed) if hasattr(sc, "agree_seed") else (self.ap.seed or 0)
         als = ALS()
         als.setUserBlocks(-1).setProductBlocks(-1).setRank(self.ap.rank).setIterations(self.ap.numIterations)
         als.setLambda(self.ap.lambda_).setImplicitPrefs(self.ap.implicitPrefs).setAlpha(1.0).setSeed(seed)

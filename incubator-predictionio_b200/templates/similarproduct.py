@@ -197,7 +197,7 @@ class ALSAlgorithm(P2LAlgorithm):
         if u.size == 0:
             raise ValueError("requirement failed: mllibRatings cannot be empty. Please check if your events contain "
                              "valid user and item ID.")
-        seed = self.ap.seed if self.ap.seed is not None else int.from_bytes(os.urandom(7), "little")
+        seed = sc.agree_seed(self.ap.seed) if hasattr(sc, "agree_seed") else (self.ap.seed or 0)
         m = ALS.trainImplicit((u, i, v), rank=self.ap.rank, iterations=self.ap.numIterations, lambda_=self.ap.lambda_,
                               blocks=-1, alpha=1.0, seed=seed, dedup=self._dedup(), n_users=userMap.size,
                               n_products=itemMap.size, sc=sc)
@@ -240,7 +240,7 @@ class LikeAlgorithm(ALSAlgorithm):
         u, i, v, ts = self._ratings(data, userMap, itemMap)
         if u.size == 0:
             raise ValueError("requirement failed: mllibRatings cannot be empty.")
-        seed = self.ap.seed if self.ap.seed is not None else int.from_bytes(os.urandom(7), "little")
+        seed = sc.agree_seed(self.ap.seed) if hasattr(sc, "agree_seed") else (self.ap.seed or 0)
         m = ALS.trainImplicit((u, i, v, ts), rank=self.ap.rank, iterations=self.ap.numIterations,
                               lambda_=self.ap.lambda_, blocks=-1, alpha=1.0, seed=seed, dedup="keep_last",
                               n_users=userMap.size, n_products=itemMap.size, sc=sc)

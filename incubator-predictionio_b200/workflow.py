@@ -77,6 +77,26 @@ class WorkflowContext:
         dist.broadcast(t, 0)
         return bytes(t.cpu().tolist())
 
+    def broadcast_object(self, obj):
+        """Rank 0's value of `obj` on every rank (single process: obj itself).  Used for everything the ranks of a
+        multi-GPU training must agree on: the engine-instance id, the initial-factor seed, NCCL ids."""
+        if self.world_size == 1:
+            return obj
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        box = [obj if self.world_rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def agree_seed(self, seed: Optional[int]) -> int:
+        """The templates' `ap.seed.getOrElse(System.nanoTime)`: drawn once (rank 0) and shared, so that every rank
+        hash-initialises the same factors."""
+        if seed is None:
+            seed = int.from_bytes(os.urandom(7), "little")
+        return int(self.broadcast_object(int(seed)))
+
     def stop(self):
         self._stopped = True
 
@@ -141,17 +161,25 @@ class EngineInstances:
         return json.loads(p.read_text()) if p.exists() else []
 
     @staticmethod
+    def _store(rows: List[Dict[str, Any]]) -> None:
+        # written whole and renamed into place: a reader (or a crash) never sees a half-written registry
+        p = EngineInstances._path()
+        tmp = p.with_name(p.name + f".tmp{os.getpid()}")
+        tmp.write_text(json.dumps(rows, indent=1))
+        os.replace(tmp, p)
+
+    @staticmethod
     def insert(i: EngineInstance) -> str:
         rows = EngineInstances._load()
         rows.append(dataclasses.asdict(i))
-        EngineInstances._path().write_text(json.dumps(rows, indent=1))
+        EngineInstances._store(rows)
         return i.id
 
     @staticmethod
     def update(i: EngineInstance) -> None:
         rows = [r for r in EngineInstances._load() if r["id"] != i.id]
         rows.append(dataclasses.asdict(i))
-        EngineInstances._path().write_text(json.dumps(rows, indent=1))
+        EngineInstances._store(rows)
 
     @staticmethod
     def get(id: str) -> Optional[EngineInstance]:
@@ -187,10 +215,12 @@ class CoreWorkflow:
         sc = WorkflowContext(params.batch, env or {}, mode="Training", sparkConf=engineInstance.sparkConf)
         try:
             models = engine.train(sc, engineParams, engineInstance.id, params)
-            Models.insert(engineInstance.id, models)
-            engineInstance.status = "COMPLETED"
-            engineInstance.endTime = _dt.datetime.now(_dt.timezone.utc).isoformat()
-            EngineInstances.update(engineInstance)
+            if sc.world_rank == 0:   # under torchrun every rank trains (one GPU each); rank 0 alone owns the metadata
+                Models.insert(engineInstance.id, models)
+                engineInstance.status = "COMPLETED"
+                engineInstance.endTime = _dt.datetime.now(_dt.timezone.utc).isoformat()
+                EngineInstances.update(engineInstance)
+            sc.broadcast_object(True)   # the other ranks leave only after the instance is registered
             logger.info("Training completed successfully.")
             return models
         except (StopAfterReadInterruption, StopAfterPrepareInterruption) as e:
@@ -241,11 +271,14 @@ class CreateWorkflow:
             raise SystemExit("evaluation workflow: use Engine.eval from Python (out of scope of this runner)")
         engineParams = engine.jValueToEngineParams(variantJson)
         now = _dt.datetime.now(_dt.timezone.utc).isoformat()
-        inst = EngineInstance(id=uuid.uuid4().hex, status="INIT", startTime=now, endTime=now,
+        boot = WorkflowContext(wfc.batch, pioEnv, mode="Training", sparkConf=sparkConf)
+        inst_id, now = boot.broadcast_object((uuid.uuid4().hex, now))   # one engine instance for all ranks of the job
+        inst = EngineInstance(id=inst_id, status="INIT", startTime=now, endTime=now,
                               engineId=wfc.engine_id, engineVersion=wfc.engine_version,
                               engineVariant=variantJson.get("id", "default"), engineFactory=engineFactory,
                               batch=wfc.batch, env=pioEnv, sparkConf=sparkConf, variantJson=variantJson)
-        EngineInstances.insert(inst)
+        if boot.world_rank == 0:
+            EngineInstances.insert(inst)
         CoreWorkflow.runTrain(engine, engineParams, inst, env=pioEnv,
                               params=WorkflowParams(batch=wfc.batch, verbose=wfc.verbosity,
                                                     skipSanityCheck=wfc.skip_sanity_check,

@@ -332,6 +332,13 @@ def test_scoring_weights_query_items_large_topk_and_batch(native, oracle):
                 for j, q in enumerate(queries):
                     oi, os_, oc = oracle.similar(itf, ih, np.array(q, np.int32), topk, mk, wt, keep)
                     assert bc[j] == oc and np.array_equal(bi[j], oi) and np.array_equal(bs[j], os_)
+    # a larger batch (several query groups, 1..6 items per query, unknown and factor-less items mixed in)
+    many = [list(rng.choice(np.concatenate([have[:400], np.flatnonzero(ih == 0)[:3]]), rng.integers(1, 7), replace=False))
+            for _ in range(61)]
+    bi, bs, bc = m.similar_batch(many, 20, mask, w)
+    for j, q in enumerate(many):
+        oi, os_, oc = oracle.similar(itf, ih, np.array(q, np.int32), 20, mask, w, False)
+        assert bc[j] == oc and np.array_equal(bi[j], oi) and np.array_equal(bs[j], os_), j
     # keep_query really changes the answer: the query item itself is the most similar item
     gi, _, _ = m.similar(np.array([int(have[3])], np.int32), 5, keep_query_items=True)
     assert gi[0] == have[3]

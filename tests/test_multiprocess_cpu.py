@@ -58,6 +58,28 @@ WORKER = textwrap.dedent("""
     assert sum(s[0] for s in sizes) == 3000 and sum(s[1] for s in sizes) == 50000
     allrows = sorted(x for s in sizes for x in s[2])
     assert allrows == list(range(3000))
+    # what a multi-GPU training job must agree on and write exactly once: instance id, seed, registry, models
+    seeds = [None] * world
+    dist.all_gather_object(seeds, sc.agree_seed(None))
+    assert len(set(seeds)) == 1, "ranks drew different initial-factor seeds"
+    assert sc.agree_seed(7) == 7
+    os.environ["PIO_MODELDATA_DIR"] = {md!r}
+    inst_id = sc.broadcast_object("inst-" + os.urandom(4).hex())
+    inst = workflow.EngineInstance(id=inst_id, status="INIT", startTime="t", endTime="t", engineId="e", engineVersion="1",
+                                   engineVariant="default", engineFactory="f", batch="", env={{}}, sparkConf={{}},
+                                   variantJson={{}})
+    if rank == 0:
+        workflow.EngineInstances.insert(inst)
+    dist.barrier()
+    got = workflow.EngineInstances.get(inst_id)
+    assert got is not None and got.id == inst_id
+    assert len(workflow.EngineInstances._load()) == 1, "the registry must hold ONE record for the job"
+    from pio_b200 import controller
+    class _Algo(controller.P2LAlgorithm):
+        pass
+    eng = controller.Engine.__new__(controller.Engine)
+    out = eng.makeSerializableModels(sc, inst_id, [None], [_Algo()], [{{"w": rank}}])
+    assert (out == [{{"w": 0}}]) if rank == 0 else (out == [controller.Unit]), "only rank 0 persists models"
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")
@@ -66,7 +88,7 @@ WORKER = textwrap.dedent("""
 
 def test_two_process_gloo_agreement(tmp_path):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=str(ROOT)))
+    script.write_text(WORKER.format(root=str(ROOT), md=str(tmp_path / "modeldata")))
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
