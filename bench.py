@@ -357,6 +357,34 @@ def topk_bench(native, o, cores, m, nu, ni, k, uf, itf, uh, ih, peaks, dev):
         mm.close()
     except Exception as e:
         out["similar_c4"] = {"error": repr(e)}
+    # classification template (A11, BASELINE.json configs[4]): MLlib multinomial NaiveBayes on 10 M labelled points x 3 features
+    try:
+        n_nb = 10_000_000
+        y = rng.integers(0, 4, n_nb).astype(np.int32)
+        x = rng.integers(0, 10, (n_nb, 3)).astype(np.float32)
+        native.nb_train(y[:1000], x[:1000], 4, 1.0, device=dev)
+        t0 = time.perf_counter()
+        pi, theta = native.nb_train(y, x, 4, 1.0, device=dev)
+        t_tr = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        lab = native.nb_predict(x, pi, theta, device=dev)
+        t_pr = time.perf_counter() - t0
+        ns3 = 1_000_000
+        t0 = time.perf_counter()
+        opi, oth = o.nb_train(y[:ns3], x[:ns3], 4, 1.0)
+        cpu_tr = time.perf_counter() - t0
+        fpi, fth = o.nb_train(y, x, 4, 1.0)
+        out["naive_bayes_c5"] = {
+            "what": f"pio_nb_train / pio_nb_predict: {n_nb} labelled points x 3 features, 4 classes, host buffers (H2D inside)",
+            "train_rows_per_s": n_nb / t_tr, "train_seconds": t_tr, "predict_rows_per_s": n_nb / t_pr,
+            "predict_seconds": t_pr, "bytes": int(x.nbytes + y.nbytes),
+            "train_gbs_incl_h2d": (x.nbytes + y.nbytes) / t_tr / 1e9,
+            "bit_exact_vs_oracle": bool(np.array_equal(pi, fpi) and np.array_equal(theta, fth) and
+                                        np.array_equal(lab[:ns3], o.nb_predict(x[:ns3], fpi, fth))),
+            "cpu_baseline": {"value": ns3 / cpu_tr, "unit": "rows/s (train)", "cores": 1, "kind": "port",
+                             "sample": f"{ns3} of the same rows, single-threaded restatement of NaiveBayes.train"}}
+    except Exception as e:
+        out["naive_bayes_c5"] = {"error": repr(e)}
     # single-query latency
     lat = []
     for q in range(20):

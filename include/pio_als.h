@@ -206,6 +206,18 @@ PIO_API int pio_als_synth_ratings_device(int device, int32_t n_users, int32_t n_
                                          int64_t seed, int implicit, int64_t start,
                                          int32_t* d_user, int32_t* d_item, float* d_rating);
 
+/* String ids -> dense indices on the GPU: BiMap.stringInt(keys) (data/src/main/scala/org/apache/predictionio/data/storage/
+ * BiMap.scala:116-128: keys.distinct.collect -> index) as the templates apply it to the user and item id columns before
+ * building MLlibRating (examples/scala-parallel-recommendation/blacklist-items/src/main/scala/ALSAlgorithm.scala:59-65).
+ * The n strings are passed as one byte buffer plus n + 1 offsets (offsets[0] == 0); HOST buffers.
+ *   out_index[e]   : dense index of string e; indices are handed out in order of first occurrence (the reference's
+ *                    collect order is unspecified: compare by string id)
+ *   out_first[id]  : nullable, capacity n: position of the first occurrence of the string with index id (the inverse map)
+ *   out_n_unique   : number of distinct strings
+ * Hash + radix sort + byte-wise verification: two different strings never share an index. */
+PIO_API int pio_ids_encode(int device, const uint8_t* bytes, const int64_t* offsets, int64_t n, int32_t* out_index,
+                           int64_t* out_first, int32_t* out_n_unique);
+
 /* MLlib multinomial NaiveBayes (classification template). HOST buffers.
  * label: class index 0..n_class-1; x: n x n_feat, non-negative. pi: n_class, theta: n_class x n_feat
  * (fp64 log-probabilities, as MLlib's NaiveBayesModel.pi/theta). */

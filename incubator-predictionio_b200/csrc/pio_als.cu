@@ -41,6 +41,7 @@
 #undef TC_NRAW
 #include "sort_scan.cuh"
 #include "topk.cuh"
+#include "ids_encode.cuh"
 
 namespace pio {
 
@@ -2422,6 +2423,72 @@ int pio_als_synth_ratings_device(int device, int32_t n_users, int32_t n_items, i
   synth_kernel<<<nblk(nnz, 256), 256>>>(n_users, n_items, nnz, (uint64_t)seed, implicit, start, d_user, d_item, d_rating);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "synth kernel: %s", cudaGetErrorString(e));
+  return PIO_ALS_OK;
+}
+
+// ---- string ids -> dense indices (BiMap.stringInt) ---------------------------------------------------------------------
+int pio_ids_encode(int device, const uint8_t* bytes, const int64_t* offsets, int64_t n, int32_t* out_index,
+                   int64_t* out_first, int32_t* out_n_unique) {
+  if (n < 0 || !offsets || !out_index || !out_n_unique || (n > 0 && !bytes && offsets[n] > offsets[0]))
+    return fail(nullptr, PIO_ALS_ERR_ARG, "bad pio_ids_encode arguments");
+  *out_n_unique = 0;
+  if (n == 0) return PIO_ALS_OK;
+  if (n >= (1ll << 32)) return fail(nullptr, PIO_ALS_ERR_ARG, "n must be < 2^32");
+  if (offsets[0] != 0) return fail(nullptr, PIO_ALS_ERR_ARG, "offsets[0] must be 0");
+  CK0(cudaSetDevice(device));
+  const size_t nb = (size_t)offsets[n];
+  uint8_t* d_bytes = nullptr;
+  long long *d_off = nullptr, *d_first = nullptr;
+  uint64_t *ka = nullptr, *kb = nullptr;
+  uint32_t *va = nullptr, *vb = nullptr, *f1 = nullptr, *f2 = nullptr, *run_start = nullptr, *head = nullptr, *ishead = nullptr,
+           *firstpos = nullptr, *isfirst = nullptr;
+  int* d_out = nullptr;
+  std::vector<void*> owned;
+  auto A = [&](void** p, size_t bytes_) -> cudaError_t {
+    cudaError_t e = cudaMalloc(p, bytes_ ? bytes_ : 1);
+    if (e == cudaSuccess) owned.push_back(*p);
+    return e;
+  };
+  struct Guard { std::vector<void*>& v; ~Guard() { for (void* q : v) cudaFree(q); } } guard{owned};
+  CK0(A((void**)&d_bytes, nb));
+  CK0(A((void**)&d_off, sizeof(long long) * (n + 1)));
+  CK0(A((void**)&ka, 8 * (size_t)n)); CK0(A((void**)&kb, 8 * (size_t)n));
+  CK0(A((void**)&va, 4 * (size_t)n)); CK0(A((void**)&vb, 4 * (size_t)n));
+  CK0(A((void**)&f1, 4 * (size_t)n)); CK0(A((void**)&f2, 4 * (size_t)n));
+  CK0(A((void**)&run_start, 4 * (size_t)n)); CK0(A((void**)&head, 4 * (size_t)n)); CK0(A((void**)&ishead, 4 * (size_t)n));
+  CK0(A((void**)&firstpos, 4 * (size_t)n)); CK0(A((void**)&isfirst, 4 * (size_t)n));
+  CK0(A((void**)&d_out, 4 * (size_t)n));
+  CK0(A((void**)&d_first, 8 * (size_t)n));
+  cudaStream_t st = 0;
+  CK0(cudaMemcpyAsync(d_bytes, bytes, nb, cudaMemcpyHostToDevice, st));
+  CK0(cudaMemcpyAsync(d_off, offsets, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
+  uint64_t mask = ~0ull;
+  if (const char* hb = getenv("PIO_IDS_HASH_BITS")) {   // tests: a short hash makes different strings collide on purpose
+    const int b = atoi(hb);
+    if (b >= 1 && b < 64) mask = (1ull << b) - 1ull;
+  }
+  ids_hash_kernel<<<nblk(n, 256), 256, 0, st>>>(d_bytes, d_off, n, ka, va, mask);
+  bool in_b = false;
+  CK0(radix_sort_pairs(ka, va, kb, vb, (size_t)n, 64, st, &in_b, nullptr));
+  const uint64_t* ks = in_b ? kb : ka;
+  const uint32_t* vs = in_b ? vb : va;
+  ids_runflag_kernel<<<nblk(n, 256), 256, 0, st>>>(ks, n, f1);
+  CK0(scan_exclusive_u32(f1, f1, (size_t)n, st, nullptr));                 // f1 = run ids
+  ids_runstart_kernel<<<nblk(n, 256), 256, 0, st>>>(ks, f1, n, run_start);
+  ids_head_kernel<<<nblk(n, 256), 256, 0, st>>>(ks, vs, f1, run_start, d_bytes, d_off, n, head, ishead);
+  uint32_t last_flag = 0, last_ex = 0;
+  CK0(cudaMemcpyAsync(&last_flag, ishead + n - 1, 4, cudaMemcpyDeviceToHost, st));
+  CK0(scan_exclusive_u32(ishead, f2, (size_t)n, st, nullptr));             // f2 = group ids (valid at heads)
+  CK0(cudaMemcpyAsync(&last_ex, f2 + n - 1, 4, cudaMemcpyDeviceToHost, st));
+  CK0(cudaMemsetAsync(isfirst, 0, 4 * (size_t)n, st));
+  ids_firstpos_kernel<<<nblk(n, 256), 256, 0, st>>>(vs, ishead, f2, n, firstpos, isfirst);
+  CK0(scan_exclusive_u32(isfirst, isfirst, (size_t)n, st, nullptr));       // ids by first occurrence
+  ids_assign_kernel<<<nblk(n, 256), 256, 0, st>>>(vs, head, isfirst, n, d_out, out_first ? d_first : nullptr);
+  CK0(cudaMemcpyAsync(out_index, d_out, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK0(cudaStreamSynchronize(st));
+  const int64_t nuniq = (int64_t)last_ex + last_flag;
+  if (out_first) CK0(cudaMemcpy(out_first, d_first, 8 * (size_t)nuniq, cudaMemcpyDeviceToHost));
+  *out_n_unique = (int32_t)nuniq;
   return PIO_ALS_OK;
 }
 

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "pio_als_set_ratings_coo_sharded_device",
     "pio_als_set_init", "pio_als_run", "pio_als_get_factors", "pio_als_train", "pio_als_recommend",
     "pio_als_similar", "pio_als_similar_batch", "pio_als_model_import", "pio_als_save", "pio_als_load", "pio_als_get_stats", "pio_als_get_phase_ms",
-    "pio_als_synth_ratings_device", "pio_nb_train", "pio_nb_predict",
+    "pio_als_synth_ratings_device", "pio_nb_train", "pio_nb_predict", "pio_ids_encode",
 ]
 
 
@@ -335,6 +335,30 @@ def synth_ratings_device(device, n_users, n_items, nnz, seed, implicit, start, d
                                             C.c_void_p(d_user), C.c_void_p(d_item), C.c_void_p(d_rating))
     if rc != 0:
         raise NativeError(rc, lib().pio_als_last_error(None).decode())
+
+
+def ids_encode(strings, device=0):
+    """BiMap.stringInt on the GPU: (index per string int32[n], first-occurrence position per distinct id int64[n_unique]).
+    `strings`: a sequence of str / bytes, or a (bytes_buffer uint8[], offsets int64[n+1]) pair."""
+    if isinstance(strings, tuple):
+        buf, off = strings
+        buf = np.ascontiguousarray(buf, np.uint8)
+        off = np.ascontiguousarray(off, np.int64)
+    else:
+        enc = [s if isinstance(s, (bytes, bytearray)) else str(s).encode("utf-8") for s in strings]
+        off = np.zeros(len(enc) + 1, np.int64)
+        if enc:
+            off[1:] = np.cumsum([len(b) for b in enc])
+        buf = np.frombuffer(b"".join(enc), np.uint8) if enc else np.zeros(0, np.uint8)
+    n = off.shape[0] - 1
+    idx = np.empty(n, np.int32)
+    first = np.empty(max(n, 1), np.int64)
+    nu = C.c_int32(0)
+    rc = lib().pio_ids_encode(C.c_int(device), _ptr(buf, C.c_uint8) if buf.size else None, _ptr(off, C.c_int64),
+                              C.c_int64(n), _ptr(idx, C.c_int32), _ptr(first, C.c_int64), C.byref(nu))
+    if rc != 0:
+        raise NativeError(rc, lib().pio_als_last_error(None).decode())
+    return idx, first[:nu.value]
 
 
 def nb_train(label, x, n_class, lam, device=0):

@@ -450,3 +450,27 @@ def test_naive_bayes_parity(native, oracle):
     opi, otheta = oracle.nb_train(y, x, 4, 1.0)
     assert np.array_equal(pi, opi) and np.array_equal(theta, otheta)
     assert np.array_equal(native.nb_predict(x, pi, theta), oracle.nb_predict(x, opi, otheta))
+
+
+@pytest.mark.parametrize("hash_bits", [None, "6"])
+def test_ids_encode_matches_bimap_stringint(native, monkeypatch, hash_bits):
+    """pio_ids_encode == BiMap.stringInt (storage.py restatement of BiMap.scala:116-128, first-occurrence order): same index
+    for every event, same inverse map; empty strings, unicode, shared prefixes and a forced 64-bit hash collision path
+    (ids_head_kernel's byte comparison) are covered by construction."""
+    from pio_b200.storage import BiMap
+    monkeypatch.delenv("PIO_IDS_HASH_BITS", raising=False)
+    if hash_bits:       # 6-bit hashes: hundreds of different strings per hash value, groups interleaved inside every run
+        monkeypatch.setenv("PIO_IDS_HASH_BITS", hash_bits)
+    rng = np.random.default_rng(3)
+    pool = [f"u{int(x)}" for x in rng.integers(0, 5000, 4000)] + ["", "\u00fcser-\u4e2d", "u1", "u10", "u100", "a" * 300]
+    keys = [pool[int(j)] for j in rng.integers(0, len(pool), 200_000 if not hash_bits else 20_000)]
+    idx, first = native.ids_encode(keys)
+    bm = BiMap.stringInt(keys)
+    want = np.array([bm(k) for k in keys], np.int32)
+    assert np.array_equal(idx, want)
+    assert first.shape[0] == bm.size and all(bm(keys[int(p)]) == j for j, p in enumerate(first))
+    # degenerate inputs
+    i0, f0 = native.ids_encode([])
+    assert i0.shape == (0,) and f0.shape == (0,)
+    i1, f1 = native.ids_encode(["x"] * 1000)
+    assert (i1 == 0).all() and f1.tolist() == [0]
