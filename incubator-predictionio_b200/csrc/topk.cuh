@@ -101,56 +101,6 @@ __device__ __forceinline__ void sb_cp_async16(void* smem_dst, const void* gsrc) 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
 }
 
-// A top-k pool in shared memory shared by the whole CTA: unsorted (score, id) entries, the index / score of its worst
-// entry and a spin lock.  Called by all 32 lanes of a warp (want = this lane has a candidate).  The unlocked pre-check
-// is conservative (thr only rises; ties go on to the locked re-check), so the final pool holds exactly the best topk
-// under better(): higher score first, smaller external id on equal scores.
-__device__ __forceinline__ void pool_offer(bool want, double s, int ext, int topk, double* hs, int* hi, double* thr,
-                                           int* cnt, int* worst, int* lock) {
-  const int lane = threadIdx.x & 31;
-  if (want) {
-    const int c = *reinterpret_cast<volatile int*>(cnt);
-    if (c >= topk) want = s >= *reinterpret_cast<volatile double*>(thr);
-  }
-  unsigned m = __ballot_sync(0xffffffffu, want);
-  while (m) {
-    const int leader = __ffs(m) - 1;
-    m &= m - 1;
-    if (lane == leader) {
-      while (atomicCAS(lock, 0, 1) != 0) {}
-      __threadfence_block();
-      volatile double* ps = hs;
-      volatile int* pi = hi;
-      int c = *reinterpret_cast<volatile int*>(cnt);
-      bool changed = false;
-      if (c < topk) {
-        ps[c] = s;
-        pi[c] = ext;
-        ++c;
-        *reinterpret_cast<volatile int*>(cnt) = c;
-        changed = c == topk;
-      } else {
-        const int w = *reinterpret_cast<volatile int*>(worst);
-        if (better(s, ext, ps[w], pi[w])) {
-          ps[w] = s;
-          pi[w] = ext;
-          changed = true;
-        }
-      }
-      if (changed) {   // the pool is full: find its new worst entry
-        int w = 0;
-        for (int t = 1; t < topk; ++t)
-          if (better(ps[w], pi[w], ps[t], pi[t])) w = t;
-        *reinterpret_cast<volatile int*>(worst) = w;
-        *reinterpret_cast<volatile double*>(thr) = ps[w];
-      }
-      __threadfence_block();
-      atomicExch(lock, 0);
-    }
-    __syncwarp();
-  }
-}
-
 // A top-k pool owned by ONE warp (entries in shared memory, bookkeeping in warp-uniform registers): no lock, no atomics.
 // All 32 lanes call; candidates are taken in lane order.  The worst entry is found cooperatively (each lane scans the
 // entries lane, lane+32, ..., then a butterfly reduction), so an insertion costs ~100 cycles instead of a serial scan.
@@ -646,49 +596,59 @@ score_cos_topk_kernel(const float* __restrict__ Y, int n_items, int kp, int k,
 }
 
 // grid: n_queries. Merges n_cand unsorted candidates per query (i = -1: empty) -> final topk, best first.
-// The candidates are offered to one shared-memory pool (almost all are rejected by the threshold pre-check once it is
-// full); the survivors are ordered by rank counting (ids are distinct, so better() is a total order).
+// Lock-free: every warp folds a strided share of the candidates into its own pool (wpool_offer: almost everything is
+// rejected by the threshold once the pool is full), then the <= 8 x topk survivors are ordered by rank counting (ids are
+// distinct, so better() is a total order).  A single-query call (serving latency) no longer serialises on a lock.
 __global__ void __launch_bounds__(TK_THREADS)
 topk_merge_kernel(const ScoreIdx* __restrict__ cand, int n_cand, int topk, int out_stride, int out_off,
                   int* __restrict__ out_items, float* __restrict__ out_scores, int* __restrict__ out_count,
                   ScoreIdx* __restrict__ bound_out) {
-  __shared__ double hs[TK_MAXK];
-  __shared__ int hi[TK_MAXK];
-  __shared__ double hthr;
-  __shared__ int hcnt, hworst, hlock;
+  constexpr int NW = TK_THREADS / 32;
+  __shared__ double hs[NW * TK_MAXK];
+  __shared__ int hi[NW * TK_MAXK];
+  __shared__ int wcnt[NW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const ScoreIdx* c = cand + (size_t)blockIdx.x * n_cand;
-  if (threadIdx.x == 0) {
-    hcnt = 0;
-    hworst = 0;
-    hlock = 0;
-    hthr = 0.0;
-  }
-  __syncthreads();
-  for (int base = 0; base < n_cand; base += TK_THREADS) {
-    const int o = base + threadIdx.x;
+  WarpPool wp;
+  wp.thr = 0.0; wp.wid = -1; wp.worst = 0; wp.cnt = 0;
+  double* ps = hs + warp * topk;
+  int* pi = hi + warp * topk;
+  for (int base = warp * 32; base < n_cand; base += TK_THREADS) {
+    const int o = base + lane;
     ScoreIdx e;
     e.s = 0.0;
     e.i = -1;
     if (o < n_cand) e = c[o];
-    pool_offer(e.i >= 0, e.s, e.i, topk, hs, hi, &hthr, &hcnt, &hworst, &hlock);
+    wpool_offer(wp, e.i >= 0, e.s, e.i, topk, ps, pi);
   }
+  if (lane == 0) wcnt[warp] = wp.cnt;
   __syncthreads();
-  const int cnt = hcnt;
+  int total = 0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) total += wcnt[w];
+  const int cnt = total < topk ? total : topk;
   int* oi = out_items + (size_t)blockIdx.x * out_stride + out_off;
   float* os = out_scores + (size_t)blockIdx.x * out_stride + out_off;
-  for (int t = threadIdx.x; t < topk; t += TK_THREADS) {
+  for (int t = threadIdx.x; t < topk; t += TK_THREADS)
     if (t >= cnt) {   // fewer candidates than topk: the tail stays empty
       oi[t] = -1;
       os[t] = 0.f;
     }
-    if (t < cnt) {
-      int rank = 0;
-      for (int u = 0; u < cnt; ++u) rank += (u != t) && better(hs[u], hi[u], hs[t], hi[t]);
-      oi[rank] = hi[t];
-      os[rank] = (float)hs[t];
+  // rank of every survivor among all survivors
+  for (int t = threadIdx.x; t < NW * topk; t += TK_THREADS) {
+    const int w = t / topk, j = t % topk;
+    if (j >= wcnt[w]) continue;
+    const double s = hs[t];
+    const int id = hi[t];
+    int rank = 0;
+    for (int w2 = 0; w2 < NW; ++w2)
+      for (int u = 0; u < wcnt[w2]; ++u) rank += better(hs[w2 * topk + u], hi[w2 * topk + u], s, id) ? 1 : 0;
+    if (rank < topk) {
+      oi[rank] = id;
+      os[rank] = (float)s;
       if (bound_out && rank == topk - 1) {   // the last result of a full pass bounds the next pass
-        bound_out[blockIdx.x].s = hs[t];
-        bound_out[blockIdx.x].i = hi[t];
+        bound_out[blockIdx.x].s = s;
+        bound_out[blockIdx.x].i = id;
       }
     }
   }
