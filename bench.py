@@ -586,8 +586,7 @@ def main():
     kernel_names = {"fp32": "als_solve_kernel (gather + FP32 Gramian + warp Cholesky)",
                     "tcgen05": "tc::als_solve_tc_kernel (tcgen05 split-TF32 Gramian + warp Cholesky)",
                     "mma": "mm::als_solve_mma_kernel (one warp per row: mma.sync 3xTF32 Gramian + warp Cholesky)",
-                    "pair": "pr::als_solve_pair_kernel (two rows per warp: mma.sync 3xTF32 Gramian + lockstep Cholesky)",
-                    "duo": "duo::als_solve_duo_kernel (two warps per row: mma.sync 3xTF32 Gramian + lockstep Cholesky)"}
+                    "pair": "pr::als_solve_pair_kernel (two rows per warp: mma.sync 3xTF32 Gramian + lockstep Cholesky)"}
     fp32_peak = peaks["fp32"]
     tf32_peak = bf16_peak / 2.0
     split_peak = tf32_peak / 3.0   # an fp32-class product costs three TF32 MMAs (hi*hi + lo*hi + hi*lo)

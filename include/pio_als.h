@@ -146,7 +146,7 @@ PIO_API int pio_als_run(pio_als_handle* h, int n_iters);
 /* Device-time breakdown of the last pio_als_run (CUDA events on the handle's stream), for bench.py's roofline:
  * out[0] item half-step solve kernels (ms, summed over the run), out[1] user half-step solve kernels, out[2] YtY
  * kernels, out[3] all-gathers, out[4]/out[5] = solve kernel of the item / user side (0 FP32 CUDA-core kernel, 1 tcgen05
- * kernel, 2 round-1 warp-level mma.sync kernel, 3 pair kernel, 4 duo kernel), out[6] iterations of that run, out[7] reserved.  No reference counterpart (Spark's stage timings,
+ * kernel, 2 warp-level mma.sync kernel), out[6] iterations of that run, out[7] reserved.  No reference counterpart (Spark's stage timings,
  * core/.../workflow/CoreWorkflow.scala:74-81, are the nearest thing). */
 PIO_API int pio_als_get_phase_ms(pio_als_handle* h, double out[8]);
 

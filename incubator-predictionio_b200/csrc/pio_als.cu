@@ -23,7 +23,6 @@
 #include "als_kernels.cuh"
 #include "als_mma_kernel.cuh"
 #include "als_pair_kernel.cuh"
-#include "als_duo_kernel.cuh"
 // the tcgen05 half-step kernel; the header is parametrised by the role partition of its sixteen warps.  Measured at C2:
 // 2 gather + 5 converter warps + 2 solve teams (below) beats 1 + 2 + 3 teams on long rows AND on short rows (user side
 // 38 ms vs 86 ms: two converter warps cannot feed the MMAs), so only this partition is instantiated.
@@ -423,7 +422,6 @@ struct pio_als_handle {
   bool use_pair = true;       // PIO_ALS_MMA=1: round-1 one-warp-per-row mma.sync kernel instead of the pair kernel
   int pair_seg_t = PAIR_SEG_T, pair_part = PAIR_PART;   // PIO_ALS_SEG_T / PIO_ALS_PART
   int pair_warps = 4;         // PIO_ALS_PAIR_WARPS: warps per CTA of the pair kernel (1, 2, 4, 6 or 12)
-  bool use_duo = true;        // PIO_ALS_DUO=0: pair kernel (one warp per row) instead of the duo kernel (two warps per row)
   // half-step pipeline (pair-kernel sides): long rows (parts + finish) run on `aux` next to the whole rows on `stream`;
   // the destination rows are cut into n_pieces local ranges and the all-gather of a finished range runs on `comm_st`
   // while the next range is solved (world_size > 1)
@@ -1034,19 +1032,14 @@ static cudaError_t launch_tc(pio_als_handle* h, Side& dst, const SolveParams& p,
   return e;
 }
 
-// WARPS > 0: pair kernel with that many warps per CTA; WARPS == 0: duo kernel (als_duo_kernel.cuh: two warps per row,
-// four rows per worker round, two workers per CTA).
 template <int WARPS>
 static cudaError_t launch_pair_w(pio_als_handle* h, Side& dst, const SolveParams& p0, bool imp) {
-  constexpr bool DUO = WARPS == 0;
-  constexpr int PW = DUO ? 1 : WARPS;                   // a valid instantiation index for the pair kernel
   cudaError_t e = cudaSuccess;
   static bool attr_set[64] = {};
-  const size_t smem = DUO ? duo::SMEM_BYTES : pr::smem_bytes(PW), fsmem = pr::smem_bytes(1);
-  const void* sk_t = DUO ? (const void*)duo::als_solve_duo_kernel<true> : (const void*)pr::als_solve_pair_kernel<true, PW>;
-  const void* sk_f = DUO ? (const void*)duo::als_solve_duo_kernel<false> : (const void*)pr::als_solve_pair_kernel<false, PW>;
+  const size_t smem = pr::smem_bytes(WARPS), fsmem = pr::smem_bytes(1);
   if (h->cfg.device < 64 && !attr_set[h->cfg.device]) {
-    struct { const void* f; size_t sm; } ks[4] = {{sk_t, smem}, {sk_f, smem},
+    struct { const void* f; size_t sm; } ks[4] = {{(const void*)pr::als_solve_pair_kernel<true, WARPS>, smem},
+                                                 {(const void*)pr::als_solve_pair_kernel<false, WARPS>, smem},
                                                  {(const void*)pr::als_finish_pair_kernel<true>, fsmem},
                                                  {(const void*)pr::als_finish_pair_kernel<false>, fsmem}};
     for (auto& kf : ks) {
@@ -1055,17 +1048,13 @@ static cudaError_t launch_pair_w(pio_als_handle* h, Side& dst, const SolveParams
     }
     attr_set[h->cfg.device] = true;
   }
-  const int threads = DUO ? 64 * duo::WORKERS : 32 * PW;
-  const int max_ctas = DUO ? 3 * h->sm_count : (12 / PW) * h->sm_count;
+  const int max_ctas = (12 / WARPS) * h->sm_count;
   auto grid_for = [&](int items) {
-    const int per_cta = DUO ? duo::ROWS_PER_ROUND * duo::WORKERS : 2 * PW;
-    const int g = (items + per_cta - 1) / per_cta;
+    const int npairs = (items + 1) / 2;
+    const int g = (npairs + WARPS - 1) / WARPS;
     return g < max_ctas ? g : max_ctas;
   };
-  auto launch_sk = [&](const SolveParams& q, int items, cudaStream_t s_) {
-    void* args[2] = {(void*)&q, (void*)&items};
-    return cudaLaunchKernel(imp ? sk_t : sk_f, dim3(grid_for(items)), dim3(threads), args, smem, s_);
-  };
+  auto sk = imp ? pr::als_solve_pair_kernel<true, WARPS> : pr::als_solve_pair_kernel<false, WARPS>;
   cudaEventRecord(h->ev_start, h->stream);
   if (dst.n_heavy > 0) {
     // long rows on the auxiliary stream: parts, then the finish kernel.  Launched first: the kernels are persistent
@@ -1083,9 +1072,10 @@ static cudaError_t launch_pair_w(pio_als_handle* h, Side& dst, const SolveParams
     pp.n_items = dst.n_parts;
     pp.row_begin = 0;
     pp.row_end = dst.n_heavy;
-    if ((e = launch_sk(pp, dst.n_parts, h->aux)) != cudaSuccess) return e;
+    sk<<<grid_for(dst.n_parts), 32 * WARPS, smem, h->aux>>>(pp, dst.n_parts);
     LAUNCHED(h);
     ++h->st.solve_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     auto fk = imp ? pr::als_finish_pair_kernel<true> : pr::als_finish_pair_kernel<false>;
     int fgrid = (dst.n_heavy + 1) / 2;
     if (fgrid > 12 * h->sm_count) fgrid = 12 * h->sm_count;
@@ -1105,9 +1095,10 @@ static cudaError_t launch_pair_w(pio_als_handle* h, Side& dst, const SolveParams
       SolveParams p = p0;
       p.row_begin = lo;
       p.row_end = hi;
-      if ((e = launch_sk(p, hi - lo, h->stream)) != cudaSuccess) return e;
+      sk<<<grid_for(hi - lo), 32 * WARPS, smem, h->stream>>>(p, hi - lo);
       LAUNCHED(h);
       ++h->st.solve_launches;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     cudaEventRecord(h->ev_piece[c], h->stream);
   }
@@ -1119,7 +1110,6 @@ static cudaError_t launch_pair_w(pio_als_handle* h, Side& dst, const SolveParams
 // Rank 33..64, pair kernel (als_pair_kernel.cuh): persistent CTAs of pair_warps independent warps, twelve warps per
 // SM.  Long rows first (their 512-rating parts as work items, then the finish kernel), then the rows that stay whole.
 static cudaError_t launch_pair(pio_als_handle* h, Side& dst, const SolveParams& p0, bool imp) {
-  if (h->use_duo) return launch_pair_w<0>(h, dst, p0, imp);
   switch (h->pair_warps) {
     case 1: return launch_pair_w<1>(h, dst, p0, imp);
     case 2: return launch_pair_w<2>(h, dst, p0, imp);
@@ -1445,7 +1435,6 @@ static int create_common(pio_als_handle* h) {
       h->use_pair = mm_[0] != '1';
     }
     if (const char* v = getenv("PIO_ALS_PAIR_WARPS")) h->pair_warps = atoi(v);
-    if (const char* v = getenv("PIO_ALS_DUO")) h->use_duo = v[0] != '0';
     if (const char* v = getenv("PIO_ALS_SEG_T")) h->pair_seg_t = atoi(v) > 0 ? atoi(v) : PAIR_SEG_T;
     if (const char* v = getenv("PIO_ALS_PART")) h->pair_part = atoi(v) >= 8 ? (atoi(v) + 7) / 8 * 8 : PAIR_PART;
   }
@@ -1677,9 +1666,8 @@ int pio_als_get_phase_ms(pio_als_handle* h, double out[8]) {
   for (int i = 0; i < 8; ++i) out[i] = h->phase_ms[i];
   // kernel of the rows below the heavy-row threshold: 0 = FP32 (als_solve_kernel), 1 = tcgen05, 2 = mma.sync
   const bool mma = h->KP == 64 && h->use_mma;
-  const double pk = h->use_duo ? 4.0 : 3.0;   // 3 = pair kernel (one warp per row), 4 = duo kernel (two warps per row)
-  out[4] = h->I.use_tc ? 1.0 : h->I.use_pair ? pk : (mma ? 2.0 : 0.0);
-  out[5] = h->U.use_tc ? 1.0 : h->U.use_pair ? pk : (mma ? 2.0 : 0.0);
+  out[4] = h->I.use_tc ? 1.0 : h->I.use_pair ? 3.0 : (mma ? 2.0 : 0.0);
+  out[5] = h->U.use_tc ? 1.0 : h->U.use_pair ? 3.0 : (mma ? 2.0 : 0.0);
   return PIO_ALS_OK;
 }
 

@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
 ]
 
 
-_KERNEL_NAMES = {0: "fp32", 1: "tcgen05", 2: "mma", 3: "pair", 4: "duo"}
+_KERNEL_NAMES = {0: "fp32", 1: "tcgen05", 2: "mma", 3: "pair"}
 
 
 class NativeError(RuntimeError):

@@ -144,20 +144,18 @@ def test_config_c1_recommendation_template(native, oracle):
     assert np.abs(pg - po).max() <= 1e-3 * max(1.0, np.abs(po).max())
 
 
-@pytest.mark.parametrize("path", ["fp32", "mma", "pair", "duo", "tcgen05"])
+@pytest.mark.parametrize("path", ["fp32", "mma", "pair", "tcgen05"])
 def test_heavy_rows_split_mode(native, oracle, monkeypatch, path):
     """Items with far more ratings than the heavy-row threshold are cut into parts (pair kernel: 512-rating parts above
     1024 ratings, summed by als_finish_pair_kernel; the other kernels: 2016-rating parts on the FP32 kernel +
     als_finish_kernel); the rows below the threshold go through each of the four rank-64 kernels in turn (the pair kernel
     is the default)."""
-    for v in ("PIO_ALS_TC", "PIO_ALS_MMA", "PIO_ALS_DUO"):
-        monkeypatch.delenv(v, raising=False)
+    monkeypatch.delenv("PIO_ALS_TC", raising=False)
+    monkeypatch.delenv("PIO_ALS_MMA", raising=False)
     if path == "fp32":
         monkeypatch.setenv("PIO_ALS_MMA", "0")
     elif path == "mma":
         monkeypatch.setenv("PIO_ALS_MMA", "1")
-    elif path == "pair":
-        monkeypatch.setenv("PIO_ALS_DUO", "0")
     elif path == "tcgen05":
         monkeypatch.setenv("PIO_ALS_TC", "1")
     nu, ni, nnz = 20000, 40, 400000
@@ -176,31 +174,28 @@ def test_rank64_kernel_selection(native, oracle, monkeypatch):
     """Rank 64 default: both sides on the pair kernel; PIO_ALS_TC=1 + PIO_ALS_TC_MIN_DEG=256 puts the item side (rows
     average >= 256 ratings) on the tcgen05 kernel, PIO_ALS_MMA=1 selects the round-1 mma.sync kernel, PIO_ALS_MMA=0 the
     FP32 kernel.  All are within tolerance of the oracle and of each other, and really are different code paths."""
-    for v in ("PIO_ALS_TC", "PIO_ALS_TC_MIN_DEG", "PIO_ALS_MMA", "PIO_ALS_DUO"):
+    for v in ("PIO_ALS_TC", "PIO_ALS_TC_MIN_DEG", "PIO_ALS_MMA"):
         monkeypatch.delenv(v, raising=False)
     nu, ni, nnz = 20000, 300, 400000
     for implicit in (True, False):
         u, i, r = synth.synth_ratings(nu, ni, nnz, seed=21, implicit=implicit)
         res = {}
-        for path, env in (("duo", {}), ("pair", {"PIO_ALS_DUO": "0"}),
-                          ("tcgen05", {"PIO_ALS_TC": "1", "PIO_ALS_TC_MIN_DEG": "256"}),
+        for path, env in (("pair", {}), ("tcgen05", {"PIO_ALS_TC": "1", "PIO_ALS_TC_MIN_DEG": "256"}),
                           ("mma", {"PIO_ALS_MMA": "1"}), ("fp32", {"PIO_ALS_MMA": "0"})):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             m, g, o = run_both(native, oracle, nu, ni, u, i, r, 64, 4, 0.05, implicit, 1.0)
             ph = m.phase_ms()
-            assert ph["item_kernel"] == path and ph["user_kernel"] == {"fp32": "fp32", "mma": "mma", "pair": "pair"}.get(path, "duo"), ph
+            assert ph["item_kernel"] == path and ph["user_kernel"] == {"fp32": "fp32", "mma": "mma"}.get(path, "pair"), ph
             eu, ei = frob_rel(g[0], o[0]), frob_rel(g[1], o[1])
             assert eu <= TOL and ei <= TOL, (path, implicit, eu, ei)
             res[path] = g
             for k in env:
                 monkeypatch.delenv(k)
-        for a in ("mma", "pair", "duo", "tcgen05"):
+        for a in ("mma", "pair", "tcgen05"):
             assert frob_rel(res[a][1], res["fp32"][1]) <= TOL
         assert not np.array_equal(res["pair"][1], res["fp32"][1]) and not np.array_equal(res["pair"][1], res["tcgen05"][1])
         assert not np.array_equal(res["pair"][1], res["mma"][1])
-        # the duo kernel splits a row's tiles over two warps but performs the same arithmetic as the pair kernel
-        assert np.array_equal(res["duo"][0], res["pair"][0]) and np.array_equal(res["duo"][1], res["pair"][1])
 
 
 @pytest.mark.parametrize("rank", [8, 64])    # 8: FP32 kernel, 64: mma.sync kernel
