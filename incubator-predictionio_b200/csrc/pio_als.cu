@@ -431,6 +431,8 @@ struct pio_als_handle {
   bool pieces_done = false;   // the last launch_solve recorded ev_piece[] / ev_heavy (pair path)
   // low-latency serving (few queries, topk <= 128): a persistent device arena and a mapped pinned host arena -- no
   // allocation, no staging copies, results written by the merge kernel straight into host memory
+  bool trace_on = false;      // PIO_ALS_INGEST_TRACE
+  std::chrono::steady_clock::time_point t_prev;
   unsigned char* srv_dev = nullptr;
   size_t srv_dev_cap = 0;
   unsigned char* srv_host = nullptr;       // cudaHostAlloc(mapped)
@@ -462,6 +464,15 @@ static int fail(pio_als_handle* h, int code, const char* fmt, ...) {
   if (h) h->err = buf;
   else g_create_error = buf;
   return code;
+}
+// PIO_ALS_INGEST_TRACE=1: wall-clock milliseconds per ingest phase (stream drained at every mark) on stderr
+static void tmark(pio_als_handle* h, const char* what) {
+  if (!h->trace_on) return;
+  cudaStreamSynchronize(h->stream);
+  const auto now = std::chrono::steady_clock::now();
+  fprintf(stderr, "[pio_als ingest r%d] %-34s %8.3f ms\n", h->cfg.world_rank, what,
+          std::chrono::duration<double, std::milli>(now - h->t_prev).count());
+  h->t_prev = now;
 }
 #define CK(h, call)                                                                              \
   do {                                                                                           \
@@ -545,6 +556,7 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
     LAUNCHED(h);
     CK(h, radix_sort_pairs(ka, va, kb, vb, (size_t)nnz, row.bits + col.bits, st, &in_b, &h->st.kernel_launches));
   }
+  tmark(h, "  side: keys + radix sort");
   const uint64_t* ks = in_b ? kb : ka;
   const uint32_t* vs = in_b ? vb : va;
   long long* ptr_full = nullptr;
@@ -570,6 +582,7 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
                                                                  col.p2i, row.idx, row.val);
     LAUNCHED(h);
   }
+  tmark(h, "  side: ptr + extract csr");
   CK(h, cudaMemsetAsync(h->d_counts, 0, 2 * sizeof(int), st));
   // kernel choice from global numbers only (ratings after dedup / rows of this side), so that every rank of a sharded
   // run and the single-GPU run take the same path for the same row
@@ -591,6 +604,7 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
   CK(h, cudaStreamSynchronize(st));
   row.n_active = counts[0];
   row.n_heavy = counts[1];
+  tmark(h, "  side: local rows");
   if (row.n_heavy > 0) {
     // cut the heavy rows (local rows [0, n_heavy), longest first) into parts of part_len ratings
     std::vector<long long> hp((size_t)row.n_heavy + 1);
@@ -608,6 +622,7 @@ static int build_side(pio_als_handle* h, Side& row, const Side& col, const int* 
     rpp[row.n_heavy] = (int)pb.size();
     row.n_parts = (int)pb.size();
     row.h_row_part_ptr = rpp;
+    tmark(h, "  side: parts of long rows");
     CK(h, dalloc(h, &row.part_beg, pb.size()));
     CK(h, dalloc(h, &row.part_end, pe.size()));
     CK(h, dalloc(h, &row.row_part_ptr, rpp.size()));
@@ -679,35 +694,40 @@ static int exchange_events(pio_als_handle* h, Scratch& keep, uint64_t* ka, uint3
     return fail(h, PIO_ALS_ERR_COMM, "ncclAllGather (exchange counts) failed");
   CK(h, cudaMemcpyAsync(all.data(), d_all, sizeof(long long) * W * W, cudaMemcpyDeviceToHost, st));
   CK(h, cudaStreamSynchronize(st));
+  tmark(h, "  exchange: sort by rank + counts");
   std::vector<long long> roff(W + 1, 0);
   for (int src = 0; src < W; ++src) roff[src + 1] = roff[src] + all[(size_t)src * W + me];
   const long long nrecv = roff[W];
   if (nrecv >= (1ll << 32)) return fail(h, PIO_ALS_ERR_ARG, "more than 2^32-1 events on one rank after the exchange");
+  // gather every array into destination order, then ONE grouped send/recv for all arrays and peers
+  std::vector<unsigned char*> sendbufs(na, nullptr), recvbufs(na, nullptr);
   for (int a = 0; a < na; ++a) {
     if (!arrs[a].in) { *arrs[a].out = nullptr; continue; }
-    unsigned char* sendbuf = nullptr;
-    unsigned char* recvbuf = nullptr;
-    CK(h, tmp.alloc(&sendbuf, (size_t)(n > 0 ? n : 1) * arrs[a].elem));
-    CK(h, keep.alloc(&recvbuf, (size_t)(nrecv > 0 ? nrecv : 1) * arrs[a].elem));
+    CK(h, tmp.alloc(&sendbufs[a], (size_t)(n > 0 ? n : 1) * arrs[a].elem));
+    CK(h, keep.alloc(&recvbufs[a], (size_t)(nrecv > 0 ? nrecv : 1) * arrs[a].elem));
     if (n > 0) {
       if (arrs[a].elem == 4)
-        gather_by_index_kernel<uint32_t><<<nblk(n, 256), 256, 0, st>>>((const uint32_t*)arrs[a].in, vs, n, (uint32_t*)sendbuf);
+        gather_by_index_kernel<uint32_t><<<nblk(n, 256), 256, 0, st>>>((const uint32_t*)arrs[a].in, vs, n, (uint32_t*)sendbufs[a]);
       else
-        gather_by_index_kernel<uint64_t><<<nblk(n, 256), 256, 0, st>>>((const uint64_t*)arrs[a].in, vs, n, (uint64_t*)sendbuf);
+        gather_by_index_kernel<uint64_t><<<nblk(n, 256), 256, 0, st>>>((const uint64_t*)arrs[a].in, vs, n, (uint64_t*)sendbufs[a]);
       LAUNCHED(h);
     }
-    if (nc.GroupStart() != ncclSuccess) return fail(h, PIO_ALS_ERR_COMM, "ncclGroupStart failed");
+    *arrs[a].out = recvbufs[a];
+  }
+  if (nc.GroupStart() != ncclSuccess) return fail(h, PIO_ALS_ERR_COMM, "ncclGroupStart failed");
+  for (int a = 0; a < na; ++a) {
+    if (!arrs[a].in) continue;
     for (int p = 0; p < W; ++p) {
       const long long sc = cnt[p], rc_ = all[(size_t)p * W + me];
-      if (sc > 0 && nc.Send(sendbuf + (size_t)off[p] * arrs[a].elem, (size_t)sc * arrs[a].elem, ncclInt8, p, h->comm, st) != ncclSuccess)
+      if (sc > 0 && nc.Send(sendbufs[a] + (size_t)off[p] * arrs[a].elem, (size_t)sc * arrs[a].elem, ncclInt8, p, h->comm, st) != ncclSuccess)
         return fail(h, PIO_ALS_ERR_COMM, "ncclSend failed");
-      if (rc_ > 0 && nc.Recv(recvbuf + (size_t)roff[p] * arrs[a].elem, (size_t)rc_ * arrs[a].elem, ncclInt8, p, h->comm, st) != ncclSuccess)
+      if (rc_ > 0 && nc.Recv(recvbufs[a] + (size_t)roff[p] * arrs[a].elem, (size_t)rc_ * arrs[a].elem, ncclInt8, p, h->comm, st) != ncclSuccess)
         return fail(h, PIO_ALS_ERR_COMM, "ncclRecv failed");
     }
-    if (nc.GroupEnd() != ncclSuccess) return fail(h, PIO_ALS_ERR_COMM, "ncclGroupEnd failed");
-    *arrs[a].out = recvbuf;
   }
+  if (nc.GroupEnd() != ncclSuccess) return fail(h, PIO_ALS_ERR_COMM, "ncclGroupEnd failed");
   CK(h, cudaStreamSynchronize(st));
+  tmark(h, "  exchange: gather + send/recv");
   *n_out = nrecv;
   return PIO_ALS_OK;
 }
@@ -739,17 +759,9 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
   U.bits = ceil_log2((uint64_t)U.n_internal);
   I.bits = ceil_log2((uint64_t)I.n_internal);
 
-  // PIO_ALS_INGEST_TRACE=1: wall-clock milliseconds per phase (stream drained at every mark) on stderr
-  const bool trace = getenv("PIO_ALS_INGEST_TRACE") != nullptr;
-  auto t_prev = std::chrono::steady_clock::now();
-  auto mark = [&](const char* what) {
-    if (!trace) return;
-    cudaStreamSynchronize(st);
-    const auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[pio_als ingest r%d] %-28s %8.3f ms\n", h->cfg.world_rank, what,
-            std::chrono::duration<double, std::milli>(now - t_prev).count());
-    t_prev = now;
-  };
+  h->trace_on = getenv("PIO_ALS_INGEST_TRACE") != nullptr;
+  h->t_prev = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) { tmark(h, what); };
   CK(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
   if (nnz > 0) {
     validate_coo_kernel<<<nblk(nnz, 256), 256, 0, st>>>(d_user, d_item, nnz, U.n, I.n, h->d_fail);
@@ -846,16 +858,18 @@ static int ingest_device(pio_als_handle* h, const int* d_user, const int* d_item
   long long n2_global = n2;
   if (sharded) {
     NcclApi& nc = nccl_api();   // only multi-GPU jobs touch NCCL (a single-GPU process must not load libnccl at all)
+    long long* d_n = nullptr;
+    CK(h, tmp.alloc(&d_n, 1));
+    CK(h, cudaMemcpyAsync(d_n, &n2, sizeof(long long), cudaMemcpyHostToDevice, st));
+    if (nc.GroupStart() != ncclSuccess) return fail(h, PIO_ALS_ERR_COMM, "ncclGroupStart failed");   // one launch for the five
     for (Side* s : {&U, &I}) {
       if (nc.AllReduce(s->deg, s->deg, (size_t)s->n, ncclUint32, ncclSum, h->comm, st) != ncclSuccess ||
           nc.AllReduce(s->npos, s->npos, (size_t)s->n, ncclUint32, ncclSum, h->comm, st) != ncclSuccess)
         return fail(h, PIO_ALS_ERR_COMM, "ncclAllReduce (degrees) failed");
     }
-    long long* d_n = nullptr;
-    CK(h, tmp.alloc(&d_n, 1));
-    CK(h, cudaMemcpyAsync(d_n, &n2, sizeof(long long), cudaMemcpyHostToDevice, st));
     if (nc.AllReduce(d_n, d_n, 1, ncclInt64, ncclSum, h->comm, st) != ncclSuccess)
       return fail(h, PIO_ALS_ERR_COMM, "ncclAllReduce (nnz) failed");
+    if (nc.GroupEnd() != ncclSuccess) return fail(h, PIO_ALS_ERR_COMM, "ncclGroupEnd failed");
     CK(h, cudaMemcpyAsync(&n2_global, d_n, sizeof(long long), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
     if (n2_global <= 0)
