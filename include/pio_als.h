@@ -218,6 +218,15 @@ PIO_API int pio_als_synth_ratings_device(int device, int32_t n_users, int32_t n_
 PIO_API int pio_ids_encode(int device, const uint8_t* bytes, const int64_t* offsets, int64_t n, int32_t* out_index,
                            int64_t* out_first, int32_t* out_n_unique);
 
+/* Item co-occurrence of the similarproduct template's CooccurrenceAlgorithm.trainCooccurrence
+ * (examples/scala-parallel-similarproduct/multi-events-multi-algos/src/main/scala/CooccurrenceAlgorithm.scala:72-105):
+ * (user, item) view events (indices, HOST) -> distinct -> for every user all item pairs -> count per pair -> for every item the
+ * topn co-occurring items with the largest counts.  out_item / out_count are n_items x topn (padded with -1 / 0),
+ * out_n[i] = number of valid entries of item i.  Ties (unspecified in the reference): larger count first, then the smaller
+ * item index.  Limits: n_items <= 2^20, fewer than 2^31 (user, item1, item2) triples. */
+PIO_API int pio_cooc_train(int device, const int32_t* user, const int32_t* item, int64_t n, int32_t n_users,
+                           int32_t n_items, int topn, int32_t* out_item, int32_t* out_count, int32_t* out_n);
+
 /* MLlib multinomial NaiveBayes (classification template). HOST buffers.
  * label: class index 0..n_class-1; x: n x n_feat, non-negative. pi: n_class, theta: n_class x n_feat
  * (fp64 log-probabilities, as MLlib's NaiveBayesModel.pi/theta). */

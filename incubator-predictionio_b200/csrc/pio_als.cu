@@ -42,6 +42,7 @@
 #include "sort_scan.cuh"
 #include "topk.cuh"
 #include "ids_encode.cuh"
+#include "cooc.cuh"
 
 namespace pio {
 
@@ -2503,6 +2504,102 @@ int pio_ids_encode(int device, const uint8_t* bytes, const int64_t* offsets, int
   const int64_t nuniq = (int64_t)last_ex + last_flag;
   if (out_first) CK0(cudaMemcpy(out_first, d_first, 8 * (size_t)nuniq, cudaMemcpyDeviceToHost));
   *out_n_unique = (int32_t)nuniq;
+  return PIO_ALS_OK;
+}
+
+// ---- item co-occurrence (similarproduct CooccurrenceAlgorithm) ------------------------------------------------------------
+int pio_cooc_train(int device, const int32_t* user, const int32_t* item, int64_t n, int32_t n_users, int32_t n_items,
+                   int topn, int32_t* out_item, int32_t* out_count, int32_t* out_n) {
+  if (!user || !item || !out_item || !out_count || !out_n || n < 1 || n_users < 1 || n_items < 1 || topn < 1)
+    return fail(nullptr, PIO_ALS_ERR_ARG, "bad pio_cooc_train arguments");
+  if (n >= (1ll << 32)) return fail(nullptr, PIO_ALS_ERR_ARG, "n must be < 2^32");
+  for (int64_t e = 0; e < n; ++e)
+    if (user[e] < 0 || user[e] >= n_users || item[e] < 0 || item[e] >= n_items)
+      return fail(nullptr, PIO_ALS_ERR_ARG, "event %lld has a user/item index out of range", (long long)e);
+  CK0(cudaSetDevice(device));
+  const int bits_u = ceil_log2((uint64_t)n_users), bits_i = ceil_log2((uint64_t)n_items);
+  if (2 * bits_i > 40) return fail(nullptr, PIO_ALS_ERR_ARG, "n_items too large for the pair keys (max 2^20 items)");
+  const int bits_c = 64 - 2 * bits_i > 32 ? 32 : 64 - 2 * bits_i;
+  std::vector<void*> owned;
+  auto A = [&](void** p, size_t bytes_) -> cudaError_t {
+    cudaError_t e = cudaMalloc(p, bytes_ ? bytes_ : 1);
+    if (e == cudaSuccess) owned.push_back(*p);
+    return e;
+  };
+  struct Guard { std::vector<void*>& v; ~Guard() { for (void* q : v) cudaFree(q); } } guard{owned};
+  cudaStream_t st = 0;
+  int *du = nullptr, *di = nullptr;
+  uint64_t *ka = nullptr, *kb = nullptr, *dk = nullptr;
+  uint32_t *va = nullptr, *vb = nullptr, *flag = nullptr, *rank = nullptr;
+  CK0(A((void**)&du, 4 * (size_t)n)); CK0(A((void**)&di, 4 * (size_t)n));
+  CK0(A((void**)&ka, 8 * (size_t)n)); CK0(A((void**)&kb, 8 * (size_t)n));
+  CK0(A((void**)&va, 4 * (size_t)n)); CK0(A((void**)&vb, 4 * (size_t)n));
+  CK0(A((void**)&flag, 4 * (size_t)n)); CK0(A((void**)&dk, 8 * (size_t)n)); CK0(A((void**)&rank, 4 * (size_t)n));
+  CK0(cudaMemcpyAsync(du, user, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  CK0(cudaMemcpyAsync(di, item, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  // 1. distinct (user, item), sorted by user then item
+  cooc_keys_kernel<<<nblk(n, 256), 256, 0, st>>>(du, di, n, bits_i, ka, va);
+  bool in_b = false;
+  CK0(radix_sort_pairs(ka, va, kb, vb, (size_t)n, bits_u + bits_i, st, &in_b, nullptr));
+  const uint64_t* ks = in_b ? kb : ka;
+  cooc_head_kernel<<<nblk(n, 256), 256, 0, st>>>(ks, n, flag);
+  uint32_t lf = 0, lp = 0;
+  CK0(cudaMemcpyAsync(&lf, flag + n - 1, 4, cudaMemcpyDeviceToHost, st));
+  uint32_t* pos = in_b ? va : vb;   // the payload buffer that is free now
+  CK0(scan_exclusive_u32(flag, pos, (size_t)n, st, nullptr));
+  CK0(cudaMemcpyAsync(&lp, pos + n - 1, 4, cudaMemcpyDeviceToHost, st));
+  CK0(cudaStreamSynchronize(st));
+  const long long m = (long long)lp + lf;
+  cooc_compact_kernel<<<nblk(n, 256), 256, 0, st>>>(ks, flag, pos, n, dk);
+  // 2. pairs (item1 < item2) per user
+  cooc_rank_kernel<<<nblk(m, 256), 256, 0, st>>>(dk, m, bits_i, rank);
+  uint32_t* off = flag;
+  CK0(scan_exclusive_u32(rank, off, (size_t)m, st, nullptr));
+  uint32_t lr = 0, lo = 0;
+  CK0(cudaMemcpyAsync(&lr, rank + m - 1, 4, cudaMemcpyDeviceToHost, st));
+  CK0(cudaMemcpyAsync(&lo, off + m - 1, 4, cudaMemcpyDeviceToHost, st));
+  CK0(cudaStreamSynchronize(st));
+  const long long np = (long long)lo + lr;
+  if (np >= (1ll << 31)) return fail(nullptr, PIO_ALS_ERR_ARG, "more than 2^31-1 co-occurrence pairs (%lld)", np);
+  std::vector<int> h_item((size_t)n_items * topn, -1), h_cnt((size_t)n_items * topn, 0), h_n((size_t)n_items, 0);
+  if (np > 0) {
+    uint64_t *pk = nullptr, *pk2 = nullptr, *rk = nullptr, *rk2 = nullptr;
+    uint32_t *pp = nullptr, *pp2 = nullptr, *pf = nullptr, *ppos = nullptr, *rp = nullptr, *rp2 = nullptr;
+    CK0(A((void**)&pk, 8 * (size_t)np)); CK0(A((void**)&pk2, 8 * (size_t)np));
+    CK0(A((void**)&pp, 4 * (size_t)np)); CK0(A((void**)&pp2, 4 * (size_t)np));
+    CK0(A((void**)&pf, 4 * (size_t)np)); CK0(A((void**)&ppos, 4 * (size_t)np));
+    cooc_pairs_kernel<<<nblk(m, 256), 256, 0, st>>>(dk, rank, off, m, bits_i, pk, pp);
+    bool pb_ = false;
+    CK0(radix_sort_pairs(pk, pp, pk2, pp2, (size_t)np, 2 * bits_i, st, &pb_, nullptr));
+    const uint64_t* pks = pb_ ? pk2 : pk;
+    cooc_head_kernel<<<nblk(np, 256), 256, 0, st>>>(pks, np, pf);
+    uint32_t cf = 0, cp = 0;
+    CK0(cudaMemcpyAsync(&cf, pf + np - 1, 4, cudaMemcpyDeviceToHost, st));
+    CK0(scan_exclusive_u32(pf, ppos, (size_t)np, st, nullptr));
+    CK0(cudaMemcpyAsync(&cp, ppos + np - 1, 4, cudaMemcpyDeviceToHost, st));
+    CK0(cudaStreamSynchronize(st));
+    const long long C = (long long)cp + cf, n2 = 2 * C;
+    // 3. both directions, ranked per item by (count desc, other item asc)
+    CK0(A((void**)&rk, 8 * (size_t)n2)); CK0(A((void**)&rk2, 8 * (size_t)n2));
+    CK0(A((void**)&rp, 4 * (size_t)n2)); CK0(A((void**)&rp2, 4 * (size_t)n2));
+    cooc_runs_kernel<<<nblk(np, 256), 256, 0, st>>>(pks, pf, ppos, np, bits_i, bits_c, rk, rp);
+    bool rb = false;
+    CK0(radix_sort_pairs(rk, rp, rk2, rp2, (size_t)n2, 2 * bits_i + bits_c, st, &rb, nullptr));
+    int *d_oi = nullptr, *d_oc = nullptr, *d_on = nullptr;
+    CK0(A((void**)&d_oi, 4 * (size_t)n_items * topn)); CK0(A((void**)&d_oc, 4 * (size_t)n_items * topn));
+    CK0(A((void**)&d_on, 4 * (size_t)n_items));
+    CK0(cudaMemsetAsync(d_oi, 0xff, 4 * (size_t)n_items * topn, st));
+    CK0(cudaMemsetAsync(d_oc, 0, 4 * (size_t)n_items * topn, st));
+    CK0(cudaMemsetAsync(d_on, 0, 4 * (size_t)n_items, st));
+    cooc_take_kernel<<<nblk(n2, 256), 256, 0, st>>>(rb ? rk2 : rk, rb ? rp2 : rp, n2, bits_i, bits_c, topn, d_oi, d_oc, d_on);
+    CK0(cudaMemcpyAsync(h_item.data(), d_oi, 4 * h_item.size(), cudaMemcpyDeviceToHost, st));
+    CK0(cudaMemcpyAsync(h_cnt.data(), d_oc, 4 * h_cnt.size(), cudaMemcpyDeviceToHost, st));
+    CK0(cudaMemcpyAsync(h_n.data(), d_on, 4 * h_n.size(), cudaMemcpyDeviceToHost, st));
+    CK0(cudaStreamSynchronize(st));
+  }
+  memcpy(out_item, h_item.data(), 4 * h_item.size());
+  memcpy(out_count, h_cnt.data(), 4 * h_cnt.size());
+  memcpy(out_n, h_n.data(), 4 * h_n.size());
   return PIO_ALS_OK;
 }
 

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "pio_als_set_ratings_coo_sharded_device",
     "pio_als_set_init", "pio_als_run", "pio_als_get_factors", "pio_als_train", "pio_als_recommend",
     "pio_als_similar", "pio_als_similar_batch", "pio_als_model_import", "pio_als_save", "pio_als_load", "pio_als_get_stats", "pio_als_get_phase_ms",
-    "pio_als_synth_ratings_device", "pio_nb_train", "pio_nb_predict", "pio_ids_encode",
+    "pio_als_synth_ratings_device", "pio_nb_train", "pio_nb_predict", "pio_ids_encode", "pio_cooc_train",
 ]
 
 
@@ -359,6 +359,21 @@ def ids_encode(strings, device=0):
     if rc != 0:
         raise NativeError(rc, lib().pio_als_last_error(None).decode())
     return idx, first[:nu.value]
+
+
+def cooc_train(user, item, n_users, n_items, topn, device=0):
+    """CooccurrenceAlgorithm.trainCooccurrence on the GPU: (items [n_items, topn], counts [n_items, topn], n [n_items])."""
+    user = np.ascontiguousarray(user, np.int32)
+    item = np.ascontiguousarray(item, np.int32)
+    oi = np.full((n_items, topn), -1, np.int32)
+    oc = np.zeros((n_items, topn), np.int32)
+    on = np.zeros(n_items, np.int32)
+    rc = lib().pio_cooc_train(C.c_int(device), _ptr(user, C.c_int32), _ptr(item, C.c_int32), C.c_int64(user.shape[0]),
+                              C.c_int32(n_users), C.c_int32(n_items), C.c_int(topn), _ptr(oi, C.c_int32),
+                              _ptr(oc, C.c_int32), _ptr(on, C.c_int32))
+    if rc != 0:
+        raise NativeError(rc, lib().pio_als_last_error(None).decode())
+    return oi, oc, on
 
 
 def nb_train(label, x, n_class, lam, device=0):

@@ -222,3 +222,63 @@ class Serving(LServing):
 class RecommendationEngine(EngineFactory):
     def apply(self) -> Engine:
         return Engine(DataSource, Preparator, {"als": ALSAlgorithm}, Serving)
+
+
+# ---- evaluation (examples/scala-parallel-recommendation/blacklist-items/src/main/scala/Evaluation.scala) -----------------
+from ..controller import EngineParams  # noqa: E402
+from ..evaluation import (AverageMetric, EngineParamsGenerator, Evaluation, MetricEvaluator,  # noqa: E402
+                          OptionAverageMetric)
+
+
+class PrecisionAtK(OptionAverageMetric):
+    """Evaluation.scala:32-51: hits among the first k predicted items / min(k, #positives); undefined (None) for a query
+    whose user has no rating >= ratingThreshold in the test fold."""
+
+    def __init__(self, k: int, ratingThreshold: float = 2.0):
+        assert k > 0, "k must be greater than 0"
+        self.k, self.ratingThreshold = k, ratingThreshold
+
+    @property
+    def header(self) -> str:
+        return f"Precision@K (k={self.k}, threshold={self.ratingThreshold})"
+
+    def calculate_one(self, q: Query, p: PredictedResult, a: ActualResult):
+        positives = {r.item for r in a.ratings if r.rating >= self.ratingThreshold}
+        if not positives:
+            return None
+        tp = sum(1 for s in p.itemScores[:self.k] if s.item in positives)
+        return tp / min(self.k, len(positives))
+
+
+class PositiveCount(AverageMetric):
+    """Evaluation.scala:53-62."""
+
+    def __init__(self, ratingThreshold: float = 2.0):
+        self.ratingThreshold = ratingThreshold
+
+    @property
+    def header(self) -> str:
+        return f"PositiveCount (threshold={self.ratingThreshold})"
+
+    def calculate_one(self, q, p, a: ActualResult) -> float:
+        return float(sum(1 for r in a.ratings if r.rating >= self.ratingThreshold))
+
+
+class RecommendationEvaluation(Evaluation):
+    """Evaluation.scala:64-76."""
+    engine = RecommendationEngine().apply()
+    evaluator = MetricEvaluator(
+        metric=PrecisionAtK(k=10, ratingThreshold=4.0),
+        otherMetrics=[PositiveCount(4.0), PrecisionAtK(10, 2.0), PositiveCount(2.0), PrecisionAtK(10, 1.0), PositiveCount(1.0)])
+
+
+class EngineParamsList(EngineParamsGenerator):
+    """Evaluation.scala:95-110: rank in (5, 10, 20) x numIterations in (1, 5, 10), kFold = 5, queryNum = 10, seed 3."""
+
+    def __init__(self, appName: str = "MyApp1", kFold: int = 5, queryNum: int = 10,
+                 ranks=(5, 10, 20), iterations=(1, 5, 10)):
+        base_ds = ("", DataSourceParams(appName=appName, evalParams=DataSourceEvalParams(kFold=kFold, queryNum=queryNum)))
+        self.engineParamsList = [
+            EngineParams(dataSourceParams=base_ds,
+                         algorithmParamsList=[("als", ALSAlgorithmParams(rank=r, numIterations=n, lambda_=0.01, seed=3))])
+            for r in ranks for n in iterations]

@@ -247,6 +247,80 @@ class LikeAlgorithm(ALSAlgorithm):
         return ALSModel(m, itemMap, items)
 
 
+@dataclass
+class CooccurrenceAlgorithmParams(Params):
+    n: int   # top co-occurring items kept per item
+
+
+class CooccurrenceModel:
+    """topCooccurrences: item index -> [(other item index, count), ...] (CooccurrenceAlgorithm.scala:31-42); a plain local
+    model (P2LAlgorithm keeps it as is)."""
+
+    def __init__(self, top_items: np.ndarray, top_counts: np.ndarray, top_n: np.ndarray, itemStringIntMap: BiMap,
+                 items: Dict[int, Item]):
+        self.top_items, self.top_counts, self.top_n = top_items, top_counts, top_n
+        self.itemStringIntMap, self.items = itemStringIntMap, items
+        self.itemIntStringMap = itemStringIntMap.inverse
+
+    def topCooccurrences(self, i: int):
+        return [(int(self.top_items[i, t]), int(self.top_counts[i, t])) for t in range(int(self.top_n[i]))]
+
+
+class CooccurrenceAlgorithm(P2LAlgorithm):
+    """CooccurrenceAlgorithm.scala:44-175: the counting runs on the GPU (pio_cooc_train), predict sums the stored counts of
+    the query items, filters and takes the top `num`."""
+
+    def __init__(self, ap: CooccurrenceAlgorithmParams):
+        self.ap = ap
+
+    def train(self, sc, data) -> CooccurrenceModel:
+        from .. import native
+        itemMap = BiMap.stringInt(data.items.keys())
+        userMap = BiMap.stringInt(e.user for e in data.viewEvents)     # only to index the users of the view events
+        us, its = [], []
+        for e in data.viewEvents:
+            i = itemMap.getOrElse(e.item, -1)
+            if i != -1:
+                us.append(userMap(e.user))
+                its.append(i)
+        items = {itemMap(k): v for k, v in data.items.items()}
+        n_items = itemMap.size
+        if us:
+            ti, tc, tn = native.cooc_train(np.array(us, np.int32), np.array(its, np.int32), max(userMap.size, 1), n_items,
+                                           self.ap.n, device=getattr(sc, "device", 0))
+        else:
+            ti = np.full((n_items, self.ap.n), -1, np.int32)
+            tc = np.zeros((n_items, self.ap.n), np.int32)
+            tn = np.zeros(n_items, np.int32)
+        return CooccurrenceModel(ti, tc, tn, itemMap, items)
+
+    def predict(self, model: CooccurrenceModel, query: Query) -> PredictedResult:
+        queryList = {i for i in (model.itemStringIntMap.get(x) for x in query.items) if i is not None}
+        white = None if query.whiteList is None else {i for i in (model.itemStringIntMap.get(x) for x in query.whiteList)
+                                                      if i is not None}
+        black = None if query.blackList is None else {i for i in (model.itemStringIntMap.get(x) for x in query.blackList)
+                                                      if i is not None}
+        counts: Dict[int, int] = {}
+        for q in queryList:
+            for idx, c in model.topCooccurrences(q):
+                counts[idx] = counts.get(idx, 0) + c
+
+        def candidate(i: int) -> bool:
+            if white is not None and i not in white:
+                return False
+            if black is not None and i in black:
+                return False
+            if i in queryList:
+                return False
+            if query.categories is not None:
+                cats = model.items[i].categories if i in model.items else None
+                return cats is not None and bool(set(cats) & set(query.categories))
+            return True
+
+        top = sorted(((i, v) for i, v in counts.items() if candidate(i)), key=lambda kv: (-kv[1], kv[0]))[:query.num]
+        return PredictedResult([ItemScore(model.itemIntStringMap(i), float(v)) for i, v in top])
+
+
 class Serving(LServing):
     """z-score standardisation per algorithm, then sum per item, top num (Serving.scala:29-69)."""
 
@@ -271,4 +345,5 @@ class Serving(LServing):
 
 class SimilarProductEngine(EngineFactory):
     def apply(self) -> Engine:
-        return Engine(DataSource, Preparator, {"als": ALSAlgorithm, "likealgo": LikeAlgorithm}, Serving)
+        return Engine(DataSource, Preparator, {"als": ALSAlgorithm, "cooccurrence": CooccurrenceAlgorithm,
+                                                "likealgo": LikeAlgorithm}, Serving)

@@ -338,3 +338,34 @@ def als_objective(user, item, rating, uf, itf, lam, implicit, alpha):
     nu = np.bincount(user, weights=p, minlength=U.shape[0])
     ni = np.bincount(item, weights=p, minlength=V.shape[0])
     return float(base + corr + lam * ((nu * (U ** 2).sum(1)).sum() + (ni * (V ** 2).sum(1)).sum()))
+
+
+# ----------------------------------------------------------------------------
+# similarproduct CooccurrenceAlgorithm.trainCooccurrence (CooccurrenceAlgorithm.scala:72-105), restated with Python
+# sets / dicts: distinct (user, item), all item pairs per user, count per pair, per item the topn by
+# (count descending, item index ascending) -- the reference leaves ties unspecified.
+# ----------------------------------------------------------------------------
+def cooc_train(user, item, n_items, topn):
+    from collections import defaultdict
+    per_user = defaultdict(set)
+    for u, i in zip(np.asarray(user).tolist(), np.asarray(item).tolist()):
+        per_user[u].add(i)
+    cnt = defaultdict(int)
+    for items in per_user.values():
+        li = sorted(items)
+        for a in range(len(li)):
+            for b in range(a + 1, len(li)):
+                cnt[(li[a], li[b])] += 1
+    per_item = defaultdict(list)
+    for (a, b), c in cnt.items():
+        per_item[a].append((b, c))
+        per_item[b].append((a, c))
+    oi = np.full((n_items, topn), -1, np.int32)
+    oc = np.zeros((n_items, topn), np.int32)
+    on = np.zeros(n_items, np.int32)
+    for it, lst in per_item.items():
+        lst.sort(key=lambda t: (-t[1], t[0]))
+        for r, (o, c) in enumerate(lst[:topn]):
+            oi[it, r], oc[it, r] = o, c
+        on[it] = min(len(lst), topn)
+    return oi, oc, on

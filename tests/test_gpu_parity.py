@@ -474,3 +474,19 @@ def test_ids_encode_matches_bimap_stringint(native, monkeypatch, hash_bits):
     assert i0.shape == (0,) and f0.shape == (0,)
     i1, f1 = native.ids_encode(["x"] * 1000)
     assert (i1 == 0).all() and f1.tolist() == [0]
+
+
+def test_cooccurrence_training_is_exact(native, oracle):
+    """pio_cooc_train == the restatement of CooccurrenceAlgorithm.trainCooccurrence (integer work: bit-exact), incl.
+    repeated views (counted once), users with one item (no pairs) and items nobody co-viewed."""
+    rng = np.random.default_rng(4)
+    nu, ni, n = 800, 300, 20000
+    u = rng.integers(0, nu, n).astype(np.int32)
+    i = np.minimum((rng.random(n) ** 2 * ni).astype(np.int32), ni - 2)      # popular head, item ni-1 never viewed
+    u[:50] = nu - 1
+    i[:50] = 7                                                             # one user viewing one item 50 times
+    for topn in (1, 5, 20):
+        gi, gc, gn = native.cooc_train(u, i, nu, ni, topn)
+        oi, oc, on = oracle.cooc_train(u, i, ni, topn)
+        assert np.array_equal(gn, on) and np.array_equal(gi, oi) and np.array_equal(gc, oc), topn
+    assert gn[ni - 1] == 0

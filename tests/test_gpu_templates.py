@@ -102,6 +102,30 @@ def test_similarproduct_template(tmp_path, monkeypatch, oracle):
     assert all(x.score > 0 for x in res.itemScores)
     assert algo.predict(m, sp.Query(items=["i52"], num=3)).itemScores == []     # item without a factor
 
+    # CooccurrenceAlgorithm of the same engine (CooccurrenceAlgorithm.scala:44-175): counting on the GPU, predict on the host
+    ep2 = eng.jValueToEngineParams({"datasource": {"params": {"appName": "Sim"}},
+                                    "algorithms": [{"name": "cooccurrence", "params": {"n": 10}}]})
+    cm = eng.train(sc, ep2, "cooc")[0]
+    calgo = sp.CooccurrenceAlgorithm(ep2.algorithmParamsList[0][1])
+    td = sp.DataSource(ep2.dataSourceParams[1]).readTraining(sc)
+    per_user = {}
+    for e in td.viewEvents:
+        per_user.setdefault(e.user, set()).add(cm.itemStringIntMap(e.item))
+    want = {}
+    for its in per_user.values():
+        for a in its:
+            for b in its:
+                if a != b:
+                    want.setdefault(a, {}).setdefault(b, 0)
+                    want[a][b] += 1
+    for it in (cm.itemStringIntMap("i1"), cm.itemStringIntMap("i3"), cm.itemStringIntMap("i20")):
+        exp = sorted(want.get(it, {}).items(), key=lambda kv: (-kv[1], kv[0]))[:10]
+        assert cm.topCooccurrences(it) == exp
+    res = calgo.predict(cm, sp.Query(items=["i1", "i3"], num=5, blackList={"i0"}))
+    assert len(res.itemScores) == 5 and not ({"i0", "i1", "i3"} & {x.item for x in res.itemScores})
+    assert [x.score for x in res.itemScores] == sorted((x.score for x in res.itemScores), reverse=True)
+    assert calgo.predict(cm, sp.Query(items=["i52"], num=3)).itemScores == []    # never viewed
+
 
 def test_classification_template(tmp_path, monkeypatch, oracle):
     monkeypatch.setenv("PIO_EVENTDATA_DIR", str(tmp_path / "events"))
@@ -173,6 +197,31 @@ def test_ecommerce_template(tmp_path, monkeypatch, oracle):
     res = algo.predict(m, ec.Query(user=known, num=5))
     assert res.itemScores and all(x.score > 0 for x in res.itemScores)
     assert not (bought & {x.item for x in res.itemScores})                    # unseenOnly
+    # adjust-score variant: a $set of the constraint entity "weightedItems" multiplies the scores of the listed items
+    # (adjust-score ECommAlgorithm.scala:258-266,490-497); weight 0 removes an item (score > 0 filter), a large weight
+    # promotes it
+    top = [x.item for x in res.itemScores]
+    s.import_events("Shop", [dict(event="$set", entityType="constraint", entityId="weightedItems",
+                                  eventTime=(t0 + dt.timedelta(days=30)).isoformat(),
+                                  properties={"weights": [{"items": [top[0]], "weight": 0.0},
+                                                          {"items": [top[-1]], "weight": 1000.0}]})])
+    res_w = algo.predict(m, ec.Query(user=known, num=5))
+    assert top[0] not in [x.item for x in res_w.itemScores] and res_w.itemScores[0].item == top[-1]
+    uidx = m.userStringIntMap(known)
+    wv = np.ones(m.itemStringIntMap.size)
+    wv[m.itemStringIntMap(top[0])] = 0.0
+    wv[m.itemStringIntMap(top[-1])] = 1000.0
+    mask = algo._mask(m, ec.Query(user=known, num=5), {b for b in (m.itemStringIntMap.get(x) for x in algo.genBlackList(
+        ec.Query(user=known, num=5))) if b is not None})
+    oi, os_, oc = oracle.recommend(m.mf.userFeatures, m.mf.userHas, m.mf.productFeatures, m.mf.productHas,
+                                   np.array([uidx], np.int32), 5, mask, wv)
+    assert [x.item for x in res_w.itemScores] == [m.itemIntStringMap(int(t)) for t, sc_ in zip(oi[0], os_[0]) if sc_ > 0]
+    # predictSimilar (unknown user with recent views): the recently viewed items stay candidates
+    # (train-with-rate-event ECommAlgorithm.scala:492-525 has no "not a query item" rule)
+    s.import_events("Shop", [dict(event="view", entityType="user", entityId="newcomer", targetEntityType="item",
+                                  targetEntityId=top[1], eventTime=(t0 + dt.timedelta(days=31)).isoformat())])
+    res_s = algo.predict(m, ec.Query(user="newcomer", num=3))
+    assert top[1] in [x.item for x in res_s.itemScores]      # with similarproduct's rule it could never appear
     res = algo.predict(m, ec.Query(user=known, num=40, categories={"c1"}))
     assert all(int(x.item[1:]) % 3 == 1 for x in res.itemScores)
     res = algo.predict(m, ec.Query(user="stranger", num=3))                   # unknown user, no recent views -> popularity
@@ -181,3 +230,54 @@ def test_ecommerce_template(tmp_path, monkeypatch, oracle):
         if e["event"] == "buy":
             counts[e["targetEntityId"]] = counts.get(e["targetEntityId"], 0) + 1
     assert [x.score for x in res.itemScores] == sorted(counts.values(), reverse=True)[:3]
+
+
+def test_recommendation_evaluation_k_fold_on_gpu(tmp_path, monkeypatch, oracle):
+    """`pio eval` of the recommendation template (Evaluation.scala:64-110): every fold of every engine-params set is one
+    ALS training + one batched top-N call on the device (3 x 3 sets x 5 folds = 45 trainings).  One fold is recomputed with
+    the oracle (same split, same maps, same seed) and must give the same Precision@K."""
+    from pio_b200 import evaluation as ev
+    from pio_b200.templates import recommendation as rec
+    monkeypatch.setenv("PIO_EVENTDATA_DIR", str(tmp_path / "events"))
+    monkeypatch.setenv("PIO_MODELDATA_DIR", str(tmp_path / "models"))
+    evs = _events(300, 60, 6000, seed=5)
+    s.import_events("MyApp1", evs)
+    gen = rec.EngineParamsList(appName="MyApp1")
+    assert len(gen.engineParamsList) == 9
+    res = ev.run_evaluation(rec.RecommendationEvaluation(), gen)
+    assert len(res.engineParamsScores) == 9 and res.metricHeader == "Precision@K (k=10, threshold=4.0)"
+    assert len(res.otherMetricHeaders) == 5
+    scores = [sc.score for _, sc in res.engineParamsScores]
+    assert all(0.0 <= x <= 1.0 for x in scores) and res.bestScore.score == max(scores)
+    assert res.bestIdx == scores.index(max(scores))                       # the first maximum wins
+    pos = [sc.otherScores[0] for _, sc in res.engineParamsScores]
+    assert max(pos) == min(pos) > 0                                        # PositiveCount does not depend on the model
+
+    # fold 0 of the first parameter set (rank 5, 1 iteration) through the oracle
+    ep = gen.engineParamsList[0]
+    ds = rec.DataSource(ep.dataSourceParams[1])
+    td, _, qas = ds.readEval(None)[0]
+    users = [r.user for r in td.ratings]
+    items = [r.item for r in td.ratings]
+    um, im = s.BiMap.stringInt(users), s.BiMap.stringInt(items)
+    u = np.array([um(x) for x in users], np.int32)
+    i = np.array([im(x) for x in items], np.int32)
+    r = np.array([x.rating for x in td.ratings], np.float32)
+    u0, i0 = synth.synth_init_factors(um.size, 5, 3, 0), synth.synth_init_factors(im.size, 5, 3, 1)
+    ouf, oitf, ouh, oih = oracle.als_train(um.size, im.size, u, i, r, 5, 1, 0.01, False, 1.0, u0, i0)
+    metric = rec.PrecisionAtK(10, 4.0)
+    vals = []
+    for q, a in qas:
+        uidx = um.get(q.user)
+        if uidx is None:
+            p = rec.PredictedResult([])
+        else:
+            oi, os_, oc = oracle.recommend(ouf, ouh, oitf, oih, np.array([uidx], np.int32), q.num)
+            p = rec.PredictedResult([rec.ItemScore(im.inverse(int(oi[0, t])), float(os_[0, t])) for t in range(int(oc[0]))])
+        v = metric.calculate_one(q, p, a)
+        if v is not None:
+            vals.append(v)
+    want = sum(vals) / len(vals)
+    engine = rec.RecommendationEvaluation.engine
+    got = metric.calculate(None, [engine.eval(w.WorkflowContext(mode="Evaluation"), ep)[0]])
+    assert abs(got - want) <= 1e-9, (got, want)
