@@ -229,7 +229,9 @@ def test_ecommerce_template(tmp_path, monkeypatch, oracle):
     for e in evs:
         if e["event"] == "buy":
             counts[e["targetEntityId"]] = counts.get(e["targetEntityId"], 0) + 1
-    assert [x.score for x in res.itemScores] == sorted(counts.values(), reverse=True)[:3]
+    # predictDefault multiplies the popularity count by the item weight as well (adjust-score :505-533)
+    wmap = {top[0]: 0.0, top[-1]: 1000.0}
+    assert [x.score for x in res.itemScores] == sorted((c * wmap.get(it, 1.0) for it, c in counts.items()), reverse=True)[:3]
 
 
 def test_recommendation_evaluation_k_fold_on_gpu(tmp_path, monkeypatch, oracle):
