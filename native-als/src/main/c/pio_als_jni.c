@@ -331,3 +331,54 @@ JNIEXPORT jdoubleArray JNICALL JNAME(nbTrain)(JNIEnv* env, jobject self, jint de
   }
   return out;
 }
+
+/* int[] encodeIds(int device, byte[] bytes, long[] offsets, long[] outFirst):  (outFirst: capacity n, nullable)
+ * BiMap.stringInt on the device -- returns the dense index of every string; outFirst[id] = position of the first
+ * occurrence of the string with that index (the inverse map); the number of distinct ids is max(index) + 1. */
+JNIEXPORT jintArray JNICALL JNAME(encodeIds)(JNIEnv* env, jobject self, jint device, jbyteArray bytes, jlongArray offsets,
+                                             jlongArray outFirst) {
+  jsize n = (*env)->GetArrayLength(env, offsets) - 1;
+  jintArray out = (*env)->NewIntArray(env, n > 0 ? n : 0);
+  int32_t nuniq = 0;
+  jbyte* b;
+  jlong *off, *first;
+  jint* o;
+  int rc;
+  (void)self;
+  if (!out) return NULL;
+  b = pin(env, bytes);
+  off = pin(env, offsets);
+  first = pin(env, outFirst);
+  o = pin(env, out);
+  rc = pio_ids_encode(device, (const uint8_t*)b, (const int64_t*)off, (int64_t)n, (int32_t*)o, (int64_t*)first, &nuniq);
+  unpin(env, out, o, 0);
+  unpin(env, outFirst, first, 0);
+  unpin(env, offsets, off, JNI_ABORT);
+  unpin(env, bytes, b, JNI_ABORT);
+  if (rc != PIO_ALS_OK) {
+    throw_rt(env, pio_als_last_error(NULL));
+    return NULL;
+  }
+  return out;
+}
+
+/* void coocTrain(int device, int[] user, int[] item, int nUsers, int nItems, int topn, int[] outItem, int[] outCount, int[] outN):
+ * CooccurrenceAlgorithm.trainCooccurrence (outItem / outCount: nItems x topn, outN: nItems) */
+JNIEXPORT void JNICALL JNAME(coocTrain)(JNIEnv* env, jobject self, jint device, jintArray user, jintArray item, jint nUsers,
+                                        jint nItems, jint topn, jintArray outItem, jintArray outCount, jintArray outN) {
+  jsize n = (*env)->GetArrayLength(env, user);
+  jint* u = pin(env, user);
+  jint* i = pin(env, item);
+  jint* oi = pin(env, outItem);
+  jint* oc = pin(env, outCount);
+  jint* on = pin(env, outN);
+  int rc = pio_cooc_train(device, (const int32_t*)u, (const int32_t*)i, (int64_t)n, nUsers, nItems, topn, (int32_t*)oi,
+                          (int32_t*)oc, (int32_t*)on);
+  (void)self;
+  unpin(env, outN, on, 0);
+  unpin(env, outCount, oc, 0);
+  unpin(env, outItem, oi, 0);
+  unpin(env, item, i, JNI_ABORT);
+  unpin(env, user, u, JNI_ABORT);
+  if (rc != PIO_ALS_OK) throw_rt(env, pio_als_last_error(NULL));
+}

@@ -46,6 +46,20 @@ object NativeALS {
   @native def stats(h: Long): Array[Long]
   @native def nbTrain(device: Int, label: Array[Int], x: Array[Float], nFeat: Int, nClass: Int,
     lambda: Double): Array[Double]
+  @native def encodeIds(device: Int, bytes: Array[Byte], offsets: Array[Long], outFirst: Array[Long]): Array[Int]
+  @native def coocTrain(device: Int, user: Array[Int], item: Array[Int], nUsers: Int, nItems: Int, topn: Int,
+    outItem: Array[Int], outCount: Array[Int], outN: Array[Int]): Unit
+
+  /** BiMap.stringInt(keys) on the device (BiMap.scala:116-128): index per key in first-occurrence order and the keys of
+    * the distinct ids in index order. */
+  def stringInt(keys: Array[String], device: Int = 0): (Array[Int], Array[String]) = {
+    val enc = keys.map(_.getBytes("UTF-8"))
+    val offsets = enc.scanLeft(0L)(_ + _.length)
+    val first = new Array[Long](keys.length)
+    val idx = encodeIds(device, enc.flatten, offsets, first)
+    val n = if (idx.isEmpty) 0 else idx.max + 1
+    (idx, first.take(n).map(p => keys(p.toInt)))
+  }
 
   /** How repeated (user, item) pairs are treated (the templates' own reduceByKey, moved to the device). */
   val DEDUP_NONE = 0      // recommendation: every event is its own rating (ALSAlgorithm.scala:62-65)

@@ -39,6 +39,7 @@ struct JNINativeInterface_ {
   jbyteArray (*NewByteArray)(JNIEnv*, jsize);
   jlongArray (*NewLongArray)(JNIEnv*, jsize);
   jdoubleArray (*NewDoubleArray)(JNIEnv*, jsize);
+  jintArray (*NewIntArray)(JNIEnv*, jsize);
   const char* (*GetStringUTFChars)(JNIEnv*, jstring, jboolean*);
   void (*ReleaseStringUTFChars)(JNIEnv*, jstring, const char*);
 };
