@@ -612,34 +612,44 @@ als_finish_kernel(const SolveParams p, const int* __restrict__ row_part_ptr, int
 }
 
 // Rank 65..128: one warp per row; fixed-order sum of the row's partial normal equations (LsLayout<128> + b) into shared
-// memory, then the lockstep Cholesky with all 32 lanes on the one 128 x 128 matrix.
+// memory, then the lockstep Cholesky with all 32 lanes on the one 128 x 128 matrix.  FIN128_WARPS warps per CTA (one CTA per
+// SM: 33 KB of shared memory per matrix) share one barrier before the solve, so that they walk the large unrolled solver
+// together (instruction-cache locality, as in the pair kernel).
+constexpr int FIN128_WARPS = 6;
+constexpr int FIN128_FLOATS = LsLayout<128>::STRIDE + 128 + 80;   // slot, b, pivot line -- per warp
+
 template <bool IMPLICIT>
-__global__ void __launch_bounds__(32) als_finish_ls128_kernel(const SolveParams p, const int* __restrict__ row_part_ptr,
-                                                              int row0, int n_rows, int part0) {
+__global__ void __launch_bounds__(32 * FIN128_WARPS, 1)
+als_finish_ls128_kernel(const SolveParams p, const int* __restrict__ row_part_ptr, int row0, int n_rows, int part0) {
   using LL = LsLayout<128>;
   constexpr int PF = LL::SIZE + 128;
   extern __shared__ __align__(16) float fsm128[];
-  float* slot = fsm128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* slot = fsm128 + warp * FIN128_FLOATS;
   float* bv = slot + LL::STRIDE;
   float* colbuf = bv + 128;
-  const int lane = threadIdx.x & 31;
 #pragma unroll 1
-  for (int rr = blockIdx.x; rr < n_rows; rr += gridDim.x) {
-    const int r = row0 + rr;
-    const int p0 = row_part_ptr[r] - part0, p1 = row_part_ptr[r + 1] - part0;
-    for (int o = lane; o < PF / 4; o += 32) {
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int q = p0; q < p1; ++q) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p.partial + (size_t)q * PF) + o);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  for (int base = blockIdx.x * FIN128_WARPS; base < n_rows; base += gridDim.x * FIN128_WARPS) {
+    const int rr = base + warp;
+    const bool have = rr < n_rows;
+    const int r = row0 + (have ? rr : 0);
+    if (have) {
+      const int p0 = row_part_ptr[r] - part0, p1 = row_part_ptr[r + 1] - part0;
+      for (int o = lane; o < PF / 4; o += 32) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = p0; q < p1; ++q) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(p.partial + (size_t)q * PF) + o);
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        if (o < LL::SIZE / 4) reinterpret_cast<float4*>(slot)[o] = s;
+        else reinterpret_cast<float4*>(bv)[o - LL::SIZE / 4] = s;
       }
-      if (o < LL::SIZE / 4) reinterpret_cast<float4*>(slot)[o] = s;
-      else reinterpret_cast<float4*>(bv)[o - LL::SIZE / 4] = s;
     }
-    __syncwarp();
-    chol_lockstep<128, IMPLICIT>(slot, bv, p.yty, p.lambda * p.nreg[r], p.k, colbuf,
-                                 p.dst + (size_t)(p.dst_row_offset + r) * 128, true, p.fail);
-    __syncwarp();
+    __syncthreads();
+    if (have)
+      chol_lockstep<128, IMPLICIT>(slot, bv, p.yty, p.lambda * p.nreg[r], p.k, colbuf,
+                                   p.dst + (size_t)(p.dst_row_offset + r) * 128, true, p.fail);
+    __syncthreads();
   }
 }
 

@@ -439,6 +439,9 @@ struct pio_als_handle {
   unsigned char* srv_host = nullptr;       // cudaHostAlloc(mapped)
   unsigned char* srv_host_dev = nullptr;   // its device address
   size_t srv_host_cap = 0;
+  unsigned* srv_counter = nullptr;         // arrival counter of score_one_kernel (zero between calls)
+  unsigned srv_seq = 0;                    // sequence number of the last fused single-query call
+  bool serve_fused = true;                 // PIO_ALS_SERVE_FUSED=0: single queries take the three-launch path
   bool tc_split = false;      // PIO_ALS_TC_SPLIT=1: the tensor-core kernel only accumulates, a second kernel solves (measured: no gain)
   float* tc_out = nullptr;    // split mode: normal equations of one tile of rows ([rows][ASLOT + KP])
   size_t tc_out_rows = 0;
@@ -1171,7 +1174,7 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
       if ((e = cudaMallocAsync((void**)&dst.partial, sizeof(float) * (size_t)mx * Cfg::PART_FLOATS, h->stream)) != cudaSuccess) return e;
     }
     static bool fattr[64] = {};
-    const size_t fsmem = sizeof(float) * (size_t)(LsLayout<128>::STRIDE + 128 + 80);
+    const size_t fsmem = sizeof(float) * (size_t)FIN128_FLOATS * FIN128_WARPS;
     if (h->cfg.device < 64 && !fattr[h->cfg.device]) {
       if ((e = cudaFuncSetAttribute(als_finish_ls128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)) != cudaSuccess) return e;
       if ((e = cudaFuncSetAttribute(als_finish_ls128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)) != cudaSuccess) return e;
@@ -1190,9 +1193,10 @@ static cudaError_t launch_solve_cfg(pio_als_handle* h, Side& dst, const Side& sr
       const int grid = (np + Cfg::NG - 1) / Cfg::NG;
       e = imp ? launch_solve_one<Cfg, true>(h, pp, grid, h->stream) : launch_solve_one<Cfg, false>(h, pp, grid, h->stream);
       if (e != cudaSuccess) return e;
-      int fgrid = r1 - r0 < 6 * h->sm_count ? r1 - r0 : 6 * h->sm_count;
-      if (imp) als_finish_ls128_kernel<true><<<fgrid, 32, fsmem, h->stream>>>(pp, dst.row_part_ptr, r0, r1 - r0, part0);
-      else als_finish_ls128_kernel<false><<<fgrid, 32, fsmem, h->stream>>>(pp, dst.row_part_ptr, r0, r1 - r0, part0);
+      int fgrid = (r1 - r0 + FIN128_WARPS - 1) / FIN128_WARPS;
+      if (fgrid > h->sm_count) fgrid = h->sm_count;
+      if (imp) als_finish_ls128_kernel<true><<<fgrid, 32 * FIN128_WARPS, fsmem, h->stream>>>(pp, dst.row_part_ptr, r0, r1 - r0, part0);
+      else als_finish_ls128_kernel<false><<<fgrid, 32 * FIN128_WARPS, fsmem, h->stream>>>(pp, dst.row_part_ptr, r0, r1 - r0, part0);
       LAUNCHED(h);
       ++h->st.solve_launches;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -1428,6 +1432,7 @@ static int create_common(pio_als_handle* h) {
     for (int i = 0; i < 8; ++i)
       if (cudaEventCreateWithFlags(&h->ev_piece[i], cudaEventDisableTiming) != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaEventCreate");
     h->n_pieces = h->cfg.world_size > 1 ? 4 : 1;
+    if (const char* v = getenv("PIO_ALS_SERVE_FUSED")) h->serve_fused = atoi(v) != 0;
     if (const char* v = getenv("PIO_ALS_PIECES")) {
       const int n = atoi(v);
       if (n >= 1 && n <= 8) h->n_pieces = n;
@@ -1522,6 +1527,7 @@ void pio_als_destroy(pio_als_handle* h) {
       if (h->ev_piece[i]) cudaEventDestroy(h->ev_piece[i]);
     if (h->srv_dev) cudaFree(h->srv_dev);
     if (h->srv_host) cudaFreeHost(h->srv_host);
+    if (h->srv_counter) cudaFree(h->srv_counter);
     if (h->aux) cudaStreamDestroy(h->aux);
     if (h->comm_st) cudaStreamDestroy(h->comm_st);
     cudaStreamDestroy(h->stream);
@@ -1861,6 +1867,104 @@ static int similar_small(pio_als_handle* h, const int32_t* query_items, int nq, 
   if (out_count) *out_count = *(int*)(h->srv_host + ho_c);
   return PIO_ALS_OK;
 }
+
+// ONE query in ONE launch (score_one_kernel): recommend for one user (cos = false, ids[0] = the user) or similar for
+// nq <= S1_MAXNV query items.  The host waits on a sequence flag in the mapped arena instead of a stream synchronisation.
+extern "C++" {
+template <bool COS, int NVP, int KPT>
+static void launch_score_one_kp(pio_als_handle* h, int gx, size_t smem, const Side& q, const OneQuery& qry, const uint8_t* d_mask,
+                                const double* d_weight, int keep, int topk, ScoreIdx* d_cand, int* m_oi, float* m_os, int* m_oc,
+                                unsigned* m_flag, unsigned seq) {
+  static size_t attr_smem[64] = {};
+  if (h->cfg.device < 64 && attr_smem[h->cfg.device] < smem) {
+    cudaFuncSetAttribute(score_one_kernel<COS, NVP, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_smem[h->cfg.device] = smem;
+  }
+  unsigned long long* g_thr = reinterpret_cast<unsigned long long*>(h->srv_counter + 2);
+  score_one_kernel<COS, NVP, KPT><<<gx, S1_THREADS, smem, h->stream>>>(
+      h->I.F, h->I.n_internal, h->cfg.rank, q.F, q.perm, q.deg, q.n, qry, h->I.cand_ext, d_mask, d_weight, keep, topk, d_cand,
+      h->srv_counter, g_thr, m_oi, m_os, m_oc, m_flag, seq);
+}
+template <bool COS, int NVP>
+static void launch_score_one(pio_als_handle* h, int gx, size_t smem, const Side& q, const OneQuery& qry, const uint8_t* d_mask,
+                             const double* d_weight, int keep, int topk, ScoreIdx* d_cand, int* m_oi, float* m_os, int* m_oc,
+                             unsigned* m_flag, unsigned seq) {
+  if (h->KP == 16) launch_score_one_kp<COS, NVP, 16>(h, gx, smem, q, qry, d_mask, d_weight, keep, topk, d_cand, m_oi, m_os, m_oc, m_flag, seq);
+  else if (h->KP == 32) launch_score_one_kp<COS, NVP, 32>(h, gx, smem, q, qry, d_mask, d_weight, keep, topk, d_cand, m_oi, m_os, m_oc, m_flag, seq);
+  else launch_score_one_kp<COS, NVP, 64>(h, gx, smem, q, qry, d_mask, d_weight, keep, topk, d_cand, m_oi, m_os, m_oc, m_flag, seq);
+}
+}  // extern "C++"
+
+static bool serve_one_ok(const pio_als_handle* h, int nq, int topk) {
+  return h->serve_fused && h->KP <= 64 && topk <= TK_MAXK && nq >= 1 && nq <= S1_MAXNV;
+}
+
+static int serve_one(pio_als_handle* h, bool cos, const int32_t* ids, int nq, int topk, const uint8_t* item_mask,
+                     const double* item_weight, int flags, int32_t* out_items, float* out_scores, int32_t* out_count) {
+  cudaStream_t st = h->stream;
+  const int KP = h->KP;
+  const int ntiles = (h->I.n_internal + S1_THREADS - 1) / S1_THREADS;
+  int gx = h->sm_count < ntiles ? h->sm_count : ntiles;
+  if (gx > S1_THREADS) gx = S1_THREADS;   // the list merge reads one list head per thread
+  if (gx < 1) gx = 1;
+  const int nvp = !cos ? 1 : nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : 8;
+  const size_t o_cand = 0, o_mask = al256(sizeof(ScoreIdx) * (size_t)gx * topk),
+               o_w = al256(o_mask + (item_mask ? (size_t)h->I.n : 0)),
+               dev_bytes = al256(o_w + (item_weight ? sizeof(double) * (size_t)h->I.n : 0));
+  const size_t ho_i = 0, ho_s = al256(sizeof(int) * (size_t)topk), ho_c = ho_s + al256(sizeof(float) * (size_t)topk),
+               ho_flag = ho_c + 256, host_bytes = ho_flag + 256;
+  const bool fresh_host = h->srv_host_cap < host_bytes;
+  int rc = serve_reserve(h, dev_bytes, host_bytes);
+  if (rc) return rc;
+  if (fresh_host) memset(h->srv_host, 0, h->srv_host_cap);
+  if (!h->srv_counter) {
+    CK(h, cudaMalloc((void**)&h->srv_counter, 256));
+    CK(h, cudaMemsetAsync(h->srv_counter, 0, 256, st));
+  }
+  ScoreIdx* d_cand = (ScoreIdx*)(h->srv_dev + o_cand);
+  uint8_t* d_mask = item_mask ? h->srv_dev + o_mask : nullptr;
+  double* d_weight = item_weight ? (double*)(h->srv_dev + o_w) : nullptr;
+  if (item_mask) CK(h, cudaMemcpyAsync(d_mask, item_mask, (size_t)h->I.n, cudaMemcpyHostToDevice, st));
+  if (item_weight) CK(h, cudaMemcpyAsync(d_weight, item_weight, sizeof(double) * (size_t)h->I.n, cudaMemcpyHostToDevice, st));
+  OneQuery qry;
+  qry.nq = nq;
+  for (int t = 0; t < S1_MAXNV; ++t) qry.ids[t] = t < nq ? ids[t] : -1;
+  const unsigned seq = ++h->srv_seq ? h->srv_seq : ++h->srv_seq;   // never 0: a fresh arena reads 0
+  volatile unsigned* flag = (volatile unsigned*)(h->srv_host + ho_flag);
+  int* m_oi = (int*)(h->srv_host_dev + ho_i);
+  float* m_os = (float*)(h->srv_host_dev + ho_s);
+  int* m_oc = (int*)(h->srv_host_dev + ho_c);
+  unsigned* m_flag = (unsigned*)(h->srv_host_dev + ho_flag);
+  const size_t smem = s1_smem_bytes(KP, nvp, topk);
+  const int keep = (flags & PIO_ALS_SIM_KEEP_QUERY_ITEMS) ? 1 : 0;
+  const Side& q = cos ? h->I : h->U;
+#define PIO_S1(C, N) launch_score_one<C, N>(h, gx, smem, q, qry, d_mask, d_weight, keep, topk, d_cand, m_oi, m_os, m_oc, m_flag, seq)
+  if (!cos) PIO_S1(false, 1);
+  else if (nvp == 1) PIO_S1(true, 1);
+  else if (nvp == 2) PIO_S1(true, 2);
+  else if (nvp == 4) PIO_S1(true, 4);
+  else PIO_S1(true, 8);
+#undef PIO_S1
+  LAUNCHED(h);
+  CK(h, cudaGetLastError());
+  for (unsigned spins = 1; *flag != seq; ++spins) {
+    if ((spins & 0x3FFFu) == 0) {   // a faulted kernel never writes the flag: ask the stream now and then
+      const cudaError_t e = cudaStreamQuery(st);
+      if (e != cudaErrorNotReady) {
+        if (e != cudaSuccess) CK(h, e);
+        if (*flag != seq) return fail(h, PIO_ALS_ERR_CUDA, "single-query kernel finished without publishing its result");
+      }
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  memcpy(out_items, h->srv_host + ho_i, sizeof(int) * (size_t)topk);
+  memcpy(out_scores, h->srv_host + ho_s, sizeof(float) * (size_t)topk);
+  if (out_count) *out_count = *(int*)(h->srv_host + ho_c);
+  return PIO_ALS_OK;
+}
 }  // namespace pio
 
 // Scoring passes: at most TK_MAXK results per pass; a query asking for more runs further passes, each bounded by the last
@@ -1874,7 +1978,9 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
   std::lock_guard<std::mutex> lk(h->mu);
   if (!h->U.F || !h->I.F || !h->I.cand_ext) return fail(h, PIO_ALS_ERR_STATE, "no model");
   CK(h, cudaSetDevice(h->cfg.device));
-  if (n <= SB_QB && topk <= TK_MAXK)   // the serving case: one or a few queries
+  if (n == 1 && serve_one_ok(h, 1, topk))   // the serving case: one query, one launch
+    return serve_one(h, false, users, 1, topk, item_mask, item_weight, 0, out_items, out_scores, out_count);
+  if (n <= SB_QB && topk <= TK_MAXK)   // a few queries
     return recommend_small(h, users, n, topk, item_mask, item_weight, out_items, out_scores, out_count);
   cudaStream_t st = h->stream;
   const int KP = h->KP;
@@ -2040,7 +2146,10 @@ int pio_als_similar_batch(pio_als_handle* h, const int64_t* q_ptr, const int32_t
   std::lock_guard<std::mutex> lk(h->mu);
   if (!h->I.F || !h->I.cand_ext) return fail(h, PIO_ALS_ERR_STATE, "no model");
   CK(h, cudaSetDevice(h->cfg.device));
-  if (n_queries == 1 && q_ptr[1] - q_ptr[0] >= 1 && q_ptr[1] - q_ptr[0] <= SM_NV && topk <= TK_MAXK)   // the serving case
+  if (n_queries == 1 && serve_one_ok(h, (int)std::min<long long>(q_ptr[1] - q_ptr[0], 1 << 20), topk))   // the serving case
+    return serve_one(h, true, q_items + q_ptr[0], (int)(q_ptr[1] - q_ptr[0]), topk, item_mask, item_weight, flags, out_items,
+                     out_scores, out_count);
+  if (n_queries == 1 && q_ptr[1] - q_ptr[0] >= 1 && q_ptr[1] - q_ptr[0] <= SM_NV && topk <= TK_MAXK)
     return similar_small(h, q_items + q_ptr[0], (int)(q_ptr[1] - q_ptr[0]), topk, item_mask, item_weight, flags, out_items,
                          out_scores, out_count);
   Scratch tmp(h);

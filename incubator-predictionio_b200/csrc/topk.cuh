@@ -658,6 +658,391 @@ topk_merge_kernel(const ScoreIdx* __restrict__ cand, int n_cand, int topk, int o
   }
 }
 
+// ---- one query, one launch (serving latency) -----------------------------------------------------------------------
+// The whole predict call of a deployed engine for ONE query (ALSModel.recommendProducts for a user; the similarproduct
+// cosine scan for <= S1_MAXNV query items) as a single kernel: the query rows are looked up by the CTAs themselves (ids
+// travel in the kernel parameters); one persistent CTA per SM streams its share of the item matrix; inside the CTA every
+// warp is independent -- it stages its own 32 rows per step through its own three-stage cp.async ring (padded rows,
+// conflict-free LDS.128 per thread), scores them and keeps its own top-k pool, with no CTA barrier in the scan; a score
+// below the smallest entry of ANY full pool (shared through shared / global memory) never reaches a pool; the eight
+// pools of a CTA are merged by rank counting; the last CTA to finish (device counter) merges the per-CTA lists and
+// writes the result straight into mapped host memory, followed by a sequence flag the host polls.  Arithmetic and
+// tie-breaking are those of the batched kernels above (fp64 in index order, better()): results are bit-identical.
+constexpr int S1_THREADS = 256;
+constexpr int S1_STAGES = 3;
+constexpr int S1_MAXNV = 8;
+struct OneQuery {
+  int nq;
+  int ids[S1_MAXNV];   // external ids (COS: the query items; dot: ids[0] = the user)
+};
+__host__ __device__ inline size_t s1_smem_bytes(int kp, int nvp, int topk) {
+  return sizeof(double) * ((size_t)kp * nvp + S1_MAXNV) + sizeof(float) * (size_t)S1_STAGES * S1_THREADS * (kp + 4) +
+         (sizeof(double) + sizeof(int)) * (size_t)(S1_THREADS / 32) * topk + 128;
+}
+// n_lists lists of topk candidates each, every list best first and padded with i = -1 -> the best topk overall.
+// Only candidates at least as good as the topk-th best list head can make it: those few are collected in `surv` (shared
+// memory, capacity cap) and ordered by rank counting.  All S1_THREADS threads call; returns the number of results.
+template <typename Emit>
+__device__ __forceinline__ int s1_merge_lists(const ScoreIdx* c, int n_lists, int topk, ScoreIdx* surv, int cap, int* s_int,
+                                              double* s_dbl, Emit emit) {
+  const int tid = threadIdx.x;
+  // s_int[0] = survivors, s_int[1] = id of the threshold head (or -1: keep everything), s_dbl[0] = its score
+  if (tid == 0) { s_int[0] = 0; s_int[1] = -1; }
+  __syncthreads();
+  double hs_ = 0.0;
+  int hi_ = -1;
+  if (tid < n_lists) {
+    hs_ = __ldcg(&c[(size_t)tid * topk].s);
+    hi_ = __ldcg(&c[(size_t)tid * topk].i);
+  }
+  surv[tid].s = hs_;      // heads, exchanged through the survivor buffer (cap >= S1_THREADS)
+  surv[tid].i = hi_;
+  __syncthreads();
+  if (hi_ >= 0) {
+    int rank = 0;
+    for (int l = 0; l < n_lists; ++l) {
+      const int oi = surv[l].i;
+      rank += (oi >= 0 && better(surv[l].s, oi, hs_, hi_)) ? 1 : 0;
+    }
+    if (rank == topk - 1) { s_int[1] = hi_; s_dbl[0] = hs_; }
+  }
+  __syncthreads();
+  const int ti = s_int[1];
+  const double ts = s_dbl[0];
+  __syncthreads();          // the heads have been read: the buffer now collects survivors
+  const int n_cand = n_lists * topk;
+  for (int o = tid; o < n_cand; o += S1_THREADS) {
+    const double sv = __ldcg(&c[o].s);
+    const int id = __ldcg(&c[o].i);
+    if (id >= 0 && (ti < 0 || !better(ts, ti, sv, id))) {
+      const int at = atomicAdd(&s_int[0], 1);
+      if (at < cap) { surv[at].s = sv; surv[at].i = id; }
+    }
+  }
+  __syncthreads();
+  const int m = s_int[0];
+  if (m > cap) return -1;   // (adversarial input) the caller takes the pool path
+  for (int t = tid; t < m; t += S1_THREADS) {
+    const double sv = surv[t].s;
+    const int id = surv[t].i;
+    int rank = 0;
+    for (int u = 0; u < m; ++u) rank += better(surv[u].s, surv[u].i, sv, id) ? 1 : 0;
+    if (rank < topk) emit(rank, sv, id);
+  }
+  return m < topk ? m : topk;
+}
+
+// merge through per-warp pools (the CTA's own eight pools when c == nullptr: wcnt[] is already set)
+template <typename Emit>
+__device__ __forceinline__ int s1_merge(const ScoreIdx* c, int n_cand, int topk, double* hs, int* hi, int* wcnt, Emit emit) {
+  constexpr int NW = S1_THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (c) {
+    WarpPool wp;
+    wp.thr = 0.0; wp.wid = -1; wp.worst = 0; wp.cnt = 0;
+    for (int base = warp * 32; base < n_cand; base += S1_THREADS) {
+      const int o = base + lane;
+      double s = 0.0;
+      int i = -1;
+      if (o < n_cand) {
+        s = __ldcg(&c[o].s);
+        i = __ldcg(&c[o].i);
+      }
+      wpool_offer(wp, i >= 0, s, i, topk, hs + warp * topk, hi + warp * topk);
+    }
+    if (lane == 0) wcnt[warp] = wp.cnt;
+  }
+  __syncthreads();
+  int total = 0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) total += wcnt[w];
+  for (int t = threadIdx.x; t < NW * topk; t += S1_THREADS) {
+    const int w = t / topk, j = t % topk;
+    if (j >= wcnt[w]) continue;
+    const double s = hs[t];
+    const int id = hi[t];
+    int rank = 0;
+    for (int w2 = 0; w2 < NW; ++w2)
+      for (int u = 0; u < wcnt[w2]; ++u) rank += better(hs[w2 * topk + u], hi[w2 * topk + u], s, id) ? 1 : 0;
+    if (rank < topk) emit(rank, s, id);
+  }
+  return total < topk ? total : topk;
+}
+
+// A top-k pool kept SORTED in the registers of one warp: entry g (0 = best) lives in lane g % 32, slot g / 32.  An
+// insertion is one position count (ballots) and one shift (shuffles) -- no search for the worst entry; the threshold is
+// entry topk - 1.  Warp-uniform: cnt.  All 32 lanes call offer(); candidates are taken in lane order.
+struct SortedPool {
+  static constexpr int SLOTS = TK_MAXK / 32;
+  double s[SLOTS];
+  int i[SLOTS];
+  int cnt;
+  double thr;   // score and id of entry topk - 1 once cnt == topk
+  int tid_;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) { s[q] = 0.0; i[q] = -1; }
+    cnt = 0; thr = 0.0; tid_ = -1;
+  }
+  __device__ __forceinline__ void insert(double cs, int ce, int topk) {
+    const int lane = threadIdx.x & 31;
+    const int nslot = (topk + 31) >> 5;
+    int p = 0;   // entries better than the candidate = its position
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q)
+      if (q < nslot) p += __popc(__ballot_sync(0xffffffffu, q * 32 + lane < cnt && better(s[q], i[q], cs, ce)));
+    double carry_s = 0.0;   // lane 31 of the previous slot (moves into lane 0 of this one)
+    int carry_i = -1;
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q)
+      if (q < nslot) {
+        double us = __shfl_up_sync(0xffffffffu, s[q], 1);
+        int ui = __shfl_up_sync(0xffffffffu, i[q], 1);
+        const double last_s = __shfl_sync(0xffffffffu, s[q], 31);
+        const int last_i = __shfl_sync(0xffffffffu, i[q], 31);
+        if (lane == 0) { us = carry_s; ui = carry_i; }
+        const int g = q * 32 + lane;
+        if (g == p) { s[q] = cs; i[q] = ce; }
+        else if (g > p) { s[q] = us; i[q] = ui; }
+        carry_s = last_s;
+        carry_i = last_i;
+      }
+    if (cnt < topk) ++cnt;
+    if (cnt == topk) {
+      const int q = (topk - 1) >> 5, l = (topk - 1) & 31;
+      double ts = 0.0;
+      int ti = -1;
+#pragma unroll
+      for (int qq = 0; qq < SLOTS; ++qq)
+        if (qq == q) { ts = s[qq]; ti = i[qq]; }
+      thr = __shfl_sync(0xffffffffu, ts, l);
+      tid_ = __shfl_sync(0xffffffffu, ti, l);
+    }
+  }
+  __device__ __forceinline__ void offer(bool want, double sc, int ext, int topk) {
+    want = want && (cnt < topk || sc >= thr);
+    unsigned m = __ballot_sync(0xffffffffu, want);
+    while (m) {
+      const int leader = __ffs(m) - 1;
+      m &= m - 1;
+      const double cs = __shfl_sync(0xffffffffu, sc, leader);
+      const int ce = __shfl_sync(0xffffffffu, ext, leader);
+      if (cnt < topk || better(cs, ce, thr, tid_)) insert(cs, ce, topk);
+    }
+  }
+  // entries to shared memory ([topk] each), best first
+  __device__ __forceinline__ void dump(int topk, double* ps, int* pi) const {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+      const int g = q * 32 + lane;
+      if (g < cnt) { ps[g] = s[q]; pi[g] = i[q]; }
+    }
+  }
+};
+
+// order-preserving map double -> unsigned 64-bit (a < b  <=>  key(a) < key(b)); key 0 is below every score
+__device__ __forceinline__ unsigned long long s1_key(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+template <bool COS, int NVP, int KP>
+__global__ void __launch_bounds__(S1_THREADS, 1)
+score_one_kernel(const float* __restrict__ Y, int n_items, int k, const float* __restrict__ Q,
+                 const int* __restrict__ q_perm, const uint32_t* __restrict__ q_deg, int q_n_ext, const OneQuery qry,
+                 const int* __restrict__ cand_ext, const uint8_t* __restrict__ mask, const double* __restrict__ weight,
+                 int keep_query, int topk, ScoreIdx* __restrict__ cand, unsigned* __restrict__ counter,
+                 unsigned long long* __restrict__ g_thr,
+                 int* __restrict__ out_items, float* __restrict__ out_scores, int* __restrict__ out_count,
+                 volatile unsigned* __restrict__ done_flag, unsigned seq) {
+  constexpr int NW = S1_THREADS / 32;
+  constexpr int ROW = KP + 4;                 // floats per staged row: 16 bytes of skew -> conflict-free LDS.128 per thread
+  constexpr int F4 = KP / 4;                  // 16-byte chunks per row
+  extern __shared__ __align__(16) unsigned char s1_smem[];
+  double* xd = reinterpret_cast<double*>(s1_smem);                       // [KP][NVP]
+  double* s1 = xd + (size_t)KP * NVP;                                     // [S1_MAXNV]
+  float* tiles = reinterpret_cast<float*>(s1 + S1_MAXNV);                // [NW][S1_STAGES][32][ROW]
+  double* hs = reinterpret_cast<double*>(tiles + (size_t)S1_STAGES * S1_THREADS * ROW);   // [NW][topk]
+  int* hi = reinterpret_cast<int*>(hs + (size_t)NW * topk);              // [NW][topk]
+  int* wcnt = hi + (size_t)NW * topk;                                     // [NW]
+  int* s_int = wcnt + NW;                                                 // [4]
+  double* s_dbl = reinterpret_cast<double*>(s_int + 4);                  // [1]
+  __shared__ unsigned long long s_thr;        // key of the CTA's pruning threshold (0 = none yet)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntiles = (n_items + S1_THREADS - 1) / S1_THREADS;
+  const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  float* ring = tiles + (size_t)warp * S1_STAGES * 32 * ROW;
+  // step j of this warp: rows base(j) .. base(j) + 31 -> ring slot j % S1_STAGES; one commit group per step (empty past the end)
+  auto base_of = [&](int j) { return (((int)blockIdx.x + j * (int)gridDim.x) * NW + warp) * 32; };
+  auto fetch = [&](int j) {
+    if (j < my_tiles) {
+      const int base = base_of(j);
+      float* slot = ring + (size_t)(j % S1_STAGES) * 32 * ROW;
+#pragma unroll
+      for (int m = 0; m < F4; ++m) {        // a warp copies 512 contiguous bytes per instruction
+        const int o = lane + m * 32, r = o / F4, c4 = o % F4;
+        if (base + r < n_items) sb_cp_async16(slot + (size_t)r * ROW + c4 * 4, Y + (size_t)(base + r) * KP + c4 * 4);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+#pragma unroll
+  for (int s = 0; s < S1_STAGES - 1; ++s) fetch(s);
+  if (tid == 0) s_thr = 0ull;
+  // the query: rows looked up by external id; an id without a factor enters as a zero vector (its cosine terms are 0)
+  for (int o = tid; o < KP * NVP; o += S1_THREADS) {
+    const int c = o / NVP, t = o % NVP;
+    const int id = t < qry.nq ? qry.ids[t] : -1;
+    const bool ok = id >= 0 && id < q_n_ext && q_deg[id] > 0;
+    xd[o] = ok ? (double)Q[(size_t)q_perm[id] * KP + c] : 0.0;
+  }
+  bool qvalid;
+  {
+    const int id = qry.ids[0];
+    qvalid = qry.nq > 0 && id >= 0 && id < q_n_ext && q_deg[id] > 0;   // dot: an unknown user has no recommendations
+  }
+  __syncthreads();
+  if (COS && tid < S1_MAXNV) {
+    double n1 = 0.0;
+    if (tid < NVP)
+      for (int c = 0; c < k; ++c) {
+        const double a = xd[(size_t)c * NVP + tid];
+        n1 += a * a;
+      }
+    s1[tid] = sqrt(n1);
+  }
+  __syncthreads();
+  double s1r[NVP];
+#pragma unroll
+  for (int t = 0; t < NVP; ++t) s1r[t] = COS ? s1[t] : 0.0;
+  SortedPool wp;
+  wp.init();
+  int ext_next = -1;
+  if (my_tiles > 0) {
+    const int i0 = base_of(0) + lane;
+    ext_next = i0 < n_items ? __ldg(cand_ext + i0) : -1;
+  }
+  for (int j = 0; j < my_tiles; ++j) {
+    int ext = ext_next;
+    if (j + 1 < my_tiles) {
+      const int in = base_of(j + 1) + lane;
+      ext_next = in < n_items ? __ldg(cand_ext + in) : -1;
+    }
+    if (ext >= 0 && mask && mask[ext]) ext = -1;
+    unsigned long long gthr = 0ull;
+    if (lane == 0) gthr = __ldcg(g_thr);   // consumed after the row has been scored: the load latency hides behind it
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(S1_STAGES - 2));
+    __syncwarp();               // step j has landed for the whole warp; slot (j - 1) % S1_STAGES has been consumed
+    fetch(j + S1_STAGES - 1);
+    double score = 0.0;
+    if (ext >= 0) {
+      const float4* yrow = reinterpret_cast<const float4*>(ring + ((size_t)(j % S1_STAGES) * 32 + lane) * ROW);
+      double d[NVP];
+#pragma unroll
+      for (int t = 0; t < NVP; ++t) d[t] = 0.0;
+      double n2 = 0.0;
+#pragma unroll 4
+      for (int c4 = 0; c4 < F4; ++c4) {
+        const float4 y4 = yrow[c4];
+        const double yd[4] = {(double)y4.x, (double)y4.y, (double)y4.z, (double)y4.w};
+        if (NVP == 1) {
+          const double2 xa = *reinterpret_cast<const double2*>(xd + c4 * 4);
+          const double2 xb = *reinterpret_cast<const double2*>(xd + c4 * 4 + 2);
+          const double xe[4] = {xa.x, xa.y, xb.x, xb.y};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (COS) n2 = fma(yd[e], yd[e], n2);
+            d[0] = fma(xe[e], yd[e], d[0]);          // index order, like blas.ddot over Array[Double]
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (COS) n2 = fma(yd[e], yd[e], n2);
+            const double2* xr = reinterpret_cast<const double2*>(xd + (size_t)(c4 * 4 + e) * NVP);
+#pragma unroll
+            for (int t = 0; t < NVP; t += 2) {
+              const double2 x2 = xr[t / 2];
+              d[t] = fma(x2.x, yd[e], d[t]);
+              d[t + (NVP > 1 ? 1 : 0)] = fma(x2.y, yd[e], d[t + (NVP > 1 ? 1 : 0)]);
+            }
+          }
+        }
+      }
+      if (COS) {
+        const double s2 = sqrt(n2);
+#pragma unroll
+        for (int t = 0; t < NVP; ++t)
+          if (t < qry.nq) {
+            const double n1n2 = s1r[t] * s2;
+            score += (n1n2 == 0.0) ? 0.0 : d[t] / n1n2;   // query order
+          }
+      } else {
+        score = d[0];
+      }
+      if (weight) score = score * weight[ext];
+    }
+    bool want = ext >= 0 && (COS ? score > 0.0 : qvalid);
+    if (COS && want && !keep_query) {
+#pragma unroll
+      for (int t = 0; t < S1_MAXNV; ++t)
+        if (t < qry.nq && qry.ids[t] == ext) want = false;
+    }
+    if (lane == 0 && gthr) atomicMax(&s_thr, gthr);
+    want = want && s1_key(score) >= *reinterpret_cast<volatile unsigned long long*>(&s_thr);
+    if (__any_sync(0xffffffffu, want)) {
+      const double thr0 = wp.thr;
+      const int cnt0 = wp.cnt;
+      wp.offer(want, score, ext, topk);
+      if (lane == 0 && wp.cnt == topk && (cnt0 < topk || wp.thr != thr0)) {
+        const unsigned long long key = s1_key(wp.thr);
+        if (atomicMax(&s_thr, key) < key) atomicMax(g_thr, key);
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  wp.dump(topk, hs + (size_t)warp * topk, hi + (size_t)warp * topk);
+  if (lane == 0) wcnt[warp] = wp.cnt;
+  // the CTA's own list: topk entries best first, empty slots marked
+  ScoreIdx* mine = cand + (size_t)blockIdx.x * topk;
+  const int got = s1_merge(nullptr, 0, topk, hs, hi, wcnt, [&](int rank, double s, int id) {
+    mine[rank].s = s;
+    mine[rank].i = id;
+  });
+  for (int t = got + tid; t < topk; t += S1_THREADS) {
+    mine[t].s = 0.0;
+    mine[t].i = -1;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_int[2] = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_int[2]) return;
+  __threadfence();   // the scan is over everywhere: the staging rings are free to hold the survivors
+  auto publish = [&](int rank, double s, int id) {
+    out_items[rank] = id;
+    out_scores[rank] = (float)s;
+  };
+  constexpr int CAP = (int)(sizeof(float) * S1_STAGES * S1_THREADS * ROW / sizeof(ScoreIdx));
+  int cnt = s1_merge_lists(cand, (int)gridDim.x, topk, reinterpret_cast<ScoreIdx*>(tiles), CAP, s_int, s_dbl, publish);
+  if (cnt < 0) {
+    __syncthreads();
+    cnt = s1_merge(cand, (int)gridDim.x * topk, topk, hs, hi, wcnt, publish);
+  }
+  for (int t = cnt + tid; t < topk; t += S1_THREADS) {
+    out_items[t] = -1;
+    out_scores[t] = 0.f;
+  }
+  if (tid == 0) {
+    *out_count = cnt;
+    *counter = 0u;
+    *g_thr = 0ull;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) *done_flag = seq;
+}
+
 // ------------------------------------------------------------------------------------------
 // NaiveBayes: per-class counts and feature sums (fp64), deterministic two-stage reduction.
 // partial: [gridDim.x][n_class * (n_feat + 1)]  (slot n_feat = count)

@@ -354,6 +354,55 @@ def test_scoring_weights_query_items_large_topk_and_batch(native, oracle):
     assert gc[0] == 0
 
 
+def test_single_query_fused_launch_is_bit_exact(native, oracle, monkeypatch):
+    """The serving case (one user / one similar query of <= 8 items, topk <= 128) runs as ONE kernel that looks the query
+    up, scans, selects and publishes the result through mapped host memory; it must agree bit for bit with the oracle
+    and with the three-launch path (PIO_ALS_SERVE_FUSED=0).  120 k items x rank 32: several tiles per CTA, so the
+    staging ring wraps; rank 64 covers the widest rows the fused path takes."""
+    rng = np.random.default_rng(21)
+    for k, ni in ((32, 120_000), (64, 40_000), (10, 700)):
+        nu = 500
+        itf = synth.synth_init_factors(ni, k, 3, 1)
+        itf *= (1.0 + (np.arange(ni, dtype=np.float32) % 89)[:, None] / 89.0)
+        uf = synth.synth_init_factors(nu, k, 4, 0)
+        ih = (np.arange(ni) % 11 != 3).astype(np.uint8)
+        uh = (np.arange(nu) % 5 != 2).astype(np.uint8)
+        m = native.NativeALS.from_factors(uf, itf, uh, ih)
+        monkeypatch.setenv("PIO_ALS_SERVE_FUSED", "0")
+        m0 = native.NativeALS.from_factors(uf, itf, uh, ih)
+        monkeypatch.delenv("PIO_ALS_SERVE_FUSED")
+        w = np.ones(ni, np.float64)
+        w[rng.integers(0, ni, 200)] = rng.choice([0.0, 0.5, 2.0, -1.0], 200)
+        mask = (np.arange(ni) % 7 == 0).astype(np.uint8)
+        have, miss = np.flatnonzero(ih), np.flatnonzero(ih == 0)
+        for topk in (1, 10, 128):
+            for mk, wt in ((None, None), (mask, w)):
+                for user in (0, 1, 2, nu - 1, -1):
+                    us = np.array([user], np.int32)
+                    g = m.recommend(us, topk, mk, wt)
+                    o_ = oracle.recommend(uf, uh, itf, ih, us, topk, mk, wt)
+                    for a, b, c in zip(g, o_, m0.recommend(us, topk, mk, wt)):
+                        assert np.array_equal(a, b) and np.array_equal(a, c), (k, topk, user)
+                for nq in (1, 2, 3, 5, 8):
+                    q = rng.choice(have, nq, replace=False).astype(np.int32)
+                    if nq >= 3:
+                        q[1] = miss[0]          # an item without a factor: a zero vector, still excluded from the result
+                    for keep in (False, True):
+                        gi, gs, gc = m.similar(q, topk, mk, wt, keep_query_items=keep)
+                        oi, os_, oc = oracle.similar(itf, ih, q, topk, mk, wt, keep)
+                        zi, zs, zc = m0.similar(q, topk, mk, wt, keep_query_items=keep)
+                        assert gc == oc == zc and np.array_equal(gi, oi) and np.array_equal(gs, os_), (k, topk, nq, keep)
+                        assert np.array_equal(gi, zi) and np.array_equal(gs, zs)
+        # repeated calls reuse the arena and the arrival counter
+        q = have[:2].astype(np.int32)
+        first = m.similar(q, 10)
+        for _ in range(50):
+            again = m.similar(q, 10)
+            assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1])
+        m.close()
+        m0.close()
+
+
 def test_load_rejects_corrupt_files(native, tmp_path):
     nu, ni = 50, 40
     u, i, r = synth.synth_ratings(nu, ni, 800, seed=8, implicit=False)
