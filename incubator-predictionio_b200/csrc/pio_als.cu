@@ -442,6 +442,7 @@ struct pio_als_handle {
   unsigned* srv_counter = nullptr;         // arrival counter of score_one_kernel (zero between calls)
   unsigned srv_seq = 0;                    // sequence number of the last fused single-query call
   bool serve_fused = true;                 // PIO_ALS_SERVE_FUSED=0: single queries take the three-launch path
+  bool serve_trace = false;                // PIO_ALS_SERVE_TRACE=1: per-phase device timestamps of every fused call on stderr
   bool tc_split = false;      // PIO_ALS_TC_SPLIT=1: the tensor-core kernel only accumulates, a second kernel solves (measured: no gain)
   float* tc_out = nullptr;    // split mode: normal equations of one tile of rows ([rows][ASLOT + KP])
   size_t tc_out_rows = 0;
@@ -1433,6 +1434,7 @@ static int create_common(pio_als_handle* h) {
       if (cudaEventCreateWithFlags(&h->ev_piece[i], cudaEventDisableTiming) != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaEventCreate");
     h->n_pieces = h->cfg.world_size > 1 ? 4 : 1;
     if (const char* v = getenv("PIO_ALS_SERVE_FUSED")) h->serve_fused = atoi(v) != 0;
+    if (const char* v = getenv("PIO_ALS_SERVE_TRACE")) h->serve_trace = atoi(v) != 0;
     if (const char* v = getenv("PIO_ALS_PIECES")) {
       const int n = atoi(v);
       if (n >= 1 && n <= 8) h->n_pieces = n;
@@ -1874,7 +1876,7 @@ extern "C++" {
 template <bool COS, int NVP, int KPT>
 static void launch_score_one_kp(pio_als_handle* h, int gx, size_t smem, const Side& q, const OneQuery& qry, const uint8_t* d_mask,
                                 const double* d_weight, int keep, int topk, ScoreIdx* d_cand, int* m_oi, float* m_os, int* m_oc,
-                                unsigned* m_flag, unsigned seq) {
+                                unsigned* m_flag, unsigned seq, unsigned long long* m_trace) {
   static size_t attr_smem[64] = {};
   if (h->cfg.device < 64 && attr_smem[h->cfg.device] < smem) {
     cudaFuncSetAttribute(score_one_kernel<COS, NVP, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1883,15 +1885,15 @@ static void launch_score_one_kp(pio_als_handle* h, int gx, size_t smem, const Si
   unsigned long long* g_thr = reinterpret_cast<unsigned long long*>(h->srv_counter + 2);
   score_one_kernel<COS, NVP, KPT><<<gx, S1_THREADS, smem, h->stream>>>(
       h->I.F, h->I.n_internal, h->cfg.rank, q.F, q.perm, q.deg, q.n, qry, h->I.cand_ext, d_mask, d_weight, keep, topk, d_cand,
-      h->srv_counter, g_thr, m_oi, m_os, m_oc, m_flag, seq);
+      h->srv_counter, g_thr, m_oi, m_os, m_oc, m_flag, seq, m_trace);
 }
 template <bool COS, int NVP>
 static void launch_score_one(pio_als_handle* h, int gx, size_t smem, const Side& q, const OneQuery& qry, const uint8_t* d_mask,
                              const double* d_weight, int keep, int topk, ScoreIdx* d_cand, int* m_oi, float* m_os, int* m_oc,
-                             unsigned* m_flag, unsigned seq) {
-  if (h->KP == 16) launch_score_one_kp<COS, NVP, 16>(h, gx, smem, q, qry, d_mask, d_weight, keep, topk, d_cand, m_oi, m_os, m_oc, m_flag, seq);
-  else if (h->KP == 32) launch_score_one_kp<COS, NVP, 32>(h, gx, smem, q, qry, d_mask, d_weight, keep, topk, d_cand, m_oi, m_os, m_oc, m_flag, seq);
-  else launch_score_one_kp<COS, NVP, 64>(h, gx, smem, q, qry, d_mask, d_weight, keep, topk, d_cand, m_oi, m_os, m_oc, m_flag, seq);
+                             unsigned* m_flag, unsigned seq, unsigned long long* m_trace) {
+  if (h->KP == 16) launch_score_one_kp<COS, NVP, 16>(h, gx, smem, q, qry, d_mask, d_weight, keep, topk, d_cand, m_oi, m_os, m_oc, m_flag, seq, m_trace);
+  else if (h->KP == 32) launch_score_one_kp<COS, NVP, 32>(h, gx, smem, q, qry, d_mask, d_weight, keep, topk, d_cand, m_oi, m_os, m_oc, m_flag, seq, m_trace);
+  else launch_score_one_kp<COS, NVP, 64>(h, gx, smem, q, qry, d_mask, d_weight, keep, topk, d_cand, m_oi, m_os, m_oc, m_flag, seq, m_trace);
 }
 }  // extern "C++"
 
@@ -1912,7 +1914,7 @@ static int serve_one(pio_als_handle* h, bool cos, const int32_t* ids, int nq, in
                o_w = al256(o_mask + (item_mask ? (size_t)h->I.n : 0)),
                dev_bytes = al256(o_w + (item_weight ? sizeof(double) * (size_t)h->I.n : 0));
   const size_t ho_i = 0, ho_s = al256(sizeof(int) * (size_t)topk), ho_c = ho_s + al256(sizeof(float) * (size_t)topk),
-               ho_flag = ho_c + 256, host_bytes = ho_flag + 256;
+               ho_flag = ho_c + 256, ho_trace = ho_flag + 256, host_bytes = ho_trace + 256;
   const bool fresh_host = h->srv_host_cap < host_bytes;
   int rc = serve_reserve(h, dev_bytes, host_bytes);
   if (rc) return rc;
@@ -1938,7 +1940,9 @@ static int serve_one(pio_als_handle* h, bool cos, const int32_t* ids, int nq, in
   const size_t smem = s1_smem_bytes(KP, nvp, topk);
   const int keep = (flags & PIO_ALS_SIM_KEEP_QUERY_ITEMS) ? 1 : 0;
   const Side& q = cos ? h->I : h->U;
-#define PIO_S1(C, N) launch_score_one<C, N>(h, gx, smem, q, qry, d_mask, d_weight, keep, topk, d_cand, m_oi, m_os, m_oc, m_flag, seq)
+  unsigned long long* m_trace = h->serve_trace ? (unsigned long long*)(h->srv_host_dev + ho_trace) : nullptr;
+  const auto t_call = std::chrono::steady_clock::now();
+#define PIO_S1(C, N) launch_score_one<C, N>(h, gx, smem, q, qry, d_mask, d_weight, keep, topk, d_cand, m_oi, m_os, m_oc, m_flag, seq, m_trace)
   if (!cos) PIO_S1(false, 1);
   else if (nvp == 1) PIO_S1(true, 1);
   else if (nvp == 2) PIO_S1(true, 2);
@@ -1960,6 +1964,13 @@ static int serve_one(pio_als_handle* h, bool cos, const int32_t* ids, int nq, in
 #endif
   }
   __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  if (h->serve_trace) {
+    const unsigned long long* t = (const unsigned long long*)(h->srv_host + ho_trace);
+    const double host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_call).count();
+    fprintf(stderr, "pio serve trace: host launch->flag %.1f us; publishing CTA: query lookup %.1f us, first step %.1f us, rest of the scan "
+            "%.1f us, cta merge + arrival %.1f us, list merge %.1f us, system fence %.1f us\n", host_us, (t[5] - t[0]) * 1e-3,
+            (t[6] - t[5]) * 1e-3, (t[1] - t[6]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3);
+  }
   memcpy(out_items, h->srv_host + ho_i, sizeof(int) * (size_t)topk);
   memcpy(out_scores, h->srv_host + ho_s, sizeof(float) * (size_t)topk);
   if (out_count) *out_count = *(int*)(h->srv_host + ho_c);

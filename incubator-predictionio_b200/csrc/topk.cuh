@@ -700,6 +700,7 @@ __device__ __forceinline__ int s1_merge_lists(const ScoreIdx* c, int n_lists, in
   __syncthreads();
   if (hi_ >= 0) {
     int rank = 0;
+#pragma unroll 4
     for (int l = 0; l < n_lists; ++l) {
       const int oi = surv[l].i;
       rank += (oi >= 0 && better(surv[l].s, oi, hs_, hi_)) ? 1 : 0;
@@ -711,13 +712,25 @@ __device__ __forceinline__ int s1_merge_lists(const ScoreIdx* c, int n_lists, in
   const double ts = s_dbl[0];
   __syncthreads();          // the heads have been read: the buffer now collects survivors
   const int n_cand = n_lists * topk;
-  for (int o = tid; o < n_cand; o += S1_THREADS) {
-    const double sv = __ldcg(&c[o].s);
-    const int id = __ldcg(&c[o].i);
-    if (id >= 0 && (ti < 0 || !better(ts, ti, sv, id))) {
-      const int at = atomicAdd(&s_int[0], 1);
-      if (at < cap) { surv[at].s = sv; surv[at].i = id; }
+  for (int o0 = tid; o0 < n_cand; o0 += 8 * S1_THREADS) {   // eight loads in flight per thread
+    double sv[8];
+    int id[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int o = o0 + u * S1_THREADS;
+      id[u] = -1;
+      sv[u] = 0.0;
+      if (o < n_cand) {
+        sv[u] = __ldcg(&c[o].s);
+        id[u] = __ldcg(&c[o].i);
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (id[u] >= 0 && (ti < 0 || !better(ts, ti, sv[u], id[u]))) {
+        const int at = atomicAdd(&s_int[0], 1);
+        if (at < cap) { surv[at].s = sv[u]; surv[at].i = id[u]; }
+      }
   }
   __syncthreads();
   const int m = s_int[0];
@@ -726,6 +739,7 @@ __device__ __forceinline__ int s1_merge_lists(const ScoreIdx* c, int n_lists, in
     const double sv = surv[t].s;
     const int id = surv[t].i;
     int rank = 0;
+#pragma unroll 4
     for (int u = 0; u < m; ++u) rank += better(surv[u].s, surv[u].i, sv, id) ? 1 : 0;
     if (rank < topk) emit(rank, sv, id);
   }
@@ -762,8 +776,21 @@ __device__ __forceinline__ int s1_merge(const ScoreIdx* c, int n_cand, int topk,
     const double s = hs[t];
     const int id = hi[t];
     int rank = 0;
-    for (int w2 = 0; w2 < NW; ++w2)
-      for (int u = 0; u < wcnt[w2]; ++u) rank += better(hs[w2 * topk + u], hi[w2 * topk + u], s, id) ? 1 : 0;
+    if (c) {
+      for (int w2 = 0; w2 < NW; ++w2)
+        for (int u = 0; u < wcnt[w2]; ++u) rank += better(hs[w2 * topk + u], hi[w2 * topk + u], s, id) ? 1 : 0;
+    } else {
+      // the CTA's own pools are sorted best first: entries better than (s, id) in a pool = a lower bound by bisection
+      for (int w2 = 0; w2 < NW; ++w2) {
+        int lo = 0, hi2 = wcnt[w2];
+        while (lo < hi2) {
+          const int mid = (lo + hi2) >> 1;
+          if (better(hs[w2 * topk + mid], hi[w2 * topk + mid], s, id)) lo = mid + 1;
+          else hi2 = mid;
+        }
+        rank += lo;
+      }
+    }
     if (rank < topk) emit(rank, s, id);
   }
   return total < topk ? total : topk;
@@ -819,9 +846,39 @@ struct SortedPool {
       tid_ = __shfl_sync(0xffffffffu, ti, l);
     }
   }
+  // empty pool: the 32 candidates of a step are sorted by a bitonic network (15 exchange stages) instead of being
+  // inserted one after the other; lane g ends up with the g-th best, which IS slot 0 of the pool
+  __device__ __forceinline__ void fill_sorted(bool want, double sc, int ext, int topk) {
+    const int lane = threadIdx.x & 31;
+    double ms = want ? sc : 0.0;
+    int mi = want ? ext : -1;
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, ms, j);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, j);
+        const bool mine_better = mi >= 0 && (oi < 0 || better(ms, mi, os, oi));
+        const bool want_better = ((lane & j) == 0) == ((lane & kk) == 0);   // this lane keeps the better one of the pair
+        if (mine_better != want_better) { ms = os; mi = oi; }
+      }
+    }
+    const int nvalid = __popc(__ballot_sync(0xffffffffu, want));
+    s[0] = ms;
+    i[0] = mi;
+    cnt = nvalid < topk ? nvalid : topk;
+    if (cnt == topk) {      // only possible for topk <= 32: the threshold is entry topk - 1 of slot 0
+      thr = __shfl_sync(0xffffffffu, ms, (topk - 1) & 31);
+      tid_ = __shfl_sync(0xffffffffu, mi, (topk - 1) & 31);
+    }
+  }
   __device__ __forceinline__ void offer(bool want, double sc, int ext, int topk) {
     want = want && (cnt < topk || sc >= thr);
     unsigned m = __ballot_sync(0xffffffffu, want);
+    if (cnt == 0 && (m & (m - 1))) {   // nothing pooled yet and more than one candidate
+      fill_sorted(want, sc, ext, topk);
+      return;
+    }
     while (m) {
       const int leader = __ffs(m) - 1;
       m &= m - 1;
@@ -841,8 +898,16 @@ struct SortedPool {
   }
 };
 
+// streaming copy: the scanned matrix is marked evict-first in L2, so that what the NEXT query needs again (this kernel's
+// code, the id maps, the query rows) is not pushed out of the 126 MB L2 by a 256 MB scan
+__device__ __forceinline__ void s1_cp_async16_stream(void* smem_dst, const void* gsrc, unsigned long long policy) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "l"(policy));
+}
+
 // order-preserving map double -> unsigned 64-bit (a < b  <=>  key(a) < key(b)); key 0 is below every score
 __device__ __forceinline__ unsigned long long s1_key(double v) {
+  v += 0.0;   // -0.0 -> +0.0: the two compare equal as doubles and must share a key
   const unsigned long long b = (unsigned long long)__double_as_longlong(v);
   return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
@@ -855,10 +920,17 @@ score_one_kernel(const float* __restrict__ Y, int n_items, int k, const float* _
                  int keep_query, int topk, ScoreIdx* __restrict__ cand, unsigned* __restrict__ counter,
                  unsigned long long* __restrict__ g_thr,
                  int* __restrict__ out_items, float* __restrict__ out_scores, int* __restrict__ out_count,
-                 volatile unsigned* __restrict__ done_flag, unsigned seq) {
+                 volatile unsigned* __restrict__ done_flag, unsigned seq, unsigned long long* __restrict__ trace) {
   constexpr int NW = S1_THREADS / 32;
   constexpr int ROW = KP + 4;                 // floats per staged row: 16 bytes of skew -> conflict-free LDS.128 per thread
   constexpr int F4 = KP / 4;                  // 16-byte chunks per row
+  unsigned long long t_begin = 0ull;          // PIO_ALS_SERVE_TRACE: %globaltimer stamps of the CTA that publishes the result
+  auto now = [&]() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+  };
+  if (trace && threadIdx.x == 0) t_begin = now();
   extern __shared__ __align__(16) unsigned char s1_smem[];
   double* xd = reinterpret_cast<double*>(s1_smem);                       // [KP][NVP]
   double* s1 = xd + (size_t)KP * NVP;                                     // [S1_MAXNV]
@@ -873,16 +945,24 @@ score_one_kernel(const float* __restrict__ Y, int n_items, int k, const float* _
   const int ntiles = (n_items + S1_THREADS - 1) / S1_THREADS;
   const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   float* ring = tiles + (size_t)warp * S1_STAGES * 32 * ROW;
+  unsigned long long l2_stream;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_stream));
   // step j of this warp: rows base(j) .. base(j) + 31 -> ring slot j % S1_STAGES; one commit group per step (empty past the end)
   auto base_of = [&](int j) { return (((int)blockIdx.x + j * (int)gridDim.x) * NW + warp) * 32; };
   auto fetch = [&](int j) {
     if (j < my_tiles) {
       const int base = base_of(j);
-      float* slot = ring + (size_t)(j % S1_STAGES) * 32 * ROW;
+      // a warp copies 512 contiguous bytes per instruction: lane -> (row lane / F4, chunk lane % F4), + 32 / F4 rows per copy
+      float* dst = ring + (size_t)(j % S1_STAGES) * 32 * ROW + (size_t)(lane / F4) * ROW + (lane % F4) * 4;
+      const float* src = Y + (size_t)(base + lane / F4) * KP + (lane % F4) * 4;
+      if (base + 32 <= n_items) {
 #pragma unroll
-      for (int m = 0; m < F4; ++m) {        // a warp copies 512 contiguous bytes per instruction
-        const int o = lane + m * 32, r = o / F4, c4 = o % F4;
-        if (base + r < n_items) sb_cp_async16(slot + (size_t)r * ROW + c4 * 4, Y + (size_t)(base + r) * KP + c4 * 4);
+        for (int m = 0; m < F4; ++m) s1_cp_async16_stream(dst + (size_t)m * (32 / F4) * ROW, src + (size_t)m * (32 / F4) * KP, l2_stream);
+      } else {
+#pragma unroll
+        for (int m = 0; m < F4; ++m)
+          if (base + lane / F4 + m * (32 / F4) < n_items)
+            s1_cp_async16_stream(dst + (size_t)m * (32 / F4) * ROW, src + (size_t)m * (32 / F4) * KP, l2_stream);
       }
     }
     asm volatile("cp.async.commit_group;\n" ::);
@@ -903,19 +983,30 @@ score_one_kernel(const float* __restrict__ Y, int n_items, int k, const float* _
     qvalid = qry.nq > 0 && id >= 0 && id < q_n_ext && q_deg[id] > 0;   // dot: an unknown user has no recommendations
   }
   __syncthreads();
-  if (COS && tid < S1_MAXNV) {
-    double n1 = 0.0;
-    if (tid < NVP)
-      for (int c = 0; c < k; ++c) {
+  // one query vector: it lives in registers for the whole scan (one CTA per SM: 255 registers per thread are free)
+  constexpr bool XREG = NVP == 1 && !COS;
+  double xreg[XREG ? KP : 1];
+  double s1r[NVP];
+  if (XREG) {
+#pragma unroll
+    for (int c = 0; c < KP; ++c) xreg[c] = xd[c];
+    s1r[0] = 0.0;
+  } else {
+    if (COS && tid < NVP) {
+      double n1 = 0.0;      // index order; columns >= k hold zeros: + 0.0 is exact
+#pragma unroll 8
+      for (int c = 0; c < KP; ++c) {
         const double a = xd[(size_t)c * NVP + tid];
         n1 += a * a;
       }
-    s1[tid] = sqrt(n1);
-  }
-  __syncthreads();
-  double s1r[NVP];
+      s1[tid] = sqrt(n1);
+    }
+    __syncthreads();
 #pragma unroll
-  for (int t = 0; t < NVP; ++t) s1r[t] = COS ? s1[t] : 0.0;
+    for (int t = 0; t < NVP; ++t) s1r[t] = COS ? s1[t] : 0.0;
+  }
+  unsigned long long t_query = 0ull, t_step0 = 0ull;
+  if (trace && tid == 0) t_query = now();
   SortedPool wp;
   wp.init();
   int ext_next = -1;
@@ -942,29 +1033,35 @@ score_one_kernel(const float* __restrict__ Y, int n_items, int k, const float* _
 #pragma unroll
       for (int t = 0; t < NVP; ++t) d[t] = 0.0;
       double n2 = 0.0;
-#pragma unroll 4
-      for (int c4 = 0; c4 < F4; ++c4) {
-        const float4 y4 = yrow[c4];
-        const double yd[4] = {(double)y4.x, (double)y4.y, (double)y4.z, (double)y4.w};
-        if (NVP == 1) {
-          const double2 xa = *reinterpret_cast<const double2*>(xd + c4 * 4);
-          const double2 xb = *reinterpret_cast<const double2*>(xd + c4 * 4 + 2);
-          const double xe[4] = {xa.x, xa.y, xb.x, xb.y};
+      if (XREG) {
+#pragma unroll
+        for (int c4 = 0; c4 < F4; ++c4) {
+          const float4 y4 = yrow[c4];
+          const double yd[4] = {(double)y4.x, (double)y4.y, (double)y4.z, (double)y4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             if (COS) n2 = fma(yd[e], yd[e], n2);
-            d[0] = fma(xe[e], yd[e], d[0]);          // index order, like blas.ddot over Array[Double]
+            d[0] = fma(xreg[(XREG ? c4 * 4 + e : 0)], yd[e], d[0]);   // index order, like blas.ddot over Array[Double]
           }
-        } else {
+        }
+      } else {
+#pragma unroll 4
+        for (int c4 = 0; c4 < F4; ++c4) {
+          const float4 y4 = yrow[c4];
+          const double yd[4] = {(double)y4.x, (double)y4.y, (double)y4.z, (double)y4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             if (COS) n2 = fma(yd[e], yd[e], n2);
-            const double2* xr = reinterpret_cast<const double2*>(xd + (size_t)(c4 * 4 + e) * NVP);
+            if (NVP == 1) {
+              d[0] = fma(xd[c4 * 4 + e], yd[e], d[0]);
+            } else {
+              const double2* xr = reinterpret_cast<const double2*>(xd + (size_t)(c4 * 4 + e) * NVP);
 #pragma unroll
-            for (int t = 0; t < NVP; t += 2) {
-              const double2 x2 = xr[t / 2];
-              d[t] = fma(x2.x, yd[e], d[t]);
-              d[t + (NVP > 1 ? 1 : 0)] = fma(x2.y, yd[e], d[t + (NVP > 1 ? 1 : 0)]);
+              for (int t = 0; t < NVP; t += 2) {
+                const double2 x2 = xr[t / 2];
+                d[t] = fma(x2.x, yd[e], d[t]);
+                d[t + (NVP > 1 ? 1 : 0)] = fma(x2.y, yd[e], d[t + (NVP > 1 ? 1 : 0)]);
+              }
             }
           }
         }
@@ -999,8 +1096,11 @@ score_one_kernel(const float* __restrict__ Y, int n_items, int k, const float* _
         if (atomicMax(&s_thr, key) < key) atomicMax(g_thr, key);
       }
     }
+    if (trace && tid == 0 && j == 0) t_step0 = now();
   }
   asm volatile("cp.async.wait_group 0;\n" ::);
+  unsigned long long t_scan = 0ull;
+  if (trace && tid == 0) t_scan = now();
   wp.dump(topk, hs + (size_t)warp * topk, hi + (size_t)warp * topk);
   if (lane == 0) wcnt[warp] = wp.cnt;
   // the CTA's own list: topk entries best first, empty slots marked
@@ -1013,12 +1113,16 @@ score_one_kernel(const float* __restrict__ Y, int n_items, int k, const float* _
     mine[t].s = 0.0;
     mine[t].i = -1;
   }
-  __threadfence();
+  __syncthreads();          // the CTA's list is written; thread 0 publishes it (its fence is cumulative over the barrier)
+  if (tid == 0) {
+    __threadfence();
+    s_int[2] = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
+    __threadfence();        // the last CTA reads the other lists after this
+  }
   __syncthreads();
-  if (tid == 0) s_int[2] = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
-  __syncthreads();
-  if (!s_int[2]) return;
-  __threadfence();   // the scan is over everywhere: the staging rings are free to hold the survivors
+  if (!s_int[2]) return;    // the scan is over everywhere: the staging rings are free to hold the survivors
+  unsigned long long t_last = 0ull;
+  if (trace && tid == 0) t_last = now();
   auto publish = [&](int rank, double s, int id) {
     out_items[rank] = id;
     out_scores[rank] = (float)s;
@@ -1037,10 +1141,16 @@ score_one_kernel(const float* __restrict__ Y, int n_items, int k, const float* _
     *out_count = cnt;
     *counter = 0u;
     *g_thr = 0ull;
+    if (trace) {
+      trace[0] = t_begin; trace[1] = t_scan; trace[2] = t_last; trace[3] = now(); trace[5] = t_query; trace[6] = t_step0;
+    }
   }
   __threadfence_system();
   __syncthreads();
-  if (tid == 0) *done_flag = seq;
+  if (tid == 0) {
+    if (trace) trace[4] = now();
+    *done_flag = seq;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

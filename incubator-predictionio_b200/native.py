@@ -95,6 +95,15 @@ def lib():
         L.pio_als_last_error.argtypes = [C.c_void_p]
         L.pio_als_destroy.restype = None
         L.pio_als_destroy.argtypes = [C.c_void_p]
+        # the serving calls take raw addresses (ndarray.ctypes.data): building typed ctypes pointers costs ~2 us each,
+        # which is visible next to a 50 us query
+        vp, ci = C.c_void_p, C.c_int
+        L.pio_als_recommend.restype = ci
+        L.pio_als_recommend.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
+        L.pio_als_similar.restype = ci
+        L.pio_als_similar.argtypes = [vp, vp, ci, ci, vp, vp, ci, vp, vp, vp]
+        L.pio_als_similar_batch.restype = ci
+        L.pio_als_similar_batch.argtypes = [vp, vp, vp, ci, ci, vp, vp, ci, vp, vp, vp]
         for name in EXPORTED_SYMBOLS:
             getattr(L, name)  # AttributeError if the ABI is incomplete
         _lib = L
@@ -105,6 +114,11 @@ def _ptr(a, t):
     if a is None:
         return None
     return a.ctypes.data_as(C.POINTER(t))
+
+
+def _addr(a):
+    """Raw address of a contiguous ndarray (None stays None) for entry points declared with c_void_p parameters."""
+    return None if a is None else a.ctypes.data
 
 
 def device_count() -> int:
@@ -246,22 +260,20 @@ class NativeALS:
         os_ = np.zeros((n, topk), np.float32)
         oc = np.zeros(n, np.int32)
         mk, wt = self._mask_weight(item_mask, item_weight)
-        self._check(lib().pio_als_recommend(self._h, _ptr(users, C.c_int32), C.c_int(n), C.c_int(topk),
-                                            _ptr(mk, C.c_uint8), _ptr(wt, C.c_double), _ptr(oi, C.c_int32),
-                                            _ptr(os_, C.c_float), _ptr(oc, C.c_int32)))
+        self._check(lib().pio_als_recommend(self._h, users.ctypes.data, n, topk, _addr(mk), _addr(wt), oi.ctypes.data,
+                                            os_.ctypes.data, oc.ctypes.data))
         return oi, os_, oc
 
     def similar(self, query_items, topk, item_mask=None, item_weight=None, keep_query_items=False):
         q = np.ascontiguousarray(query_items, np.int32)
         oi = np.full(topk, -1, np.int32)
         os_ = np.zeros(topk, np.float32)
-        oc = C.c_int32(0)
+        oc = np.zeros(1, np.int32)
         mk, wt = self._mask_weight(item_mask, item_weight)
-        self._check(lib().pio_als_similar(self._h, _ptr(q, C.c_int32), C.c_int(q.shape[0]), C.c_int(topk),
-                                          _ptr(mk, C.c_uint8), _ptr(wt, C.c_double),
-                                          C.c_int(SIM_KEEP_QUERY_ITEMS if keep_query_items else 0),
-                                          _ptr(oi, C.c_int32), _ptr(os_, C.c_float), C.byref(oc)))
-        return oi, os_, int(oc.value)
+        self._check(lib().pio_als_similar(self._h, q.ctypes.data, q.shape[0], topk, _addr(mk), _addr(wt),
+                                          SIM_KEEP_QUERY_ITEMS if keep_query_items else 0, oi.ctypes.data,
+                                          os_.ctypes.data, oc.ctypes.data))
+        return oi, os_, int(oc[0])
 
     def similar_batch(self, queries, topk, item_mask=None, item_weight=None, keep_query_items=False):
         """queries: sequence of item-index sequences; returns (items [n, topk], scores [n, topk], count [n])."""
@@ -274,10 +286,9 @@ class NativeALS:
         os_ = np.zeros((n, topk), np.float32)
         oc = np.zeros(n, np.int32)
         mk, wt = self._mask_weight(item_mask, item_weight)
-        self._check(lib().pio_als_similar_batch(self._h, _ptr(ptr, C.c_int64), _ptr(flat, C.c_int32), C.c_int(n),
-                                                C.c_int(topk), _ptr(mk, C.c_uint8), _ptr(wt, C.c_double),
-                                                C.c_int(SIM_KEEP_QUERY_ITEMS if keep_query_items else 0),
-                                                _ptr(oi, C.c_int32), _ptr(os_, C.c_float), _ptr(oc, C.c_int32)))
+        self._check(lib().pio_als_similar_batch(self._h, ptr.ctypes.data, flat.ctypes.data, n, topk, _addr(mk), _addr(wt),
+                                                SIM_KEEP_QUERY_ITEMS if keep_query_items else 0, oi.ctypes.data,
+                                                os_.ctypes.data, oc.ctypes.data))
         return oi, os_, oc
 
     # -- persistence / introspection -----------------------------------------------------------

@@ -365,6 +365,7 @@ def test_single_query_fused_launch_is_bit_exact(native, oracle, monkeypatch):
         itf = synth.synth_init_factors(ni, k, 3, 1)
         itf *= (1.0 + (np.arange(ni, dtype=np.float32) % 89)[:, None] / 89.0)
         uf = synth.synth_init_factors(nu, k, 4, 0)
+        uf[3] = 0.0            # every score is +0.0 or (negative weight) -0.0: all ties, decided by the item index
         ih = (np.arange(ni) % 11 != 3).astype(np.uint8)
         uh = (np.arange(nu) % 5 != 2).astype(np.uint8)
         m = native.NativeALS.from_factors(uf, itf, uh, ih)
@@ -377,7 +378,7 @@ def test_single_query_fused_launch_is_bit_exact(native, oracle, monkeypatch):
         have, miss = np.flatnonzero(ih), np.flatnonzero(ih == 0)
         for topk in (1, 10, 128):
             for mk, wt in ((None, None), (mask, w)):
-                for user in (0, 1, 2, nu - 1, -1):
+                for user in (0, 1, 2, 3, nu - 1, -1):
                     us = np.array([user], np.int32)
                     g = m.recommend(us, topk, mk, wt)
                     o_ = oracle.recommend(uf, uh, itf, ih, us, topk, mk, wt)
