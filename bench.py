@@ -51,12 +51,40 @@ def algorithmic_work(nu, ni, nnz, k, implicit):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs: NVML in a thread every 2 ms (a timed region of a
+    few tens of milliseconds at N = 8 is over before a freshly spawned nvidia-smi prints its first line); nvidia-smi -lms
+    only if the NVML binding is missing."""
+
+    _BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.h, self.sm, self.bits, self._stop = None, None, [], 0, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while True:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                self.bits |= int(reasons(self.h))
+            except Exception:
+                pass
+            if self._stop.wait(0.002):
+                return
 
     def start(self):
+        if self.nvml:
+            self._stop.clear()
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -74,6 +102,16 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self._stop.set()
+            self.t.join(timeout=2)
+            try:
+                mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": mx,
+                    "reasons": sorted(v for b, v in self._BITS.items() if self.bits & b), "samples": len(self.sm),
+                    "how": "NVML, every 2 ms inside the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -96,7 +134,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "how": "nvidia-smi -lms 20"}
 
 
 def traffic_from_profiles(workload):
