@@ -155,7 +155,7 @@ def measured_peaks():
         d = json.loads(p.read_text())
         hbm, bf16, src = d.get("hbm_gbs", hbm), d.get("bf16_tflops", bf16), "measured"
     fp32, fp32_src = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"
-    mma_tf32 = None
+    mma_tf32 = dfma = None
     q = ROOT / "profiles" / "peaks_r02.json"
     if q.exists():
         try:
@@ -163,9 +163,11 @@ def measured_peaks():
             if d.get("ffma_tflops"):
                 fp32, fp32_src = float(d["ffma_tflops"]), "measured (tools/peaks.cu, profiles/peaks_r02.json)"
             mma_tf32 = d.get("mma_sync_tf32_tflops")
+            dfma = d.get("dfma_tflops")
         except Exception:
             pass
-    return {"hbm": hbm, "bf16": bf16, "src": src, "fp32": fp32, "fp32_src": fp32_src, "mma_tf32": mma_tf32}
+    return {"hbm": hbm, "bf16": bf16, "src": src, "fp32": fp32, "fp32_src": fp32_src, "mma_tf32": mma_tf32,
+            "dfma": dfma or 148 * 64 * 2 * 1.965e9 / 1e12}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -351,10 +353,12 @@ def topk_bench(native, o, cores, m, nu, ni, k, uf, itf, uh, ih, peaks, dev):
         "cpu_baseline": {"value": ns / cpu_dt, "unit": "predictions/s", "cores": cores, "kind": "port",
                          "sample": f"{ns} of the same queries, fp64 ddot scan + heap (oracle restatement of "
                                    "recommendProducts)"},
-        "roofline": {"bound": "hbm", "achieved": nq / 16.0 * scan_bytes / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                     "frac": nq / 16.0 * scan_bytes / dt / 1e9 / peaks["hbm"],
-                     "note": "algorithmic bytes = one scan of the item matrix per group of 16 queries (the kernel's "
-                             "batching); fp64 score accumulation makes the DFMA pipe the real bound"}}
+        "roofline": {"bound": "fp64", "achieved": 2.0 * nq * ni * k / dt / 1e12, "peak": peaks["dfma"], "unit": "TFLOP/s",
+                     "frac": 2.0 * nq * ni * k / dt / 1e12 / peaks["dfma"],
+                     "note": "scores are accumulated in fp64 in index order (bit-identical to the JVM's ddot), so the bound "
+                             "is the DFMA pipe: one DFMA per (query, item, feature); peak = tools/peaks.cu "
+                             "(profiles/peaks_r02.json). Includes the H2D / D2H copies of the call.",
+                     "hbm_frac_per_16_queries": nq / 16.0 * scan_bytes / dt / 1e9 / peaks["hbm"]}}
     # similarproduct path (A9, BASELINE.json configs[3]): cosine top-20 over 1 M item vectors (unit-norm Gaussian, rank 64),
     # 10 k queries of 1-5 items, one pio_als_similar_batch call on an imported item-only model
     try:
@@ -383,6 +387,7 @@ def topk_bench(native, o, cores, m, nu, ni, k, uf, itf, uh, ih, peaks, dev):
             if j >= 10:
                 lat2.append(time.perf_counter() - t0)
         sb = n_it * kk * 4
+        nvec = float(sum(len(q) for q in queries))
         out["similar_c4"] = {
             "what": f"pio_als_similar_batch: {nqs} queries of 1-5 items, cosine top-20 over {n_it} item vectors, rank {kk}, "
                     "one call, host buffers",
@@ -390,9 +395,11 @@ def topk_bench(native, o, cores, m, nu, ni, k, uf, itf, uh, ih, peaks, dev):
             "bit_exact_vs_oracle_on_sample": bool(ok), "sample_queries_checked": ns2,
             "cpu_baseline": {"value": ns2 / cpu_dt, "unit": "predictions/s", "cores": cores, "kind": "port",
                              "sample": f"{ns2} of the same queries (oracle restatement of the similarproduct predict scan)"},
-            "roofline": {"bound": "hbm", "achieved": nqs / 8.0 * sb / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                         "frac": nqs / 8.0 * sb / dt / 1e9 / peaks["hbm"],
-                         "note": "algorithmic bytes = one scan of the item matrix per group of 8 queries"},
+            "roofline": {"bound": "fp64", "achieved": 2.0 * (nvec + nqs / 8.0) * n_it * kk / dt / 1e12, "peak": peaks["dfma"],
+                         "unit": "TFLOP/s", "frac": 2.0 * (nvec + nqs / 8.0) * n_it * kk / dt / 1e12 / peaks["dfma"],
+                         "note": "fp64 cosine in index order (bit-identical to the reference's loop): one DFMA per (query "
+                                 "vector, item, feature) + one per (item, feature) and group of 8 queries for the item norm",
+                         "hbm_frac_per_8_queries": nqs / 8.0 * sb / dt / 1e9 / peaks["hbm"]},
             "single_query_ms": float(np.median(lat2) * 1e3), "single_query_p90_ms": float(np.percentile(lat2, 90) * 1e3),
             "single_query_what": "pio_als_similar, one query item, top-20, through the Python binding (ctypes, host buffers): "
                                  "one fused launch, result polled from mapped host memory",

@@ -442,6 +442,7 @@ struct pio_als_handle {
   unsigned* srv_counter = nullptr;         // arrival counter of score_one_kernel (zero between calls)
   unsigned srv_seq = 0;                    // sequence number of the last fused single-query call
   bool serve_fused = true;                 // PIO_ALS_SERVE_FUSED=0: single queries take the three-launch path
+  bool score_blocked = true;               // PIO_ALS_SCORE_BLOCKED=0: batched recommend on the one-item-per-thread kernel
   bool serve_trace = false;                // PIO_ALS_SERVE_TRACE=1: per-phase device timestamps of every fused call on stderr
   bool tc_split = false;      // PIO_ALS_TC_SPLIT=1: the tensor-core kernel only accumulates, a second kernel solves (measured: no gain)
   float* tc_out = nullptr;    // split mode: normal equations of one tile of rows ([rows][ASLOT + KP])
@@ -1435,6 +1436,7 @@ static int create_common(pio_als_handle* h) {
     h->n_pieces = h->cfg.world_size > 1 ? 4 : 1;
     if (const char* v = getenv("PIO_ALS_SERVE_FUSED")) h->serve_fused = atoi(v) != 0;
     if (const char* v = getenv("PIO_ALS_SERVE_TRACE")) h->serve_trace = atoi(v) != 0;
+    if (const char* v = getenv("PIO_ALS_SCORE_BLOCKED")) h->score_blocked = atoi(v) != 0;
     if (const char* v = getenv("PIO_ALS_PIECES")) {
       const int n = atoi(v);
       if (n >= 1 && n <= 8) h->n_pieces = n;
@@ -1761,6 +1763,27 @@ static int serve_reserve(pio_als_handle* h, size_t dev_bytes, size_t host_bytes)
 }
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+extern "C++" {
+template <int KPT>
+static int launch_dot_blocked_kp(pio_als_handle* h, dim3 grid, size_t smem, const float* d_xq, const uint8_t* d_valid, int nq,
+                                 const uint8_t* d_mask, const double* d_weight, int topk, ScoreIdx* d_cand) {
+  static size_t attr_smem[64] = {};
+  if (h->cfg.device < 64 && attr_smem[h->cfg.device] < smem) {
+    CK(h, cudaFuncSetAttribute(score_dot_blocked_kernel<KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[h->cfg.device] = smem;
+  }
+  score_dot_blocked_kernel<KPT><<<grid, 32 * DB_WARPS, smem, h->stream>>>(h->I.F, h->I.n_internal, d_xq, d_valid, nq,
+                                                                         h->I.cand_ext, d_mask, d_weight, topk, d_cand);
+  return PIO_ALS_OK;
+}
+}  // extern "C++"
+static int launch_dot_blocked(pio_als_handle* h, dim3 grid, size_t smem, const float* d_xq, const uint8_t* d_valid, int nq,
+                              const uint8_t* d_mask, const double* d_weight, int topk, ScoreIdx* d_cand) {
+  if (h->KP == 16) return launch_dot_blocked_kp<16>(h, grid, smem, d_xq, d_valid, nq, d_mask, d_weight, topk, d_cand);
+  if (h->KP == 32) return launch_dot_blocked_kp<32>(h, grid, smem, d_xq, d_valid, nq, d_mask, d_weight, topk, d_cand);
+  return launch_dot_blocked_kp<64>(h, grid, smem, d_xq, d_valid, nq, d_mask, d_weight, topk, d_cand);
+}
+
 // recommend for n <= SB_QB users and topk <= TK_MAXK: three launches and one synchronisation
 static int recommend_small(pio_als_handle* h, const int32_t* users, int n, int topk, const uint8_t* item_mask,
                            const double* item_weight, int32_t* out_items, float* out_scores, int32_t* out_count) {
@@ -2019,10 +2042,19 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
       attr_smem[h->cfg.device] = sb_smem;
     }
   }
+  // blocked kernel (two items x 16 queries per thread, independent warps): rank <= 64, topk <= DB_MAXK
+  const bool blocked = h->score_blocked && KP <= 64 && topk <= DB_MAXK;
+  if (blocked) {
+    const int nsteps = (h->I.n_internal + DB_RINGS * DB_ROWS - 1) / (DB_RINGS * DB_ROWS);
+    gx = (h->sm_count + ngroups - 1) / ngroups;
+    if (gx > (nsteps + 7) / 8) gx = (nsteps + 7) / 8;   // at least eight steps per warp: the pools must warm up
+    if (gx < 1) gx = 1;
+  }
+  const int lists = blocked ? gx * DB_RINGS : gx;        // candidate lists per query
   CK(h, tmp.alloc(&d_users, (size_t)n));
   CK(h, tmp.alloc(&d_xq, (size_t)n * KP));
   CK(h, tmp.alloc(&d_valid, (size_t)n));
-  CK(h, tmp.alloc(&d_cand, (size_t)n * gx * pass_max));
+  CK(h, tmp.alloc(&d_cand, (size_t)n * lists * pass_max));
   CK(h, tmp.alloc(&d_oi, (size_t)n * topk));
   CK(h, tmp.alloc(&d_os, (size_t)n * topk));
   CK(h, tmp.alloc(&d_oc, (size_t)n));
@@ -2045,13 +2077,20 @@ int pio_als_recommend(pio_als_handle* h, const int32_t* users, int n, int topk, 
       const int ng = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
       const int q0 = g0 * SB_QB;
       const int nq = n - q0 < ng * SB_QB ? n - q0 : ng * SB_QB;
-      score_dot_topk_batched_kernel<<<dim3(gx, ng), SB_THREADS, sb_smem, st>>>(
-          h->I.F, h->I.n_internal, KP, d_xq + (size_t)q0 * KP, d_valid + q0, nq, h->I.cand_ext, d_mask, d_weight,
-          (done > 0) ? d_bound + q0 : nullptr, pk, d_cand + (size_t)q0 * gx * pk);
+      if (blocked) {
+        const size_t smem = db_smem_bytes(KP, pk);
+        const int brc = launch_dot_blocked(h, dim3(gx, ng), smem, d_xq + (size_t)q0 * KP, d_valid + q0, nq, d_mask, d_weight, pk,
+                                           d_cand + (size_t)q0 * lists * pk);
+        if (brc) return brc;
+      } else {
+        score_dot_topk_batched_kernel<<<dim3(gx, ng), SB_THREADS, sb_smem, st>>>(
+            h->I.F, h->I.n_internal, KP, d_xq + (size_t)q0 * KP, d_valid + q0, nq, h->I.cand_ext, d_mask, d_weight,
+            (done > 0) ? d_bound + q0 : nullptr, pk, d_cand + (size_t)q0 * lists * pk);
+      }
       LAUNCHED(h);
     }
-    // the candidate lists of a query are [gx][pk] entries, stored with stride pk
-    topk_merge_kernel<<<n, TK_THREADS, 0, st>>>(d_cand, gx * pk, pk, topk, done, d_oi, d_os, d_oc, d_bound);
+    // the candidate lists of a query are [lists][pk] entries, stored with stride pk
+    topk_merge_kernel<<<n, TK_THREADS, 0, st>>>(d_cand, lists * pk, pk, topk, done, d_oi, d_os, d_oc, d_bound);
     LAUNCHED(h);
   }
   CK(h, cudaMemcpyAsync(out_items, d_oi, sizeof(int) * (size_t)n * topk, cudaMemcpyDeviceToHost, st));

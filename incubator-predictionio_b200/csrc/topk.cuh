@@ -264,6 +264,189 @@ score_dot_topk_batched_kernel(const float* __restrict__ Y, int n_items, int kp,
   }
 }
 
+// ---- blocked dot-product scoring: two items x four queries per thread, sixteen warps per SM -------------------------
+// The batched kernel above issues one broadcast LDS.128 of query values per two DFMAs: the shared-memory pipe and the
+// fp64 pipe saturate together.  Here every lane scores TWO items against DB_QW = 4 queries, so one LDS.128 feeds four
+// DFMAs.  A CTA is four independent "rings" of four warps: the warps of a ring share 64 staged rows per step (two-stage
+// cp.async ring, each warp copies a quarter, two named barriers of 128 threads per step -- never a CTA barrier in the
+// scan) and split the 16 queries of the group between them; every warp owns the top-k pools of its four queries
+// (entries and bookkeeping in shared memory; almost every score fails the threshold test, the insertion is an
+// out-of-line call).  16 warps per SM: a single warp cannot keep the fp64 pipe busy (measured: 31 % with one warp per
+// scheduler).  Same arithmetic and order as the kernels above -> bit-identical results.
+// For kp <= 64 and topk <= DB_MAXK; cand: [n_queries][gridDim.x * DB_RINGS][topk], unsorted, i = -1 = empty.
+constexpr int DB_QW = 4;                     // queries per warp
+constexpr int DB_WPR = SB_QB / DB_QW;        // warps per ring
+constexpr int DB_RINGS = 4;
+constexpr int DB_WARPS = DB_RINGS * DB_WPR;  // 16
+constexpr int DB_ROWS = 64;                  // rows per ring step (two per lane)
+constexpr int DB_MAXK = 32;
+struct alignas(16) DbPoolHdr {   // 32 bytes; the first 16 are read with one LDS.128 for the threshold test
+  double thr;
+  int cnt, wid, worst, pad[3];
+};
+__host__ __device__ inline size_t db_smem_bytes(int kp, int topk) {
+  return sizeof(double) * (size_t)kp * SB_QB + sizeof(float) * (size_t)DB_RINGS * 2 * DB_ROWS * (kp + 4) +
+         (size_t)DB_RINGS * SB_QB * (sizeof(DbPoolHdr) + (sizeof(double) + sizeof(int)) * (size_t)topk);
+}
+
+// The rare path of the scan (a score passed the threshold test): NOT inlined -- unrolled copies of the pool insertion
+// between the threshold tests of a step are tens of KB of code on the hot path (ncu on a first version: "no
+// instruction" 2.5 stalls per issued instruction).
+__device__ __noinline__ void db_insert(DbPoolHdr* hd, double* ps, int* pi, bool w0, double s0, int e0, bool w1, double s1,
+                                       int e1, int topk) {
+  WarpPool wp;
+  wp.thr = hd->thr; wp.cnt = hd->cnt; wp.wid = hd->wid; wp.worst = hd->worst;
+  wpool_offer(wp, w0, s0, e0, topk, ps, pi);
+  wpool_offer(wp, w1, s1, e1, topk, ps, pi);
+  if ((threadIdx.x & 31) == 0) { hd->thr = wp.thr; hd->cnt = wp.cnt; hd->wid = wp.wid; hd->worst = wp.worst; }
+  __syncwarp();
+}
+
+template <int KP>
+__global__ void __launch_bounds__(32 * DB_WARPS, 1)
+score_dot_blocked_kernel(const float* __restrict__ Y, int n_items, const float* __restrict__ xq,
+                         const uint8_t* __restrict__ qvalid, int n_queries, const int* __restrict__ cand_ext,
+                         const uint8_t* __restrict__ mask, const double* __restrict__ weight, int topk,
+                         ScoreIdx* __restrict__ cand) {
+  constexpr int ROW = KP + 4, F4 = KP / 4;
+  constexpr int RPI = 32 / F4;                 // rows per warp-wide copy instruction (512 contiguous bytes)
+  constexpr int CPW = DB_ROWS / RPI / DB_WPR;  // copy instructions per warp and step
+  extern __shared__ __align__(16) unsigned char db_smem[];
+  double* xd = reinterpret_cast<double*>(db_smem);                                   // [KP][SB_QB]
+  float* rings = reinterpret_cast<float*>(xd + (size_t)KP * SB_QB);                  // [DB_RINGS][2][DB_ROWS][ROW]
+  DbPoolHdr* hdrs = reinterpret_cast<DbPoolHdr*>(rings + (size_t)DB_RINGS * 2 * DB_ROWS * ROW);   // [DB_RINGS][SB_QB]
+  double* pss = reinterpret_cast<double*>(hdrs + DB_RINGS * SB_QB);                  // [DB_RINGS][SB_QB][topk]
+  int* pis = reinterpret_cast<int*>(pss + (size_t)DB_RINGS * SB_QB * topk);          // [DB_RINGS][SB_QB][topk]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rg = warp / DB_WPR, sub = warp % DB_WPR;      // ring, and which four queries of the group
+  const int q0 = blockIdx.y * SB_QB;
+  for (int o = tid; o < KP * SB_QB; o += 32 * DB_WARPS) {
+    const int t = o / SB_QB, q = o % SB_QB;
+    xd[o] = (q0 + q < n_queries) ? (double)xq[(size_t)(q0 + q) * KP + t] : 0.0;
+  }
+  for (int o = tid; o < DB_RINGS * SB_QB; o += 32 * DB_WARPS) {
+    hdrs[o].thr = 0.0; hdrs[o].cnt = 0; hdrs[o].wid = -1; hdrs[o].worst = 0;
+  }
+  unsigned qmask = 0;   // my queries that take candidates
+  for (int q = 0; q < DB_QW; ++q)
+    if (q0 + sub * DB_QW + q < n_queries && qvalid[q0 + sub * DB_QW + q]) qmask |= 1u << q;
+  __syncthreads();
+  float* ring = rings + (size_t)rg * 2 * DB_ROWS * ROW;
+  DbPoolHdr* hdr = hdrs + rg * SB_QB + sub * DB_QW;
+  double* ps = pss + ((size_t)rg * SB_QB + sub * DB_QW) * topk;
+  int* pi = pis + ((size_t)rg * SB_QB + sub * DB_QW) * topk;
+  const double* xw = xd + sub * DB_QW;
+  auto ring_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + rg), "r"(32 * DB_WPR) : "memory"); };
+  const int nsteps = (n_items + DB_RINGS * DB_ROWS - 1) / (DB_RINGS * DB_ROWS);
+  const int my_steps = (int)blockIdx.x < nsteps ? (nsteps - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto base_of = [&](int j) { return (((int)blockIdx.x + j * (int)gridDim.x) * DB_RINGS + rg) * DB_ROWS; };
+  auto fetch = [&](int j) {   // this warp's quarter of the ring's step j
+    if (j < my_steps) {
+      const int base = base_of(j);
+      const int r0 = sub * CPW * RPI + lane / F4;
+      float* dst = ring + (size_t)(j & 1) * DB_ROWS * ROW + (size_t)r0 * ROW + (lane % F4) * 4;
+      const float* src = Y + (size_t)(base + r0) * KP + (lane % F4) * 4;
+      if (base + DB_ROWS <= n_items) {
+#pragma unroll
+        for (int m = 0; m < CPW; ++m) sb_cp_async16(dst + (size_t)m * RPI * ROW, src + (size_t)m * RPI * KP);
+      } else {
+#pragma unroll
+        for (int m = 0; m < CPW; ++m)
+          if (base + r0 + m * RPI < n_items) sb_cp_async16(dst + (size_t)m * RPI * ROW, src + (size_t)m * RPI * KP);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  fetch(0);
+  int ext_n[2] = {-1, -1};
+  if (my_steps > 0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = base_of(0) + u * 32 + lane;
+      ext_n[u] = i < n_items ? __ldg(cand_ext + i) : -1;
+    }
+  }
+  for (int j = 0; j < my_steps; ++j) {
+    int ext[2] = {ext_n[0], ext_n[1]};
+    if (j + 1 < my_steps) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = base_of(j + 1) + u * 32 + lane;
+        ext_n[u] = i < n_items ? __ldg(cand_ext + i) : -1;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (ext[u] >= 0 && mask && mask[ext[u]]) ext[u] = -1;
+    ring_bar();                // slot (j + 1) & 1 was read in step j - 1 by the four warps of the ring
+    fetch(j + 1);
+    asm volatile("cp.async.wait_group 1;\n" ::);
+    ring_bar();                // step j has landed for the whole ring
+    double acc[2][DB_QW];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int q = 0; q < DB_QW; ++q) acc[u][q] = 0.0;
+    if (qmask) {
+      const float4* r0 = reinterpret_cast<const float4*>(ring + ((size_t)(j & 1) * DB_ROWS + lane) * ROW);
+      const float4* r1 = reinterpret_cast<const float4*>(ring + ((size_t)(j & 1) * DB_ROWS + 32 + lane) * ROW);
+#pragma unroll 4
+      for (int c4 = 0; c4 < F4; ++c4) {
+        const float4 a4 = r0[c4], b4 = r1[c4];
+        const double ya[4] = {(double)a4.x, (double)a4.y, (double)a4.z, (double)a4.w};
+        const double yb[4] = {(double)b4.x, (double)b4.y, (double)b4.z, (double)b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double2* xr = reinterpret_cast<const double2*>(xw + (size_t)(c4 * 4 + e) * SB_QB);
+#pragma unroll
+          for (int q = 0; q < DB_QW; q += 2) {
+            const double2 x2 = xr[q / 2];
+            acc[0][q] = fma(x2.x, ya[e], acc[0][q]);          // index order t = 0..k-1, like blas.ddot over Array[Double]
+            acc[0][q + 1] = fma(x2.y, ya[e], acc[0][q + 1]);
+            acc[1][q] = fma(x2.x, yb[e], acc[1][q]);
+            acc[1][q + 1] = fma(x2.y, yb[e], acc[1][q + 1]);
+          }
+        }
+      }
+    }
+    if (weight) {   // per-item score weight (ecommerce adjust-score): adjustedScore = s * weights(i)
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (ext[u] >= 0) {
+          const double w = weight[ext[u]];
+#pragma unroll
+          for (int q = 0; q < DB_QW; ++q) acc[u][q] = acc[u][q] * w;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < DB_QW; ++q) {
+      if (!((qmask >> q) & 1u)) continue;
+      const int4 h4 = *reinterpret_cast<const int4*>(&hdr[q]);       // thr (8 bytes), cnt, wid
+      const double thr = __hiloint2double(h4.y, h4.x);
+      const int cnt = h4.z;
+      const bool w0 = ext[0] >= 0 && (cnt < topk || acc[0][q] >= thr);
+      const bool w1 = ext[1] >= 0 && (cnt < topk || acc[1][q] >= thr);
+      if (!__any_sync(0xffffffffu, w0 || w1)) continue;
+      db_insert(&hdr[q], ps + (size_t)q * topk, pi + (size_t)q * topk, w0, acc[0][q], ext[0], w1, acc[1][q], ext[1], topk);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncwarp();
+#pragma unroll 1
+  for (int q = 0; q < DB_QW; ++q) {
+    const int qq = q0 + sub * DB_QW + q;
+    if (qq >= n_queries) break;
+    const int cnt = hdr[q].cnt;
+    ScoreIdx* out = cand + (((size_t)qq * gridDim.x + blockIdx.x) * DB_RINGS + rg) * topk;
+    for (int t = lane; t < topk; t += 32) {
+      ScoreIdx e;
+      e.s = t < cnt ? ps[(size_t)q * topk + t] : 0.0;
+      e.i = t < cnt ? pi[(size_t)q * topk + t] : -1;
+      out[t] = e;
+    }
+  }
+}
+
 // ---- similarproduct scoring, same structure: one query = nqv item vectors -------------------------------------
 // qf: [nqv][kp] vectors of the query items that own a factor (query order kept); qid: all nq_all query item ids
 // (external) - every one of them is excluded from the candidates (ALSAlgorithm.scala:243-245).  score_i = sum over the

@@ -404,6 +404,37 @@ def test_single_query_fused_launch_is_bit_exact(native, oracle, monkeypatch):
         m0.close()
 
 
+def test_batched_recommend_blocked_kernel_is_bit_exact(native, oracle, monkeypatch):
+    """More than 16 users per call: the blocked kernel (two items x 16 queries per thread, independent warps, topk <= 32,
+    rank <= 64) against the oracle and against the one-item-per-thread kernel (PIO_ALS_SCORE_BLOCKED=0); ragged last
+    group, unknown / factor-less users, masks, weights with exact-zero and negative entries."""
+    rng = np.random.default_rng(33)
+    for k, ni, nu in ((64, 30_000, 300), (32, 5_000, 100), (10, 777, 50)):
+        itf = synth.synth_init_factors(ni, k, 5, 1)
+        itf *= (1.0 + (np.arange(ni, dtype=np.float32) % 83)[:, None] / 83.0)
+        uf = synth.synth_init_factors(nu, k, 6, 0)
+        uf[7] = 0.0
+        ih = (np.arange(ni) % 13 != 5).astype(np.uint8)
+        uh = (np.arange(nu) % 9 != 4).astype(np.uint8)
+        m = native.NativeALS.from_factors(uf, itf, uh, ih)
+        monkeypatch.setenv("PIO_ALS_SCORE_BLOCKED", "0")
+        m0 = native.NativeALS.from_factors(uf, itf, uh, ih)
+        monkeypatch.delenv("PIO_ALS_SCORE_BLOCKED")
+        w = np.ones(ni, np.float64)
+        w[rng.integers(0, ni, 300)] = rng.choice([0.0, 0.5, 2.0, -1.0], 300)
+        mask = (np.arange(ni) % 7 == 0).astype(np.uint8)
+        users = np.concatenate([np.arange(nu), [-1, nu - 1, 0]]).astype(np.int32)[: nu - 3 if nu > 60 else nu + 3]
+        for topk in (1, 10, 32, 33):
+            for mk, wt in ((None, None), (mask, w)):
+                g = m.recommend(users, topk, mk, wt)
+                o_ = oracle.recommend(uf, uh, itf, ih, users, topk, mk, wt)
+                z = m0.recommend(users, topk, mk, wt)
+                for a, b, c in zip(g, o_, z):
+                    assert np.array_equal(a, b) and np.array_equal(a, c), (k, topk, mk is None)
+        m.close()
+        m0.close()
+
+
 def test_load_rejects_corrupt_files(native, tmp_path):
     nu, ni = 50, 40
     u, i, r = synth.synth_ratings(nu, ni, 800, seed=8, implicit=False)

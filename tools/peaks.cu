@@ -104,6 +104,42 @@ __global__ void __launch_bounds__(256) lds_kernel(float* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc.x + acc.y + acc.z + acc.w;
 }
 
+// fp64: the scoring kernels accumulate in double like the JVM (bit-exact top-k), so their compute bound is the DFMA pipe
+__global__ void __launch_bounds__(256) dfma_kernel(float* out, int iters, double x, double y) {
+  double a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = (double)(threadIdx.x + j);
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a[j] = fma(a[j], x, y);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += a[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
+}
+// float -> double conversions (F2F.F64.F32, one per matrix element scored)
+__global__ void __launch_bounds__(256) f2f_kernel(float* out, int iters, float x) {
+  float a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = (float)(threadIdx.x + j) * x;
+  int acc = 0;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        acc ^= __double2hiint((double)a[j]);   // one F2F.F64.F32 per element; the XOR and the FMUL run on other pipes
+        a[j] *= x;
+      }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (float)acc + a[3];
+}
+
 int main() {
   cudaDeviceProp pr;
   CK(cudaGetDeviceProperties(&pr, 0));
@@ -174,11 +210,36 @@ int main() {
     if (rep > 0 && ms < best) best = ms;
   }
   lds_bpc = 8.0 * 512.0 * (double)iters * blocks * (threads / 32) / sms / (best * 1e-3 * pr.clockRate * 1e3);
+  // DFMA
+  best = 1e30f;
+  const int diters = 400;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    dfma_kernel<<<blocks, threads>>>(out, diters, 1.0000001, 0.5);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const double dfma_tf = 2.0 * 16 * 8 * (double)diters * blocks * threads / (best * 1e-3) / 1e12;
+  const double dfma_per_sm_clk = 16.0 * 8 * (double)diters * blocks * threads / sms / (best * 1e-3 * pr.clockRate * 1e3);
+  // F2F.F64.F32
+  best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    f2f_kernel<<<blocks, threads>>>(out, diters, 1.5f);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const double f2f_per_sm_clk = 4.0 * 16 * (double)diters * blocks * threads / sms / (best * 1e-3 * pr.clockRate * 1e3);
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_mhz_max\": %.0f, \"ffma_tflops\": %.2f, \"ffma_ms\": %.3f, "
          "\"ffma_nominal_tflops\": %.2f, \"mma_sync_tf32_tflops\": %.2f, \"mma_sync_m16n8k8_per_sm_per_clk_at_max_clock\": %.4f, "
          "\"mma_sync_m16n8k4_per_sm_per_clk_at_max_clock\": %.4f, \"shfl_warp_instr_per_sm_per_clk_at_max_clock\": %.3f, \"lds128_bytes_per_sm_per_clk_at_max_clock\": %.1f, "
+         "\"dfma_tflops\": %.2f, \"dfma_lanes_per_sm_per_clk_at_max_clock\": %.2f, \"f2f_f64_f32_lanes_per_sm_per_clk_at_max_clock\": %.2f, "
          "\"how\": \"tools/peaks.cu: 8 CTAs x 256 threads per SM, best of 4 timed launches, CUDA events\"}\n",
          pr.name, sms, pr.clockRate / 1e3, ffma_tf, ffma_ms, sms * 128 * 2 * (pr.clockRate * 1e3) / 1e12, mma_tf,
-         mma_per_sm_clk, mma4_per_sm_clk, shfl_rate, lds_bpc);
+         mma_per_sm_clk, mma4_per_sm_clk, shfl_rate, lds_bpc, dfma_tf, dfma_per_sm_clk, f2f_per_sm_clk);
   return 0;
 }
