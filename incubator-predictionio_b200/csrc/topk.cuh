@@ -29,6 +29,13 @@ __device__ __forceinline__ bool better(double s1, int i1, double s2, int i2) {
   return (s1 > s2) || (s1 == s2 && i1 < i2);
 }
 
+// order-preserving map double -> unsigned 64-bit (a < b  <=>  key(a) < key(b)); key 0 is below every score
+__device__ __forceinline__ unsigned long long s1_key(double v) {
+  v += 0.0;   // -0.0 -> +0.0: the two compare equal as doubles and must share a key
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
 // Multi-pass selection (topk > TK_MAXK): a pass only accepts candidates strictly worse than the last result of the
 // previous pass.  bound.i == TK_NO_BOUND: accept everything (first pass); TK_EXHAUSTED: the previous pass ran out of
 // candidates, accept nothing.
@@ -264,41 +271,156 @@ score_dot_topk_batched_kernel(const float* __restrict__ Y, int n_items, int kp,
   }
 }
 
-// ---- blocked dot-product scoring: two items x four queries per thread, sixteen warps per SM -------------------------
+// A top-k pool kept SORTED in the registers of one warp: entry g (0 = best) lives in lane g % 32, slot g / 32.  An
+// insertion is one position count (ballots) and one shift (shuffles) -- no search for the worst entry; the threshold is
+// entry topk - 1.  Warp-uniform: cnt.  All 32 lanes call offer(); candidates are taken in lane order.
+struct SortedPool {
+  static constexpr int SLOTS = TK_MAXK / 32;
+  double s[SLOTS];
+  int i[SLOTS];
+  int cnt;
+  double thr;   // score and id of entry topk - 1 once cnt == topk
+  int tid_;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) { s[q] = 0.0; i[q] = -1; }
+    cnt = 0; thr = 0.0; tid_ = -1;
+  }
+  __device__ __forceinline__ void insert(double cs, int ce, int topk) {
+    const int lane = threadIdx.x & 31;
+    const int nslot = (topk + 31) >> 5;
+    int p = 0;   // entries better than the candidate = its position
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q)
+      if (q < nslot) p += __popc(__ballot_sync(0xffffffffu, q * 32 + lane < cnt && better(s[q], i[q], cs, ce)));
+    double carry_s = 0.0;   // lane 31 of the previous slot (moves into lane 0 of this one)
+    int carry_i = -1;
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q)
+      if (q < nslot) {
+        double us = __shfl_up_sync(0xffffffffu, s[q], 1);
+        int ui = __shfl_up_sync(0xffffffffu, i[q], 1);
+        const double last_s = __shfl_sync(0xffffffffu, s[q], 31);
+        const int last_i = __shfl_sync(0xffffffffu, i[q], 31);
+        if (lane == 0) { us = carry_s; ui = carry_i; }
+        const int g = q * 32 + lane;
+        if (g == p) { s[q] = cs; i[q] = ce; }
+        else if (g > p) { s[q] = us; i[q] = ui; }
+        carry_s = last_s;
+        carry_i = last_i;
+      }
+    if (cnt < topk) ++cnt;
+    if (cnt == topk) {
+      const int q = (topk - 1) >> 5, l = (topk - 1) & 31;
+      double ts = 0.0;
+      int ti = -1;
+#pragma unroll
+      for (int qq = 0; qq < SLOTS; ++qq)
+        if (qq == q) { ts = s[qq]; ti = i[qq]; }
+      thr = __shfl_sync(0xffffffffu, ts, l);
+      tid_ = __shfl_sync(0xffffffffu, ti, l);
+    }
+  }
+  // empty pool: the 32 candidates of a step are sorted by a bitonic network (15 exchange stages) instead of being
+  // inserted one after the other; lane g ends up with the g-th best, which IS slot 0 of the pool
+  __device__ __forceinline__ void fill_sorted(bool want, double sc, int ext, int topk) {
+    const int lane = threadIdx.x & 31;
+    double ms = want ? sc : 0.0;
+    int mi = want ? ext : -1;
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, ms, j);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, j);
+        const bool mine_better = mi >= 0 && (oi < 0 || better(ms, mi, os, oi));
+        const bool want_better = ((lane & j) == 0) == ((lane & kk) == 0);   // this lane keeps the better one of the pair
+        if (mine_better != want_better) { ms = os; mi = oi; }
+      }
+    }
+    const int nvalid = __popc(__ballot_sync(0xffffffffu, want));
+    s[0] = ms;
+    i[0] = mi;
+    cnt = nvalid < topk ? nvalid : topk;
+    if (cnt == topk) {      // only possible for topk <= 32: the threshold is entry topk - 1 of slot 0
+      thr = __shfl_sync(0xffffffffu, ms, (topk - 1) & 31);
+      tid_ = __shfl_sync(0xffffffffu, mi, (topk - 1) & 31);
+    }
+  }
+  __device__ __forceinline__ void offer(bool want, double sc, int ext, int topk) {
+    want = want && (cnt < topk || sc >= thr);
+    unsigned m = __ballot_sync(0xffffffffu, want);
+    if (cnt == 0 && (m & (m - 1))) {   // nothing pooled yet and more than one candidate
+      fill_sorted(want, sc, ext, topk);
+      return;
+    }
+    while (m) {
+      const int leader = __ffs(m) - 1;
+      m &= m - 1;
+      const double cs = __shfl_sync(0xffffffffu, sc, leader);
+      const int ce = __shfl_sync(0xffffffffu, ext, leader);
+      if (cnt < topk || better(cs, ce, thr, tid_)) insert(cs, ce, topk);
+    }
+  }
+  // entries to shared memory ([topk] each), best first
+  __device__ __forceinline__ void dump(int topk, double* ps, int* pi) const {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+      const int g = q * 32 + lane;
+      if (g < cnt) { ps[g] = s[q]; pi[g] = i[q]; }
+    }
+  }
+};
+
+// ---- blocked dot-product scoring: two items x eight queries per thread, sixteen warps per SM ------------------------
 // The batched kernel above issues one broadcast LDS.128 of query values per two DFMAs: the shared-memory pipe and the
-// fp64 pipe saturate together.  Here every lane scores TWO items against DB_QW = 4 queries, so one LDS.128 feeds four
-// DFMAs.  A CTA is four independent "rings" of four warps: the warps of a ring share 64 staged rows per step (two-stage
-// cp.async ring, each warp copies a quarter, two named barriers of 128 threads per step -- never a CTA barrier in the
-// scan) and split the 16 queries of the group between them; every warp owns the top-k pools of its four queries
-// (entries and bookkeeping in shared memory; almost every score fails the threshold test, the insertion is an
-// out-of-line call).  16 warps per SM: a single warp cannot keep the fp64 pipe busy (measured: 31 % with one warp per
-// scheduler).  Same arithmetic and order as the kernels above -> bit-identical results.
+// fp64 pipe saturate together.  Here every lane scores TWO items against DB_QW = 8 queries, so one LDS.128 feeds four
+// DFMAs.  A CTA is eight independent "rings" of two warps: the warps of a ring share 64 staged rows per step (each copies
+// half with cp.async; two named barriers of 64 threads per step -- never a CTA barrier in the scan; a ring waits for its
+// own rows while the other seven compute) and split the 16 queries of the group between them; every warp owns the top-k
+// pools of its eight queries (entries and bookkeeping in shared memory; almost every score fails the threshold test, the
+// insertion is an out-of-line call).  Measured on the way: one warp per scheduler with 2 x 16 accumulators keeps the fp64
+// pipe 31 % busy; rings of four warps (4 queries each) convert every row four times and the conversion pipe (F2F: 15.7
+// lanes/clk/SM) becomes co-critical (fp64 45 %, XU 44 %).  Same arithmetic and order as above -> bit-identical results.
 // For kp <= 64 and topk <= DB_MAXK; cand: [n_queries][gridDim.x * DB_RINGS][topk], unsorted, i = -1 = empty.
-constexpr int DB_QW = 4;                     // queries per warp
+constexpr int DB_QW = 8;                     // queries per warp
 constexpr int DB_WPR = SB_QB / DB_QW;        // warps per ring
-constexpr int DB_RINGS = 4;
+constexpr int DB_RINGS = 8;
 constexpr int DB_WARPS = DB_RINGS * DB_WPR;  // 16
 constexpr int DB_ROWS = 64;                  // rows per ring step (two per lane)
+constexpr int DB_STAGES = 1;                 // a ring waits for its own rows while the other seven compute
 constexpr int DB_MAXK = 32;
 struct alignas(16) DbPoolHdr {   // 32 bytes; the first 16 are read with one LDS.128 for the threshold test
   double thr;
   int cnt, wid, worst, pad[3];
 };
 __host__ __device__ inline size_t db_smem_bytes(int kp, int topk) {
-  return sizeof(double) * (size_t)kp * SB_QB + sizeof(float) * (size_t)DB_RINGS * 2 * DB_ROWS * (kp + 4) +
+  return sizeof(double) * (size_t)kp * SB_QB + sizeof(float) * (size_t)DB_RINGS * DB_STAGES * DB_ROWS * (kp + 4) +
          (size_t)DB_RINGS * SB_QB * (sizeof(DbPoolHdr) + (sizeof(double) + sizeof(int)) * (size_t)topk);
 }
 
 // The rare path of the scan (a score passed the threshold test): NOT inlined -- unrolled copies of the pool insertion
 // between the threshold tests of a step are tens of KB of code on the hot path (ncu on a first version: "no
 // instruction" 2.5 stalls per issued instruction).
-__device__ __noinline__ void db_insert(DbPoolHdr* hd, double* ps, int* pi, bool w0, double s0, int e0, bool w1, double s1,
-                                       int e1, int topk) {
-  WarpPool wp;
-  wp.thr = hd->thr; wp.cnt = hd->cnt; wp.wid = hd->wid; wp.worst = hd->worst;
-  wpool_offer(wp, w0, s0, e0, topk, ps, pi);
-  wpool_offer(wp, w1, s1, e1, topk, ps, pi);
-  if ((threadIdx.x & 31) == 0) { hd->thr = wp.thr; hd->cnt = wp.cnt; hd->wid = wp.wid; hd->worst = wp.worst; }
+__device__ __noinline__ void db_insert(DbPoolHdr* hd, double* ps, int* pi, unsigned long long* cthr, bool w0, double s0,
+                                       int e0, bool w1, double s1, int e1, int topk) {
+  // the pool is kept sorted in shared memory (topk <= 32: entry g belongs to lane g); an insertion happens in registers
+  // (SortedPool: ballot-counted position + shuffle shift) between one load and one store of the 32 entries
+  const int lane = threadIdx.x & 31;
+  SortedPool sp;
+  sp.init();
+  sp.cnt = hd->cnt;
+  sp.thr = hd->thr;
+  sp.tid_ = hd->wid;
+  if (lane < sp.cnt) { sp.s[0] = ps[lane]; sp.i[0] = pi[lane]; }
+  sp.offer(w0, s0, e0, topk);
+  sp.offer(w1, s1, e1, topk);
+  if (lane < sp.cnt) { ps[lane] = sp.s[0]; pi[lane] = sp.i[0]; }
+  if (lane == 0) {
+    hd->thr = sp.thr; hd->cnt = sp.cnt; hd->wid = sp.tid_;
+    if (sp.cnt == topk) atomicMax(cthr, s1_key(sp.thr));   // the smallest entry of a FULL pool bounds the query's topk-th score
+  }
   __syncwarp();
 }
 
@@ -313,8 +435,8 @@ score_dot_blocked_kernel(const float* __restrict__ Y, int n_items, const float* 
   constexpr int CPW = DB_ROWS / RPI / DB_WPR;  // copy instructions per warp and step
   extern __shared__ __align__(16) unsigned char db_smem[];
   double* xd = reinterpret_cast<double*>(db_smem);                                   // [KP][SB_QB]
-  float* rings = reinterpret_cast<float*>(xd + (size_t)KP * SB_QB);                  // [DB_RINGS][2][DB_ROWS][ROW]
-  DbPoolHdr* hdrs = reinterpret_cast<DbPoolHdr*>(rings + (size_t)DB_RINGS * 2 * DB_ROWS * ROW);   // [DB_RINGS][SB_QB]
+  float* rings = reinterpret_cast<float*>(xd + (size_t)KP * SB_QB);                  // [DB_RINGS][DB_STAGES][DB_ROWS][ROW]
+  DbPoolHdr* hdrs = reinterpret_cast<DbPoolHdr*>(rings + (size_t)DB_RINGS * DB_STAGES * DB_ROWS * ROW);   // [DB_RINGS][SB_QB]
   double* pss = reinterpret_cast<double*>(hdrs + DB_RINGS * SB_QB);                  // [DB_RINGS][SB_QB][topk]
   int* pis = reinterpret_cast<int*>(pss + (size_t)DB_RINGS * SB_QB * topk);          // [DB_RINGS][SB_QB][topk]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -327,11 +449,15 @@ score_dot_blocked_kernel(const float* __restrict__ Y, int n_items, const float* 
   for (int o = tid; o < DB_RINGS * SB_QB; o += 32 * DB_WARPS) {
     hdrs[o].thr = 0.0; hdrs[o].cnt = 0; hdrs[o].wid = -1; hdrs[o].worst = 0;
   }
+  // per query: key of the best threshold any ring of this CTA has reached -- scores strictly below it are dropped before
+  // they are offered to this ring's pool (eight pools per query would otherwise each warm up on an eighth of the items)
+  __shared__ unsigned long long cthr[SB_QB];
+  if (tid < SB_QB) cthr[tid] = 0ull;
   unsigned qmask = 0;   // my queries that take candidates
   for (int q = 0; q < DB_QW; ++q)
     if (q0 + sub * DB_QW + q < n_queries && qvalid[q0 + sub * DB_QW + q]) qmask |= 1u << q;
   __syncthreads();
-  float* ring = rings + (size_t)rg * 2 * DB_ROWS * ROW;
+  float* ring = rings + (size_t)rg * DB_STAGES * DB_ROWS * ROW;
   DbPoolHdr* hdr = hdrs + rg * SB_QB + sub * DB_QW;
   double* ps = pss + ((size_t)rg * SB_QB + sub * DB_QW) * topk;
   int* pi = pis + ((size_t)rg * SB_QB + sub * DB_QW) * topk;
@@ -344,7 +470,7 @@ score_dot_blocked_kernel(const float* __restrict__ Y, int n_items, const float* 
     if (j < my_steps) {
       const int base = base_of(j);
       const int r0 = sub * CPW * RPI + lane / F4;
-      float* dst = ring + (size_t)(j & 1) * DB_ROWS * ROW + (size_t)r0 * ROW + (lane % F4) * 4;
+      float* dst = ring + (size_t)(j % DB_STAGES) * DB_ROWS * ROW + (size_t)r0 * ROW + (lane % F4) * 4;
       const float* src = Y + (size_t)(base + r0) * KP + (lane % F4) * 4;
       if (base + DB_ROWS <= n_items) {
 #pragma unroll
@@ -357,7 +483,7 @@ score_dot_blocked_kernel(const float* __restrict__ Y, int n_items, const float* 
     }
     asm volatile("cp.async.commit_group;\n" ::);
   };
-  fetch(0);
+  if (DB_STAGES > 1) fetch(0);
   int ext_n[2] = {-1, -1};
   if (my_steps > 0) {
 #pragma unroll
@@ -378,9 +504,9 @@ score_dot_blocked_kernel(const float* __restrict__ Y, int n_items, const float* 
 #pragma unroll
     for (int u = 0; u < 2; ++u)
       if (ext[u] >= 0 && mask && mask[ext[u]]) ext[u] = -1;
-    ring_bar();                // slot (j + 1) & 1 was read in step j - 1 by the four warps of the ring
-    fetch(j + 1);
-    asm volatile("cp.async.wait_group 1;\n" ::);
+    ring_bar();                // the slot about to be refilled has been read by every warp of the ring
+    fetch(j + DB_STAGES - 1);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(DB_STAGES - 1));
     ring_bar();                // step j has landed for the whole ring
     double acc[2][DB_QW];
 #pragma unroll
@@ -388,9 +514,9 @@ score_dot_blocked_kernel(const float* __restrict__ Y, int n_items, const float* 
 #pragma unroll
       for (int q = 0; q < DB_QW; ++q) acc[u][q] = 0.0;
     if (qmask) {
-      const float4* r0 = reinterpret_cast<const float4*>(ring + ((size_t)(j & 1) * DB_ROWS + lane) * ROW);
-      const float4* r1 = reinterpret_cast<const float4*>(ring + ((size_t)(j & 1) * DB_ROWS + 32 + lane) * ROW);
-#pragma unroll 4
+      const float4* r0 = reinterpret_cast<const float4*>(ring + ((size_t)(j % DB_STAGES) * DB_ROWS + lane) * ROW);
+      const float4* r1 = reinterpret_cast<const float4*>(ring + ((size_t)(j % DB_STAGES) * DB_ROWS + 32 + lane) * ROW);
+#pragma unroll 2
       for (int c4 = 0; c4 < F4; ++c4) {
         const float4 a4 = r0[c4], b4 = r1[c4];
         const double ya[4] = {(double)a4.x, (double)a4.y, (double)a4.z, (double)a4.w};
@@ -424,10 +550,12 @@ score_dot_blocked_kernel(const float* __restrict__ Y, int n_items, const float* 
       const int4 h4 = *reinterpret_cast<const int4*>(&hdr[q]);       // thr (8 bytes), cnt, wid
       const double thr = __hiloint2double(h4.y, h4.x);
       const int cnt = h4.z;
-      const bool w0 = ext[0] >= 0 && (cnt < topk || acc[0][q] >= thr);
-      const bool w1 = ext[1] >= 0 && (cnt < topk || acc[1][q] >= thr);
+      const unsigned long long ck = *reinterpret_cast<volatile unsigned long long*>(&cthr[sub * DB_QW + q]);
+      const bool w0 = ext[0] >= 0 && (cnt < topk || acc[0][q] >= thr) && s1_key(acc[0][q]) >= ck;
+      const bool w1 = ext[1] >= 0 && (cnt < topk || acc[1][q] >= thr) && s1_key(acc[1][q]) >= ck;
       if (!__any_sync(0xffffffffu, w0 || w1)) continue;
-      db_insert(&hdr[q], ps + (size_t)q * topk, pi + (size_t)q * topk, w0, acc[0][q], ext[0], w1, acc[1][q], ext[1], topk);
+      db_insert(&hdr[q], ps + (size_t)q * topk, pi + (size_t)q * topk, &cthr[sub * DB_QW + q], w0, acc[0][q], ext[0], w1,
+                acc[1][q], ext[1], topk);
     }
   }
   asm volatile("cp.async.wait_group 0;\n" ::);
@@ -979,120 +1107,11 @@ __device__ __forceinline__ int s1_merge(const ScoreIdx* c, int n_cand, int topk,
   return total < topk ? total : topk;
 }
 
-// A top-k pool kept SORTED in the registers of one warp: entry g (0 = best) lives in lane g % 32, slot g / 32.  An
-// insertion is one position count (ballots) and one shift (shuffles) -- no search for the worst entry; the threshold is
-// entry topk - 1.  Warp-uniform: cnt.  All 32 lanes call offer(); candidates are taken in lane order.
-struct SortedPool {
-  static constexpr int SLOTS = TK_MAXK / 32;
-  double s[SLOTS];
-  int i[SLOTS];
-  int cnt;
-  double thr;   // score and id of entry topk - 1 once cnt == topk
-  int tid_;
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q) { s[q] = 0.0; i[q] = -1; }
-    cnt = 0; thr = 0.0; tid_ = -1;
-  }
-  __device__ __forceinline__ void insert(double cs, int ce, int topk) {
-    const int lane = threadIdx.x & 31;
-    const int nslot = (topk + 31) >> 5;
-    int p = 0;   // entries better than the candidate = its position
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q)
-      if (q < nslot) p += __popc(__ballot_sync(0xffffffffu, q * 32 + lane < cnt && better(s[q], i[q], cs, ce)));
-    double carry_s = 0.0;   // lane 31 of the previous slot (moves into lane 0 of this one)
-    int carry_i = -1;
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q)
-      if (q < nslot) {
-        double us = __shfl_up_sync(0xffffffffu, s[q], 1);
-        int ui = __shfl_up_sync(0xffffffffu, i[q], 1);
-        const double last_s = __shfl_sync(0xffffffffu, s[q], 31);
-        const int last_i = __shfl_sync(0xffffffffu, i[q], 31);
-        if (lane == 0) { us = carry_s; ui = carry_i; }
-        const int g = q * 32 + lane;
-        if (g == p) { s[q] = cs; i[q] = ce; }
-        else if (g > p) { s[q] = us; i[q] = ui; }
-        carry_s = last_s;
-        carry_i = last_i;
-      }
-    if (cnt < topk) ++cnt;
-    if (cnt == topk) {
-      const int q = (topk - 1) >> 5, l = (topk - 1) & 31;
-      double ts = 0.0;
-      int ti = -1;
-#pragma unroll
-      for (int qq = 0; qq < SLOTS; ++qq)
-        if (qq == q) { ts = s[qq]; ti = i[qq]; }
-      thr = __shfl_sync(0xffffffffu, ts, l);
-      tid_ = __shfl_sync(0xffffffffu, ti, l);
-    }
-  }
-  // empty pool: the 32 candidates of a step are sorted by a bitonic network (15 exchange stages) instead of being
-  // inserted one after the other; lane g ends up with the g-th best, which IS slot 0 of the pool
-  __device__ __forceinline__ void fill_sorted(bool want, double sc, int ext, int topk) {
-    const int lane = threadIdx.x & 31;
-    double ms = want ? sc : 0.0;
-    int mi = want ? ext : -1;
-#pragma unroll
-    for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-      for (int j = kk >> 1; j > 0; j >>= 1) {
-        const double os = __shfl_xor_sync(0xffffffffu, ms, j);
-        const int oi = __shfl_xor_sync(0xffffffffu, mi, j);
-        const bool mine_better = mi >= 0 && (oi < 0 || better(ms, mi, os, oi));
-        const bool want_better = ((lane & j) == 0) == ((lane & kk) == 0);   // this lane keeps the better one of the pair
-        if (mine_better != want_better) { ms = os; mi = oi; }
-      }
-    }
-    const int nvalid = __popc(__ballot_sync(0xffffffffu, want));
-    s[0] = ms;
-    i[0] = mi;
-    cnt = nvalid < topk ? nvalid : topk;
-    if (cnt == topk) {      // only possible for topk <= 32: the threshold is entry topk - 1 of slot 0
-      thr = __shfl_sync(0xffffffffu, ms, (topk - 1) & 31);
-      tid_ = __shfl_sync(0xffffffffu, mi, (topk - 1) & 31);
-    }
-  }
-  __device__ __forceinline__ void offer(bool want, double sc, int ext, int topk) {
-    want = want && (cnt < topk || sc >= thr);
-    unsigned m = __ballot_sync(0xffffffffu, want);
-    if (cnt == 0 && (m & (m - 1))) {   // nothing pooled yet and more than one candidate
-      fill_sorted(want, sc, ext, topk);
-      return;
-    }
-    while (m) {
-      const int leader = __ffs(m) - 1;
-      m &= m - 1;
-      const double cs = __shfl_sync(0xffffffffu, sc, leader);
-      const int ce = __shfl_sync(0xffffffffu, ext, leader);
-      if (cnt < topk || better(cs, ce, thr, tid_)) insert(cs, ce, topk);
-    }
-  }
-  // entries to shared memory ([topk] each), best first
-  __device__ __forceinline__ void dump(int topk, double* ps, int* pi) const {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q) {
-      const int g = q * 32 + lane;
-      if (g < cnt) { ps[g] = s[q]; pi[g] = i[q]; }
-    }
-  }
-};
-
 // streaming copy: the scanned matrix is marked evict-first in L2, so that what the NEXT query needs again (this kernel's
 // code, the id maps, the query rows) is not pushed out of the 126 MB L2 by a 256 MB scan
 __device__ __forceinline__ void s1_cp_async16_stream(void* smem_dst, const void* gsrc, unsigned long long policy) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "l"(policy));
-}
-
-// order-preserving map double -> unsigned 64-bit (a < b  <=>  key(a) < key(b)); key 0 is below every score
-__device__ __forceinline__ unsigned long long s1_key(double v) {
-  v += 0.0;   // -0.0 -> +0.0: the two compare equal as doubles and must share a key
-  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
 template <bool COS, int NVP, int KP>

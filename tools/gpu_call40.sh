@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "batched_recommend" > gpurun_out/c37_pytest.log 2>&1
-tail -n 3 gpurun_out/c37_pytest.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "batched_recommend" > gpurun_out/c40_pytest.log 2>&1
+tail -n 3 gpurun_out/c40_pytest.log
 python - <<'PY'
 import sys, time, numpy as np, os
 sys.path.insert(0, os.getcwd())
@@ -29,4 +29,4 @@ users = np.arange(nu, dtype=np.int32)
 m = native.NativeALS.from_factors(uf, itf, None, None)
 m.recommend(users, 10)
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_dot_blocked -c 1 -f -o gpurun_out/c37_blocked python /tmp/rb.py > gpurun_out/c37.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_dot_blocked -c 1 -f -o gpurun_out/c40_blocked python /tmp/rb.py > gpurun_out/c40.log 2>&1
