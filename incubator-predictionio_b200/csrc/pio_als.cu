@@ -1777,6 +1777,31 @@ static int launch_dot_blocked_kp(pio_als_handle* h, dim3 grid, size_t smem, cons
   return PIO_ALS_OK;
 }
 }  // extern "C++"
+extern "C++" {
+template <int KPT>
+static int launch_cos_blocked_kp(pio_als_handle* h, dim3 grid, size_t smem, const float* d_qf, const int* d_bq0, const int* d_bv0,
+                                 int n_bins, const int* d_vq, const long long* d_qptr, const int* d_qid, const uint8_t* d_mask,
+                                 const double* d_weight, int keep, int topk, ScoreIdx* d_cand) {
+  static size_t attr_smem[64] = {};
+  if (h->cfg.device < 64 && attr_smem[h->cfg.device] < smem) {
+    CK(h, cudaFuncSetAttribute(score_cos_blocked_kernel<KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[h->cfg.device] = smem;
+  }
+  score_cos_blocked_kernel<KPT><<<grid, 32 * DB_WARPS, smem, h->stream>>>(h->I.F, h->I.n_internal, h->cfg.rank, d_qf, d_bq0, d_bv0,
+                                                                         n_bins, d_vq, d_qptr, d_qid, h->I.cand_ext, d_mask,
+                                                                         d_weight, keep, topk, d_cand);
+  return PIO_ALS_OK;
+}
+}  // extern "C++"
+static int launch_cos_blocked(pio_als_handle* h, dim3 grid, size_t smem, const float* d_qf, const int* d_bq0, const int* d_bv0,
+                              int n_bins, const int* d_vq, const long long* d_qptr, const int* d_qid, const uint8_t* d_mask,
+                              const double* d_weight, int keep, int topk, ScoreIdx* d_cand) {
+  if (h->KP == 16)
+    return launch_cos_blocked_kp<16>(h, grid, smem, d_qf, d_bq0, d_bv0, n_bins, d_vq, d_qptr, d_qid, d_mask, d_weight, keep, topk, d_cand);
+  if (h->KP == 32)
+    return launch_cos_blocked_kp<32>(h, grid, smem, d_qf, d_bq0, d_bv0, n_bins, d_vq, d_qptr, d_qid, d_mask, d_weight, keep, topk, d_cand);
+  return launch_cos_blocked_kp<64>(h, grid, smem, d_qf, d_bq0, d_bv0, n_bins, d_vq, d_qptr, d_qid, d_mask, d_weight, keep, topk, d_cand);
+}
 static int launch_dot_blocked(pio_als_handle* h, dim3 grid, size_t smem, const float* d_xq, const uint8_t* d_valid, int nq,
                               const uint8_t* d_mask, const double* d_weight, int topk, ScoreIdx* d_cand) {
   if (h->KP == 16) return launch_dot_blocked_kp<16>(h, grid, smem, d_xq, d_valid, nq, d_mask, d_weight, topk, d_cand);
@@ -2232,6 +2257,83 @@ int pio_als_similar_batch(pio_als_handle* h, const int64_t* q_ptr, const int32_t
     std::vector<uint8_t> valid((size_t)total);
     CK(h, cudaMemcpyAsync(valid.data(), d_valid, (size_t)total, cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
+    // blocked kernel: bins of <= CB_QPW consecutive queries and <= DB_QW query vectors per warp (rank <= 64, topk <= DB_MAXK)
+    if (h->score_blocked && KP <= 64 && topk <= DB_MAXK) {
+      std::vector<int> bin_q0, bin_v0, bvq, bvsrc;
+      bool ok = true;
+      int bq = 0, bv = 0;      // queries / vectors in the open bin
+      bin_q0.push_back(0);
+      bin_v0.push_back(0);
+      for (int j = 0; j < n_queries && ok; ++j) {
+        int nvq = 0;
+        for (long long t = q_ptr[j]; t < q_ptr[j + 1]; ++t) nvq += valid[(size_t)(t - q_ptr[0])] ? 1 : 0;
+        if (nvq > DB_QW) { ok = false; break; }
+        if (bq == CB_QPW || bv + nvq > DB_QW) {
+          bin_q0.push_back(j);
+          bin_v0.push_back((int)bvsrc.size());
+          bq = bv = 0;
+        }
+        for (long long t = q_ptr[j]; t < q_ptr[j + 1]; ++t)
+          if (valid[(size_t)(t - q_ptr[0])]) {
+            bvsrc.push_back((int)(t - q_ptr[0]));
+            bvq.push_back(j);
+          }
+        ++bq;
+        bv += nvq;
+      }
+      if (ok) {
+        bin_q0.push_back(n_queries);
+        bin_v0.push_back((int)bvsrc.size());
+        const int n_bins = (int)bin_q0.size() - 1, nvec = (int)bvsrc.size();
+        const int ngroups = (n_bins + DB_WPR - 1) / DB_WPR;
+        int *d_bq0 = nullptr, *d_bv0 = nullptr, *d_vq = nullptr, *d_vsrc = nullptr, *d_oi = nullptr, *d_oc = nullptr;
+        long long* d_qptr = nullptr;
+        float *d_qfc = nullptr, *d_os = nullptr;
+        ScoreIdx* d_cand = nullptr;
+        std::vector<long long> rel((size_t)n_queries + 1);
+        for (int j = 0; j <= n_queries; ++j) rel[j] = q_ptr[j] - q_ptr[0];
+        CK(h, tmp.alloc(&d_bq0, bin_q0.size()));
+        CK(h, tmp.alloc(&d_bv0, bin_v0.size()));
+        CK(h, tmp.alloc(&d_vq, (size_t)(nvec > 0 ? nvec : 1)));
+        CK(h, tmp.alloc(&d_vsrc, (size_t)(nvec > 0 ? nvec : 1)));
+        CK(h, tmp.alloc(&d_qptr, rel.size()));
+        CK(h, tmp.alloc(&d_qfc, (size_t)(nvec > 0 ? nvec : 1) * KP));
+        CK(h, cudaMemcpyAsync(d_bq0, bin_q0.data(), sizeof(int) * bin_q0.size(), cudaMemcpyHostToDevice, st));
+        CK(h, cudaMemcpyAsync(d_bv0, bin_v0.data(), sizeof(int) * bin_v0.size(), cudaMemcpyHostToDevice, st));
+        CK(h, cudaMemcpyAsync(d_qptr, rel.data(), sizeof(long long) * rel.size(), cudaMemcpyHostToDevice, st));
+        if (nvec > 0) {
+          CK(h, cudaMemcpyAsync(d_vq, bvq.data(), sizeof(int) * nvec, cudaMemcpyHostToDevice, st));
+          CK(h, cudaMemcpyAsync(d_vsrc, bvsrc.data(), sizeof(int) * nvec, cudaMemcpyHostToDevice, st));
+          copy_rows_kernel<<<nvec, 64, 0, st>>>(d_qf_all, KP, d_vsrc, d_qfc);
+          LAUNCHED(h);
+        }
+        const int nsteps = (h->I.n_internal + DB_RINGS * DB_ROWS - 1) / (DB_RINGS * DB_ROWS);
+        int gx = (h->sm_count + ngroups - 1) / ngroups;
+        if (gx > (nsteps + 7) / 8) gx = (nsteps + 7) / 8;
+        if (gx < 1) gx = 1;
+        const int lists = gx * DB_RINGS;
+        CK(h, tmp.alloc(&d_cand, (size_t)n_queries * lists * topk));
+        CK(h, tmp.alloc(&d_oi, (size_t)n_queries * topk));
+        CK(h, tmp.alloc(&d_os, (size_t)n_queries * topk));
+        CK(h, tmp.alloc(&d_oc, (size_t)n_queries));
+        const int keep_query = (flags & PIO_ALS_SIM_KEEP_QUERY_ITEMS) ? 1 : 0;
+        const size_t smem = db_smem_bytes(KP, topk);
+        for (int g0 = 0; g0 < ngroups; g0 += 32768) {
+          const int ng = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
+          const int brc = launch_cos_blocked(h, dim3(gx, ng), smem, d_qfc, d_bq0 + (size_t)g0 * DB_WPR, d_bv0 + (size_t)g0 * DB_WPR,
+                                             n_bins - g0 * DB_WPR, d_vq, d_qptr, d_qid, d_mask, d_weight, keep_query, topk, d_cand);
+          if (brc) return brc;
+          LAUNCHED(h);
+        }
+        topk_merge_kernel<<<n_queries, TK_THREADS, 0, st>>>(d_cand, lists * topk, topk, topk, 0, d_oi, d_os, d_oc, nullptr);
+        LAUNCHED(h);
+        CK(h, cudaMemcpyAsync(out_items, d_oi, sizeof(int) * (size_t)n_queries * topk, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaMemcpyAsync(out_scores, d_os, sizeof(float) * (size_t)n_queries * topk, cudaMemcpyDeviceToHost, st));
+        if (out_count) CK(h, cudaMemcpyAsync(out_count, d_oc, sizeof(int) * (size_t)n_queries, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaStreamSynchronize(st));
+        return PIO_ALS_OK;
+      }
+    }
     const int ngroups = (n_queries + SM_QG - 1) / SM_QG;
     gvec0.assign((size_t)ngroups + 1, 0);
     for (int g = 0; g < ngroups && fast; ++g) {

@@ -575,6 +575,234 @@ score_dot_blocked_kernel(const float* __restrict__ Y, int n_items, const float* 
   }
 }
 
+// ---- blocked cosine scoring (similarproduct batches): the same rings, eight query VECTORS per warp ------------------
+// The host packs consecutive queries into bins of <= CB_QPW queries and <= DB_QW query vectors (a query never spans two
+// bins); a warp scores two items per lane against the vectors of its bin, turns them into per-query cosine sums (in
+// query-vector order, fp64 -- bit-identical to the kernels below) and keeps the pools of its queries.  blockIdx.y = a pair
+// of bins (the two warps of every ring).  bin_q0 / bin_v0: first query / first vector of every bin (+ one end entry);
+// qf: the query vectors [n_vec][KP]; vq: global query of every vector; qid_ptr / qid: the id list of every query (all
+// of them are excluded from its results unless keep_query).  cand: [n_queries][gridDim.x * DB_RINGS][topk].
+constexpr int CB_QPW = 4;   // queries per warp
+
+__device__ __noinline__ void cb_insert(DbPoolHdr* hd, double* ps, int* pi, unsigned long long* cthr, bool w0, double s0,
+                                       int e0, bool w1, double s1, int e1, int topk, const int* __restrict__ qid, int nid) {
+  // (rare path) the query's own items are no candidates (ALSAlgorithm.scala:243-245 `!queryList.contains(i)`); nid = 0
+  // when they are kept
+  for (int t = 0; t < nid; ++t) {
+    const int id = __ldg(qid + t);
+    if (id == e0) w0 = false;
+    if (id == e1) w1 = false;
+  }
+  if (!__any_sync(0xffffffffu, w0 || w1)) return;
+  db_insert(hd, ps, pi, cthr, w0, s0, e0, w1, s1, e1, topk);
+}
+
+template <int KP>
+__global__ void __launch_bounds__(32 * DB_WARPS, 1)
+score_cos_blocked_kernel(const float* __restrict__ Y, int n_items, int k, const float* __restrict__ qf,
+                         const int* __restrict__ bin_q0, const int* __restrict__ bin_v0, int n_bins,
+                         const int* __restrict__ vq, const long long* __restrict__ qid_ptr, const int* __restrict__ qid,
+                         const int* __restrict__ cand_ext, const uint8_t* __restrict__ mask,
+                         const double* __restrict__ weight, int keep_query, int topk, ScoreIdx* __restrict__ cand) {
+  constexpr int ROW = KP + 4, F4 = KP / 4;
+  constexpr int RPI = 32 / F4;
+  constexpr int CPW = DB_ROWS / RPI / DB_WPR;
+  constexpr int NV = DB_QW;                    // vectors per warp
+  constexpr int GQ = DB_WPR * CB_QPW;          // pools per ring
+  extern __shared__ __align__(16) unsigned char db_smem[];
+  double* xd = reinterpret_cast<double*>(db_smem);                                   // [KP][DB_WPR * NV]
+  float* rings = reinterpret_cast<float*>(xd + (size_t)KP * SB_QB);                  // [DB_RINGS][DB_STAGES][DB_ROWS][ROW]
+  DbPoolHdr* hdrs = reinterpret_cast<DbPoolHdr*>(rings + (size_t)DB_RINGS * DB_STAGES * DB_ROWS * ROW);   // [DB_RINGS][GQ]
+  double* pss = reinterpret_cast<double*>(hdrs + DB_RINGS * SB_QB);                  // [DB_RINGS][GQ][topk]
+  int* pis = reinterpret_cast<int*>(pss + (size_t)DB_RINGS * SB_QB * topk);
+  __shared__ double s1[DB_WPR * NV];
+  __shared__ int svq[DB_WPR * NV];             // local query (0 .. CB_QPW - 1) of every vector
+  __shared__ unsigned long long cthr[GQ];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rg = warp / DB_WPR, sub = warp % DB_WPR;
+  const int bin = blockIdx.y * DB_WPR + sub;
+  const bool have_bin = bin < n_bins;
+  const int bq0 = have_bin ? bin_q0[bin] : 0, nqw = have_bin ? bin_q0[bin + 1] - bq0 : 0;
+  const int bv0 = have_bin ? bin_v0[bin] : 0, nvw = have_bin ? bin_v0[bin + 1] - bv0 : 0;
+  static_assert(DB_WPR * NV == SB_QB, "xd is laid out [KP][SB_QB]");
+  for (int o = tid; o < KP * SB_QB; o += 32 * DB_WARPS) {
+    const int c = o / SB_QB, col = o % SB_QB, sb = col / NV, v = col % NV;
+    const int b = blockIdx.y * DB_WPR + sb;
+    double x = 0.0;
+    if (b < n_bins) {
+      const int v0 = bin_v0[b];
+      if (v < bin_v0[b + 1] - v0) x = (double)qf[(size_t)(v0 + v) * KP + c];
+    }
+    xd[o] = x;
+  }
+  if (tid < SB_QB) {
+    const int sb = tid / NV, v = tid % NV, b = blockIdx.y * DB_WPR + sb;
+    double n1 = 0.0;
+    int lq = 0;
+    if (b < n_bins) {
+      const int v0 = bin_v0[b];
+      if (v < bin_v0[b + 1] - v0) {
+        for (int c = 0; c < k; ++c) {
+          const double a = (double)qf[(size_t)(v0 + v) * KP + c];
+          n1 += a * a;
+        }
+        lq = vq[v0 + v] - bin_q0[b];
+      }
+    }
+    s1[tid] = sqrt(n1);
+    svq[tid] = lq;
+  }
+  for (int o = tid; o < DB_RINGS * GQ; o += 32 * DB_WARPS) {
+    hdrs[o].thr = 0.0; hdrs[o].cnt = 0; hdrs[o].wid = -1; hdrs[o].worst = 0;
+  }
+  if (tid < GQ) cthr[tid] = 0ull;
+  __syncthreads();
+  float* ring = rings + (size_t)rg * DB_STAGES * DB_ROWS * ROW;
+  DbPoolHdr* hdr = hdrs + rg * GQ + sub * CB_QPW;
+  double* ps = pss + ((size_t)rg * GQ + sub * CB_QPW) * topk;
+  int* pi = pis + ((size_t)rg * GQ + sub * CB_QPW) * topk;
+  const double* xw = xd + sub * NV;
+  double s1r[NV];
+  int vqr[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) { s1r[v] = s1[sub * NV + v]; vqr[v] = svq[sub * NV + v]; }
+  const int* qid_of[CB_QPW];
+  int nid_of[CB_QPW];
+#pragma unroll
+  for (int q = 0; q < CB_QPW; ++q) {
+    qid_of[q] = qid;
+    nid_of[q] = 0;
+    if (q < nqw && !keep_query) {
+      qid_of[q] = qid + qid_ptr[bq0 + q];
+      nid_of[q] = (int)(qid_ptr[bq0 + q + 1] - qid_ptr[bq0 + q]);
+    }
+  }
+  auto ring_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + rg), "r"(32 * DB_WPR) : "memory"); };
+  const int nsteps = (n_items + DB_RINGS * DB_ROWS - 1) / (DB_RINGS * DB_ROWS);
+  const int my_steps = (int)blockIdx.x < nsteps ? (nsteps - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto base_of = [&](int j) { return (((int)blockIdx.x + j * (int)gridDim.x) * DB_RINGS + rg) * DB_ROWS; };
+  auto fetch = [&](int j) {
+    if (j < my_steps) {
+      const int base = base_of(j);
+      const int r0 = sub * CPW * RPI + lane / F4;
+      float* dst = ring + (size_t)(j % DB_STAGES) * DB_ROWS * ROW + (size_t)r0 * ROW + (lane % F4) * 4;
+      const float* src = Y + (size_t)(base + r0) * KP + (lane % F4) * 4;
+      if (base + DB_ROWS <= n_items) {
+#pragma unroll
+        for (int m = 0; m < CPW; ++m) sb_cp_async16(dst + (size_t)m * RPI * ROW, src + (size_t)m * RPI * KP);
+      } else {
+#pragma unroll
+        for (int m = 0; m < CPW; ++m)
+          if (base + r0 + m * RPI < n_items) sb_cp_async16(dst + (size_t)m * RPI * ROW, src + (size_t)m * RPI * KP);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  if (DB_STAGES > 1) fetch(0);
+  int ext_n[2] = {-1, -1};
+  if (my_steps > 0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = base_of(0) + u * 32 + lane;
+      ext_n[u] = i < n_items ? __ldg(cand_ext + i) : -1;
+    }
+  }
+  for (int j = 0; j < my_steps; ++j) {
+    int ext[2] = {ext_n[0], ext_n[1]};
+    if (j + 1 < my_steps) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = base_of(j + 1) + u * 32 + lane;
+        ext_n[u] = i < n_items ? __ldg(cand_ext + i) : -1;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (ext[u] >= 0 && mask && mask[ext[u]]) ext[u] = -1;
+    ring_bar();
+    fetch(j + DB_STAGES - 1);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(DB_STAGES - 1));
+    ring_bar();
+    if (nvw == 0) continue;     // (uniform per warp) nothing to score: the barriers above keep the ring in step
+    double d[2][NV], n2[2] = {0.0, 0.0};
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) d[u][v] = 0.0;
+    {
+      const float4* r0 = reinterpret_cast<const float4*>(ring + ((size_t)(j % DB_STAGES) * DB_ROWS + lane) * ROW);
+      const float4* r1 = reinterpret_cast<const float4*>(ring + ((size_t)(j % DB_STAGES) * DB_ROWS + 32 + lane) * ROW);
+#pragma unroll 2
+      for (int c4 = 0; c4 < F4; ++c4) {
+        const float4 a4 = r0[c4], b4 = r1[c4];
+        const double ya[4] = {(double)a4.x, (double)a4.y, (double)a4.z, (double)a4.w};
+        const double yb[4] = {(double)b4.x, (double)b4.y, (double)b4.z, (double)b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          n2[0] = fma(ya[e], ya[e], n2[0]);
+          n2[1] = fma(yb[e], yb[e], n2[1]);
+          const double2* xr = reinterpret_cast<const double2*>(xw + (size_t)(c4 * 4 + e) * SB_QB);
+#pragma unroll
+          for (int v = 0; v < NV; v += 2) {
+            const double2 x2 = xr[v / 2];
+            d[0][v] = fma(x2.x, ya[e], d[0][v]);
+            d[0][v + 1] = fma(x2.y, ya[e], d[0][v + 1]);
+            d[1][v] = fma(x2.x, yb[e], d[1][v]);
+            d[1][v + 1] = fma(x2.y, yb[e], d[1][v + 1]);
+          }
+        }
+      }
+    }
+    double sc[2][CB_QPW];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int q = 0; q < CB_QPW; ++q) sc[u][q] = 0.0;
+      const double s2 = sqrt(n2[u]);
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        if (v < nvw) {
+          const double n1n2 = s1r[v] * s2;
+          const double term = (n1n2 == 0.0) ? 0.0 : d[u][v] / n1n2;
+#pragma unroll
+          for (int q = 0; q < CB_QPW; ++q)
+            if (vqr[v] == q) sc[u][q] += term;      // the vectors of a query are consecutive: the sum runs in query order
+        }
+      if (weight && ext[u] >= 0) {
+        const double w = weight[ext[u]];
+#pragma unroll
+        for (int q = 0; q < CB_QPW; ++q) sc[u][q] = sc[u][q] * w;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CB_QPW; ++q) {
+      if (q >= nqw) continue;
+      const int4 h4 = *reinterpret_cast<const int4*>(&hdr[q]);
+      const double thr = __hiloint2double(h4.y, h4.x);
+      const int cnt = h4.z;
+      const unsigned long long ck = *reinterpret_cast<volatile unsigned long long*>(&cthr[sub * CB_QPW + q]);
+      const bool w0 = ext[0] >= 0 && sc[0][q] > 0.0 && (cnt < topk || sc[0][q] >= thr) && s1_key(sc[0][q]) >= ck;
+      const bool w1 = ext[1] >= 0 && sc[1][q] > 0.0 && (cnt < topk || sc[1][q] >= thr) && s1_key(sc[1][q]) >= ck;
+      if (!__any_sync(0xffffffffu, w0 || w1)) continue;
+      cb_insert(&hdr[q], ps + (size_t)q * topk, pi + (size_t)q * topk, &cthr[sub * CB_QPW + q], w0, sc[0][q], ext[0], w1,
+                sc[1][q], ext[1], topk, qid_of[q], nid_of[q]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncwarp();
+#pragma unroll 1
+  for (int q = 0; q < nqw; ++q) {
+    const int cnt = hdr[q].cnt;
+    ScoreIdx* out = cand + (((size_t)(bq0 + q) * gridDim.x + blockIdx.x) * DB_RINGS + rg) * topk;
+    for (int t = lane; t < topk; t += 32) {
+      ScoreIdx e;
+      e.s = t < cnt ? ps[(size_t)q * topk + t] : 0.0;
+      e.i = t < cnt ? pi[(size_t)q * topk + t] : -1;
+      out[t] = e;
+    }
+  }
+}
+
 // ---- similarproduct scoring, same structure: one query = nqv item vectors -------------------------------------
 // qf: [nqv][kp] vectors of the query items that own a factor (query order kept); qid: all nq_all query item ids
 // (external) - every one of them is excluded from the candidates (ALSAlgorithm.scala:243-245).  score_i = sum over the

@@ -435,6 +435,42 @@ def test_batched_recommend_blocked_kernel_is_bit_exact(native, oracle, monkeypat
         m0.close()
 
 
+def test_batched_similar_blocked_kernel_is_bit_exact(native, oracle, monkeypatch):
+    """pio_als_similar_batch on the blocked cosine kernel (bins of <= 4 queries / <= 8 query vectors per warp, topk <= 32,
+    rank <= 64): hundreds of queries of 0..8 items with unknown and factor-less items mixed in, masks, weights, kept query
+    items -- against the oracle and the one-item-per-thread kernel; a query of 9 items sends the call to the old path."""
+    rng = np.random.default_rng(44)
+    for k, ni in ((64, 20_000), (24, 3_000)):
+        itf = synth.synth_init_factors(ni, k, 9, 1)
+        itf *= (1.0 + (np.arange(ni, dtype=np.float32) % 71)[:, None] / 71.0)
+        ih = (np.arange(ni) % 17 != 6).astype(np.uint8)
+        m = native.NativeALS.from_factors(None, itf, None, ih)
+        monkeypatch.setenv("PIO_ALS_SCORE_BLOCKED", "0")
+        m0 = native.NativeALS.from_factors(None, itf, None, ih)
+        monkeypatch.delenv("PIO_ALS_SCORE_BLOCKED")
+        w = np.ones(ni, np.float64)
+        w[rng.integers(0, ni, 200)] = rng.choice([0.0, 0.5, 2.0, -1.0], 200)
+        mask = (np.arange(ni) % 5 == 0).astype(np.uint8)
+        pool = np.concatenate([np.flatnonzero(ih)[:500], np.flatnonzero(ih == 0)[:5]])
+        queries = [list(rng.choice(pool, rng.integers(0, 9), replace=False)) for _ in range(203)]
+        queries[7] = []
+        for topk in (1, 20, 32):
+            for mk, wt, keep in ((None, None, False), (mask, w, False), (None, w, True)):
+                bi, bs, bc = m.similar_batch(queries, topk, mk, wt, keep_query_items=keep)
+                zi, zs, zc = m0.similar_batch(queries, topk, mk, wt, keep_query_items=keep)
+                assert np.array_equal(bi, zi) and np.array_equal(bs, zs) and np.array_equal(bc, zc), (k, topk, keep)
+                for j in range(0, len(queries), 7):
+                    oi, os_, oc = oracle.similar(itf, ih, np.array(queries[j], np.int32), topk, mk, wt, keep)
+                    assert bc[j] == oc and np.array_equal(bi[j], oi) and np.array_equal(bs[j], os_), (k, topk, keep, j)
+        big = queries[:20] + [list(np.flatnonzero(ih)[:9])]
+        bi, bs, bc = m.similar_batch(big, 20)
+        for j in (0, 5, 20):
+            oi, os_, oc = oracle.similar(itf, ih, np.array(big[j], np.int32), 20)
+            assert bc[j] == oc and np.array_equal(bi[j], oi) and np.array_equal(bs[j], os_)
+        m.close()
+        m0.close()
+
+
 def test_load_rejects_corrupt_files(native, tmp_path):
     nu, ni = 50, 40
     u, i, r = synth.synth_ratings(nu, ni, 800, seed=8, implicit=False)
