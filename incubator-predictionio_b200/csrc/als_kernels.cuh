@@ -659,16 +659,23 @@ als_finish_ls128_kernel(const SolveParams p, const int* __restrict__ row_part_pt
 // ------------------------------------------------------------------------------------------
 constexpr int GRAM_THREADS = 256;
 constexpr int GRAM_ROWS = 32;
+// YtY = sum over GRAM_GROUPS = 8 CLASSES of rows, each class summed block by block in a fixed order, then the class sums
+// in class order.  Class g = the rows whose degree-rank position p has p mod 16 in {g, 15 - g}: exactly the rows the
+// serpentine dealing of assign_internal_kernel gives to rank g of an 8-GPU job, and for 4 / 2 / 1 GPUs every rank owns
+// whole classes.  So on any of these world sizes a rank can sum its classes from its OWN rows right after solving them
+// (while the factor all-gather is still in flight), the ranks all-gather 8 x KP^2 doubles, and the result is
+// bit-identical to the single-GPU sum.
+constexpr int GRAM_GROUPS = 8;
+struct GramMap {
+  int cls[GRAM_GROUPS];      // class of the lg-th group this launch computes
+  int slot_of[GRAM_GROUPS];  // storage slot of class g (a rank's slots are contiguous: the all-gather concatenates by rank)
+};
 
 template <int KP>
 __global__ void __launch_bounds__(GRAM_THREADS)
 gram_partial_kernel(const float* __restrict__ X, const int* __restrict__ p2i, int n_rows, double* __restrict__ partial,
-                    int block0, int n_blocks) {
-  // The rows are cut into n_blocks position ranges; this launch covers the ranges block0 .. block0 + gridDim.x - 1 (a
-  // sharded run gives every rank a contiguous share of the ranges and all-gathers the partials: the reduction below then
-  // adds the same n_blocks partials in the same order on every rank and on a single GPU).
-  // rows are visited in degree-rank position order (p2i: position -> internal id), which does not depend on how the
-  // rows are dealt to ranks: a sharded run sums YtY in exactly the order of the single-GPU run
+                    int slot0, int bpg, const GramMap map) {
+  // grid: (groups of this launch) x bpg blocks; block b of a class covers a fixed range of the class's positions
   constexpr int TM = KP / 16;
   __shared__ __align__(16) float tile[GRAM_ROWS * KP];
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
@@ -677,47 +684,48 @@ gram_partial_kernel(const float* __restrict__ X, const int* __restrict__ p2i, in
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < TM; ++j) acc[i][j] = 0.0;
-  const int blk = block0 + blockIdx.x;
-  const int per = (n_rows + n_blocks - 1) / n_blocks;
-  const int r0 = min(n_rows, blk * per);
-  const int r1 = min(n_rows, r0 + per);
-  for (int base = r0; base < r1; base += GRAM_ROWS) {
-    const int nr = min(GRAM_ROWS, r1 - base);
+  const int lg = blockIdx.x / bpg, b = blockIdx.x % bpg, g = map.cls[lg];
+  const int rem = n_rows % 16;
+  const int T = 2 * (n_rows / 16) + (g < rem ? 1 : 0) + (15 - g < rem ? 1 : 0);   // positions in class g
+  const int per = (T + bpg - 1) / bpg;
+  const int t0 = min(T, b * per);
+  const int t1 = min(T, t0 + per);
+  for (int base = t0; base < t1; base += GRAM_ROWS) {
+    const int nr = min(GRAM_ROWS, t1 - base);
     for (int o = tid; o < GRAM_ROWS * KP / 4; o += GRAM_THREADS) {
       const int rr = o / (KP / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rr < nr) v = reinterpret_cast<const float4*>(X + (size_t)__ldg(p2i + base + rr) * KP)[o % (KP / 4)];
+      if (rr < nr) {
+        const int t = base + rr;
+        const int pos = 16 * (t >> 1) + ((t & 1) ? 15 - g : g);     // increasing in t
+        v = reinterpret_cast<const float4*>(X + (size_t)__ldg(p2i + pos) * KP)[o % (KP / 4)];
+      }
       reinterpret_cast<float4*>(tile)[o] = v;
     }
     __syncthreads();
 #pragma unroll 4
     for (int rr = 0; rr < GRAM_ROWS; ++rr) {
-      double a[TM], b[TM];
+      double a[TM], bb[TM];
 #pragma unroll
       for (int i = 0; i < TM; ++i) {
         a[i] = (double)tile[rr * KP + ty * TM + i];
-        b[i] = (double)tile[rr * KP + tx * TM + i];
+        bb[i] = (double)tile[rr * KP + tx * TM + i];
       }
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TM; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TM; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
     }
     __syncthreads();
   }
-  double* out = partial + (size_t)blk * KP * KP;
+  double* out = partial + ((size_t)(slot0 + lg) * bpg + b) * KP * KP;
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < TM; ++j) out[(ty * TM + i) * KP + tx * TM + j] = acc[i][j];
 }
 
-// Two-level fixed-order reduction of the per-block partials: GRAM_GROUPS group sums (each over n_blocks / GRAM_GROUPS
-// consecutive blocks, in block order), then the sum of the group sums in group order.  The grouping does not depend on
-// the number of GPUs: a sharded run computes whole groups per rank, all-gathers the group sums (KP^2 doubles each) and
-// finishes with the same second level -- bit-identical to the single-GPU result.
-constexpr int GRAM_GROUPS = 8;
-
+// slot sums: the bpg block partials of a slot in block order
 __global__ void gram_group_kernel(const double* __restrict__ partial, int blocks_per_group, int n, int g0,
                                   double* __restrict__ gsum) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -729,12 +737,13 @@ __global__ void gram_group_kernel(const double* __restrict__ partial, int blocks
   gsum[(size_t)g * n + o] = s;
 }
 
-__global__ void gram_reduce_kernel(const double* __restrict__ gsum, int n, float* __restrict__ out) {
+// the class sums in class order
+__global__ void gram_reduce_kernel(const double* __restrict__ gsum, int n, float* __restrict__ out, const GramMap map) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n) return;
   double s = 0.0;
 #pragma unroll
-  for (int g = 0; g < GRAM_GROUPS; ++g) s += gsum[(size_t)g * n + o];
+  for (int g = 0; g < GRAM_GROUPS; ++g) s += gsum[(size_t)map.slot_of[g] * n + o];
   out[o] = (float)s;
 }
 

@@ -411,7 +411,9 @@ struct pio_als_handle {
   Side U, I;
   float* yty = nullptr;
   double* gram_partial = nullptr;
-  double* gram_gsum = nullptr;   // [GRAM_GROUPS][KP*KP] group sums of the YtY partials
+  double* gram_gsum = nullptr;   // [GRAM_GROUPS][KP*KP] class sums of the YtY partials (slot order, GramMap)
+  const Side* gram_side = nullptr;   // the side whose YtY currently sits in `yty` (nullptr: none / stale)
+  cudaEvent_t ev_gram = nullptr;
   int gram_blocks = 0;
   int* d_fail = nullptr;
   int* d_counts = nullptr;
@@ -1281,56 +1283,91 @@ static cudaError_t launch_solve(pio_als_handle* h, Side& dst, const Side& src) {
   }
 }
 
-// YtY of the (replicated) source factors: gram_blocks = GRAM_GROUPS x (SM count) position ranges, summed in fp64 per block,
-// then per group, then over the groups (fixed orders).  world_size > 1: every rank computes whole groups from its replica
-// and the group sums (KP^2 doubles each) are all-gathered in place -- bit-identical to the single-GPU result, and the
-// cost (0.77 ms per iteration on every rank at C2 in round 1) shrinks with the number of GPUs.
-static int launch_gram(pio_als_handle* h, const Side& src) {
-  const int nb = h->gram_blocks, W = h->cfg.world_size, n = h->KP * h->KP;
-  const int bpg = nb / GRAM_GROUPS;
-  const bool shard = W > 1 && GRAM_GROUPS % W == 0;
-  const int my_groups = shard ? GRAM_GROUPS / W : GRAM_GROUPS, g0 = shard ? h->cfg.world_rank * my_groups : 0;
-  const int mine = my_groups * bpg, b0 = g0 * bpg;
+// YtY (implicit feedback): als_kernels.cuh GramMap.  gram_sharded(): every rank owns whole classes (world size 2, 4, 8).
+static bool gram_sharded(const pio_als_handle* h) { return h->cfg.world_size > 1 && GRAM_GROUPS % h->cfg.world_size == 0; }
+static void gram_layout(const pio_als_handle* h, GramMap& m, int& my_groups, int& slot0) {
+  const bool shard = gram_sharded(h);
+  const int W = shard ? h->cfg.world_size : 1, me = shard ? h->cfg.world_rank : 0;
+  my_groups = GRAM_GROUPS / W;
+  slot0 = me * my_groups;
+  int seen[GRAM_GROUPS] = {}, mine = 0;
+  for (int g = 0; g < GRAM_GROUPS; ++g) {
+    const int blk = g / W, pos = g % W;
+    const int owner = (blk & 1) ? (W - 1 - pos) : pos;      // assign_internal_kernel's dealing, positions 0 .. 7
+    m.slot_of[g] = owner * my_groups + seen[owner]++;
+    if (owner == me) m.cls[mine++] = g;
+  }
+  for (int lg = mine; lg < GRAM_GROUPS; ++lg) m.cls[lg] = 0;
+}
+// phase A: block partials and slot sums of this rank's classes (sharded: from its own rows only)
+static int gram_local(pio_als_handle* h, const Side& s) {
+  GramMap m;
+  int my_groups, slot0;
+  gram_layout(h, m, my_groups, slot0);
+  const int bpg = h->gram_blocks / GRAM_GROUPS, n = h->KP * h->KP, grid = my_groups * bpg;
   switch (h->KP) {
-    case 16: gram_partial_kernel<16><<<mine, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial, b0, nb); break;
-    case 32: gram_partial_kernel<32><<<mine, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial, b0, nb); break;
-    case 64: gram_partial_kernel<64><<<mine, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial, b0, nb); break;
-    default: gram_partial_kernel<128><<<mine, GRAM_THREADS, 0, h->stream>>>(src.F, src.p2i, src.n, h->gram_partial, b0, nb); break;
+    case 16: gram_partial_kernel<16><<<grid, GRAM_THREADS, 0, h->stream>>>(s.F, s.p2i, s.n, h->gram_partial, slot0, bpg, m); break;
+    case 32: gram_partial_kernel<32><<<grid, GRAM_THREADS, 0, h->stream>>>(s.F, s.p2i, s.n, h->gram_partial, slot0, bpg, m); break;
+    case 64: gram_partial_kernel<64><<<grid, GRAM_THREADS, 0, h->stream>>>(s.F, s.p2i, s.n, h->gram_partial, slot0, bpg, m); break;
+    default: gram_partial_kernel<128><<<grid, GRAM_THREADS, 0, h->stream>>>(s.F, s.p2i, s.n, h->gram_partial, slot0, bpg, m); break;
   }
   LAUNCHED(h);
-  gram_group_kernel<<<dim3(nblk(n, 128), my_groups), 128, 0, h->stream>>>(h->gram_partial, bpg, n, g0, h->gram_gsum);
-  LAUNCHED(h);
-  if (shard) {
-    const size_t cnt = (size_t)my_groups * n;
-    if (nccl_api().AllGather(h->gram_gsum + (size_t)g0 * n, h->gram_gsum, cnt, ncclDouble, h->comm, h->stream) != ncclSuccess)
-      return fail(h, PIO_ALS_ERR_COMM, "ncclAllGather (YtY group sums) failed");
-  }
-  gram_reduce_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(h->gram_gsum, n, h->yty);
+  gram_group_kernel<<<dim3(nblk(n, 128), my_groups), 128, 0, h->stream>>>(h->gram_partial, bpg, n, slot0, h->gram_gsum);
   LAUNCHED(h);
   CK(h, cudaGetLastError());
   return PIO_ALS_OK;
 }
+// phase B: (sharded) all-gather of the slot sums on `comm_stream`, then the class sums in class order on the main stream
+static int gram_exchange(pio_als_handle* h, cudaStream_t comm_stream) {
+  if (!gram_sharded(h)) return PIO_ALS_OK;
+  const int n = h->KP * h->KP, my_groups = GRAM_GROUPS / h->cfg.world_size;
+  const size_t cnt = (size_t)my_groups * n;
+  if (nccl_api().AllGather(h->gram_gsum + (size_t)h->cfg.world_rank * cnt, h->gram_gsum, cnt, ncclDouble, h->comm, comm_stream) !=
+      ncclSuccess)
+    return fail(h, PIO_ALS_ERR_COMM, "ncclAllGather (YtY class sums) failed");
+  return PIO_ALS_OK;
+}
+static int gram_reduce(pio_als_handle* h, const Side& s) {
+  GramMap m;
+  int my_groups, slot0;
+  gram_layout(h, m, my_groups, slot0);
+  const int n = h->KP * h->KP;
+  gram_reduce_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(h->gram_gsum, n, h->yty, m);
+  LAUNCHED(h);
+  CK(h, cudaGetLastError());
+  h->gram_side = &s;
+  return PIO_ALS_OK;
+}
 
-static int half_step(pio_als_handle* h, Side& dst, const Side& src) {
+// One half-iteration: dst := argmin given src.  `more` = another half-step follows in this run: then YtY of the fresh dst
+// factors is prepared here -- on 2 / 4 / 8 GPUs from the rank's own rows while the last pieces of the factor all-gather
+// are still in flight, its 8 x KP^2 doubles exchanged on the communication stream right behind them.
+static int half_step(pio_als_handle* h, Side& dst, const Side& src, bool more) {
   cudaStream_t st = h->stream;
-  if (h->cfg.implicit_prefs) {
-    EvPair& e = next_ev(h, EV_GRAM);
+  const bool implicit = h->cfg.implicit_prefs != 0;
+  if (implicit && h->gram_side != &src) {     // first half-step of a run, or the factors were set from outside
+    const EvPair e = next_ev(h, EV_GRAM);
     cudaEventRecord(e.a, st);
-    const int grc = launch_gram(h, src);
+    int grc = gram_local(h, src);
+    if (!grc) grc = gram_exchange(h, st);
+    if (!grc) grc = gram_reduce(h, src);
     if (grc) return grc;
     cudaEventRecord(e.b, st);
   }
   {
-    EvPair& e = next_ev(h, &dst == &h->U ? EV_SOLVE_USER : EV_SOLVE);
+    const EvPair e = next_ev(h, &dst == &h->U ? EV_SOLVE_USER : EV_SOLVE);
     cudaEventRecord(e.a, st);
     h->pieces_done = false;
+    if (h->gram_side == &dst) h->gram_side = nullptr;
     CK(h, launch_solve(h, dst, src));
     cudaEventRecord(e.b, st);
   }
+  const bool prep = implicit && more;
+  bool gram_pending = false;      // class sums computed, exchange + reduce still to do
   if (h->cfg.world_size > 1) {
     NcclApi& nc = nccl_api();
     const int W = h->cfg.world_size, me = h->cfg.world_rank;
-    EvPair& e = next_ev(h, EV_COMM);
+    const EvPair e = next_ev(h, EV_COMM);
     if (h->pieces_done && h->n_pieces > 1) {
       // all-gather piece by piece on the communication stream: piece c = local rows [R c / C, R (c + 1) / C) of every
       // rank, exchanged as soon as its rows are solved (grouped send/recv: NVSwitch gives every pair full bandwidth)
@@ -1353,6 +1390,20 @@ static int half_step(pio_als_handle* h, Side& dst, const Side& src) {
         }
         if (nc.GroupEnd() != ncclSuccess) return fail(h, PIO_ALS_ERR_COMM, "ncclGroupEnd failed");
       }
+      if (prep && gram_sharded(h)) {
+        // the rank's own rows are final on the main stream once the heavy-row finish has joined it
+        if (dst.n_heavy > 0) cudaStreamWaitEvent(st, h->ev_heavy, 0);
+        const EvPair g = next_ev(h, EV_GRAM);
+        cudaEventRecord(g.a, st);
+        const int grc = gram_local(h, dst);
+        if (grc) return grc;
+        cudaEventRecord(g.b, st);
+        cudaEventRecord(h->ev_gram, st);
+        cudaStreamWaitEvent(sc, h->ev_gram, 0);
+        const int xrc = gram_exchange(h, sc);
+        if (xrc) return xrc;
+        gram_pending = true;
+      }
       cudaEventRecord(e.b, sc);
       cudaEventRecord(h->ev_comm, sc);
       cudaStreamWaitEvent(st, h->ev_comm, 0);
@@ -1364,6 +1415,18 @@ static int half_step(pio_als_handle* h, Side& dst, const Side& src) {
         return fail(h, PIO_ALS_ERR_COMM, "ncclAllGather failed: %s", nc.GetErrorString ? nc.GetErrorString(r) : "?");
       cudaEventRecord(e.b, st);
     }
+  }
+  if (prep) {
+    const EvPair e = next_ev(h, EV_GRAM);
+    cudaEventRecord(e.a, st);
+    int grc = PIO_ALS_OK;
+    if (!gram_pending) {
+      grc = gram_local(h, dst);
+      if (!grc) grc = gram_exchange(h, st);
+    }
+    if (!grc) grc = gram_reduce(h, dst);
+    if (grc) return grc;
+    cudaEventRecord(e.b, st);
   }
   return PIO_ALS_OK;
 }
@@ -1424,11 +1487,15 @@ static int create_common(pio_als_handle* h) {
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   h->KP = pad_rank(h->cfg.rank);
+  // the communication stream gets the highest priority: its few NCCL CTAs must not queue behind a grid that fills the
+  // SMs (the YtY class sums run on the main stream next to the last pieces of the factor exchange)
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->comm_st, cudaStreamNonBlocking) != cudaSuccess)
+      cudaStreamCreateWithPriority(&h->comm_st, cudaStreamNonBlocking, prio_hi) != cudaSuccess)
     return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaStreamCreate");
   {
-    cudaEvent_t* evs[4] = {&h->ev_start, &h->ev_heavy, &h->ev_comm, nullptr};
+    cudaEvent_t* evs[5] = {&h->ev_start, &h->ev_heavy, &h->ev_comm, &h->ev_gram, nullptr};
     for (int i = 0; evs[i]; ++i)
       if (cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming) != cudaSuccess) return fail(nullptr, PIO_ALS_ERR_CUDA, "cudaEventCreate");
     for (int i = 0; i < 8; ++i)
@@ -1527,6 +1594,7 @@ void pio_als_destroy(pio_als_handle* h) {
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_heavy) cudaEventDestroy(h->ev_heavy);
     if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+    if (h->ev_gram) cudaEventDestroy(h->ev_gram);
     for (int i = 0; i < 8; ++i)
       if (h->ev_piece[i]) cudaEventDestroy(h->ev_piece[i]);
     if (h->srv_dev) cudaFree(h->srv_dev);
@@ -1653,10 +1721,11 @@ int pio_als_run(pio_als_handle* h, int n_iters) {
   CK(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
   EvPair& tot = next_ev(h, -1);
   cudaEventRecord(tot.a, st);
+  h->gram_side = nullptr;      // the factors may have been replaced since the last run
   for (int it = 0; it < n_iters; ++it) {
-    int rc = half_step(h, h->I, h->U);  // item factors from user factors
+    int rc = half_step(h, h->I, h->U, true);                  // item factors from user factors
     if (rc) return rc;
-    rc = half_step(h, h->U, h->I);      // user factors from item factors
+    rc = half_step(h, h->U, h->I, it + 1 < n_iters);          // user factors from item factors
     if (rc) return rc;
   }
   cudaEventRecord(tot.b, st);
