@@ -1,12 +1,12 @@
 #!/bin/bash
 # 1 GPU: full test suite + full default bench after the scoring-kernel work
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/c42_pytest.log 2>&1
-tail -n 4 gpurun_out/c42_pytest.log
-timeout 1200 python bench.py > gpurun_out/c42_bench.json 2> gpurun_out/c42_bench.err
+timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/regress_pytest.log 2>&1
+tail -n 4 gpurun_out/regress_pytest.log
+timeout 1200 python bench.py > gpurun_out/regress_bench.json 2> gpurun_out/regress_bench.err
 python - <<'PY'
 import json
-d=json.loads(open("gpurun_out/c42_bench.json").read().strip().splitlines()[-1])
+d=json.loads(open("gpurun_out/regress_bench.json").read().strip().splitlines()[-1])
 r=d["roofline"]
 print(d["value"], d["ms_per_step"], "user", r["ms_per_launch"], "item", r["other_half_step"]["ms_per_launch"], "gram", r["gram_ms_per_iteration"], d["factor_checksum"], "e2e", d["e2e"]["value"], d["e2e"].get("ingest_ms"), "parity", d["parity"]["frob_rel"], d["parity"]["ok"], "cpu", d["cpu_baseline"]["value"], d["clocks"])
 t=d["topk"]
