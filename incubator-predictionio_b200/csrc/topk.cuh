@@ -136,6 +136,8 @@ __device__ __forceinline__ void wpool_find_worst(WarpPool& wp, int topk, const d
   wp.thr = ws;
   wp.wid = wi;
   wp.worst = wslot;
+  __syncwarp();   // the entries have been read by every lane before lane 0 overwrites one (the shuffles above already
+                  // converge the warp; this makes the ordering explicit for the memory model and for racecheck)
 }
 __device__ __forceinline__ void wpool_offer(WarpPool& wp, bool want, double s, int ext, int topk, double* ps, int* pi) {
   const int lane = threadIdx.x & 31;
@@ -417,6 +419,7 @@ __device__ __noinline__ void db_insert(DbPoolHdr* hd, double* ps, int* pi, unsig
   sp.offer(w0, s0, e0, topk);
   sp.offer(w1, s1, e1, topk);
   if (lane < sp.cnt) { ps[lane] = sp.s[0]; pi[lane] = sp.i[0]; }
+  __syncwarp();   // every lane has read the header before lane 0 rewrites it
   if (lane == 0) {
     hd->thr = sp.thr; hd->cnt = sp.cnt; hd->wid = sp.tid_;
     if (sp.cnt == topk) atomicMax(cthr, s1_key(sp.thr));   // the smallest entry of a FULL pool bounds the query's topk-th score
