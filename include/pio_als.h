@@ -162,7 +162,11 @@ PIO_API int pio_als_train(pio_als_handle* h, const int32_t* user, const int32_t*
                           float* user_out, float* item_out, uint8_t* user_has, uint8_t* item_has);
 
 /* Top-k scoring on a trained (or loaded / imported) handle; HOST buffers.  topk >= 1, any size (more than 128 results
- * per query are produced in several passes over the item matrix).
+ * per query are produced in several passes over the item matrix).  All paths return identical results; which kernels
+ * run is a matter of shape: ONE query (n == 1, or one similar query of <= 8 items; topk <= 128, rank <= 64) is a single
+ * fused launch whose result the call polls from mapped host memory (tens of microseconds: the Serving.serve path of a
+ * deployed engine, core/src/main/scala/org/apache/predictionio/workflow/CreateServer.scala:508-510); batches (rank <= 64,
+ * topk <= 32) run the blocked kernels; everything else the general ones.
  * recommend: for each users[q]: score_i = <x_u, y_i> (fp64, index order) over items that own a factor and have
  *   item_mask[i] == 0 (nullable = no filter), times item_weight[i] if item_weight != NULL (fp64; the ecommerce
  *   template's weightedItems, examples/scala-parallel-ecommercerecommendation/adjust-score/src/main/scala/
