@@ -1,15 +1,26 @@
 // topk.cuh -- top-k scoring over the item factor matrix (serving side of the hot path) and the
 // multinomial NaiveBayes reductions of the classification template.
 //
-//  score_dot_topk_kernel    : recommendProducts(WithFilter) -- <x_u, y_i> over all candidate items
-//      (examples/scala-parallel-recommendation/blacklist-items/src/main/scala/ALSModel.scala:44-60)
-//  score_cos_topk_kernel    : similarproduct predict -- sum_q cosine(y_q, y_i), score > 0 only
-//      (examples/scala-parallel-similarproduct/multi-events-multi-algos/src/main/scala/ALSAlgorithm.scala:160-187,220-234)
-//  topk_merge_kernel        : merges the per-tile winners (getTopN, :200-217)
+// What is scored (reference):
+//   dot     : recommendProducts(WithFilter) -- <x_u, y_i> over all candidate items
+//             (examples/scala-parallel-recommendation/blacklist-items/src/main/scala/ALSModel.scala:44-60)
+//   cosine  : similarproduct predict -- sum_q cosine(y_q, y_i), score > 0 only
+//             (examples/scala-parallel-similarproduct/multi-events-multi-algos/src/main/scala/ALSAlgorithm.scala:160-187,220-234)
+//   top-k   : getTopN (:200-217); ties by the smaller item index
+// Scores are accumulated in fp64 over the fp32 factors in index order, exactly like the reference's blas.ddot / cosine
+// loops over Array[Double], so scores and rankings are bit-identical to the oracle -- and the compute bound of every
+// kernel here is the fp64 pipe (one DFMA per query vector x item x feature), not HBM.
 //
-// Scores are accumulated in fp64 over the fp32 factors in index order, exactly like the reference's
-// blas.ddot / cosine loops over Array[Double], so scores and rankings are bit-identical to the oracle.
-// These are HBM-bound scans: every item row is read once per query batch tile.
+// Kernels, by call shape (pio_als.cu picks):
+//   score_one_kernel                 one query = one launch: lookup, scan, selection, result into mapped host memory
+//   score_dot_blocked_kernel         batches of users   (rank <= 64, topk <= 32): two items x eight queries per thread
+//   score_cos_blocked_kernel         batches of similar queries (same limits): bins of <= 4 queries / <= 8 vectors per warp
+//   score_dot_topk_batched_kernel    first-generation batch kernels (one item per thread): rank 128, topk > 32, and
+//   score_cos_topk_multi_kernel        2..16 users / long similar queries on the three-launch serving path
+//   score_cos_topk_kernel            fallback for very large single queries
+//   topk_merge_kernel                merges the per-CTA / per-warp candidate lists of a query; multi-pass bounds (topk > 128)
+// Pools: WarpPool (entries in shared memory, cooperative worst-entry search) and SortedPool (sorted in the registers of a
+// warp: ballot-counted position + shuffle shift).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
